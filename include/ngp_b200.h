@@ -1,0 +1,157 @@
+/* ngp_b200.h — C ABI of libngp_b200.so: the B200 (sm_100a) hot path of instant-ngp-pp.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream
+ * (`void* stream` = cudaStream_t, NULL = legacy default stream), launches asynchronously on that
+ * stream and returns 0 on success or a non-zero status (ngp_last_error() has the text).
+ * No torch types cross this boundary; nothing here allocates device memory; there is no CPU
+ * fallback.  All float tensors are fp32, contiguous, row-major unless a stride is given.
+ *
+ * Each function names the reference interface it replaces (file:line under the reference tree
+ * zhihao-lin/instant-ngp-pp).  `vren.X` = the pybind function registered at
+ * models/csrc/binding.cpp:323-342.
+ */
+#ifndef NGP_B200_H_
+#define NGP_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ library */
+int ngp_abi_version(void);
+const char* ngp_last_error(void);
+int ngp_check_device(void); /* 0 iff the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------ a1: intersections
+ * vren.ray_aabb_intersect  binding.cpp:4-16  -> intersection.cu:59-100
+ * hit_cnt (R) i32, hits_t (R,max_hits,2) f32 (-1 = empty), hits_voxel_idx (R,max_hits) i64 (-1). */
+int ngp_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* half_sizes,
+                           int64_t n_rays, int64_t n_voxels, int max_hits, int32_t* hit_cnt, float* hits_t,
+                           int64_t* hits_voxel_idx, void* stream);
+/* vren.ray_sphere_intersect  binding.cpp:19-31 -> intersection.cu:156-197 */
+int ngp_ray_sphere_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* radii,
+                             int64_t n_rays, int64_t n_spheres, int max_hits, int32_t* hit_cnt, float* hits_t,
+                             int64_t* hits_sphere_idx, void* stream);
+
+/* ------------------------------------------------------------------ a9: occupancy grid
+ * vren.morton3D          binding.cpp:46-50 -> raymarching.cu:72-88    coords (N,3) i32 -> (N) i32
+ * vren.morton3D_invert   binding.cpp:53-57 -> raymarching.cu:103-119
+ * vren.packbits          binding.cpp:35-43 -> raymarching.cu:143-161  dtype 0=f32 1=f16 2=f64 */
+int ngp_morton3D(const int32_t* coords, int64_t n, int32_t* indices, void* stream);
+int ngp_morton3D_invert(const int32_t* indices, int64_t n, int32_t* coords, void* stream);
+int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold,
+                 uint8_t* density_bitfield, void* stream);
+
+/* ------------------------------------------------------------------ a2: training ray marcher
+ * vren.raymarching_train  binding.cpp:60-81 -> raymarching.cu:283-332, split so the caller can
+ * size the outputs exactly (or not sync at all):
+ *   count : per-ray sample counts + scan; counter (2) i32 = [total_samples, n_rays]
+ *   write : rays_a (R,3) i64 [ray_idx,start_idx,N] in ray-index order, xyzs/dirs (S,3), deltas/ts (S)
+ * workspace: ngp_raymarching_train_workspace_bytes(n_rays) bytes of device memory shared by both. */
+int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays);
+int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                                const float* noise, int grid_size, int max_samples, int64_t n_rays, int32_t* counter,
+                                void* workspace, void* stream);
+int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const float* hits_t,
+                                const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                                int grid_size, int max_samples, int64_t n_rays, const void* workspace,
+                                int64_t capacity, int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                                void* stream);
+
+/* ------------------------------------------------------------------ a3: test-time marcher
+ * vren.raymarching_test  binding.cpp:84-106 -> raymarching.cu:407-454.  hits_t (R,2) advanced in
+ * place; outputs dense (n_alive, n_samples, .), unused slots zero; n_eff_samples (n_alive) i32. */
+int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                         const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                         int grid_size, int max_samples, int n_samples, int64_t n_alive, float* xyzs, float* dirs,
+                         float* deltas, float* ts, int32_t* n_eff_samples, void* stream);
+
+/* ------------------------------------------------------------------ a4: training compositor
+ * vren.composite_train_fw  binding.cpp:121-145 -> volumerendering.cu:118-164
+ * vren.composite_train_bw  binding.cpp:148-188 -> volumerendering.cu:249-311
+ * vren.composite_alpha_fw  binding.cpp:109-118 -> volumerendering.cu:37-63 */
+int ngp_composite_train_fw(const float* sigmas, const float* rgbs, const float* normals_pred, const float* sems,
+                           const float* deltas, const float* ts, const int64_t* rays_a, float T_threshold, int classes,
+                           int64_t n_samples, int64_t n_rays, int64_t* total_samples, float* opacity, float* depth,
+                           float* rgb, float* normal_pred, float* sem, float* ws, void* stream);
+int ngp_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb,
+                           const float* dL_dnormal_pred, const float* dL_dsem, const float* dL_dws, const float* sigmas,
+                           const float* rgbs, const float* ws, const float* deltas, const float* ts,
+                           const int64_t* rays_a, const float* opacity, const float* depth, const float* rgb,
+                           float T_threshold, int classes, int64_t n_samples, int64_t n_rays, float* dL_dsigmas,
+                           float* dL_drgbs, float* dL_dnormals_pred, float* dL_dsems, void* stream);
+int ngp_composite_alpha_fw(const float* sigmas, const float* deltas, const int64_t* rays_a, float T_threshold,
+                           int64_t n_samples, int64_t n_rays, float* alphas, float* ws, void* stream);
+
+/* ------------------------------------------------------------------ a5: test-time compositor
+ * vren.composite_test_fw  binding.cpp:242-284 -> volumerendering.cu:376-423 (in place) */
+int ngp_composite_test_fw(const float* sigmas, const float* rgbs, const float* normals, const float* normals_raw,
+                          const float* sems, const float* deltas, const float* ts, int64_t* alive_indices,
+                          float T_threshold, int classes, const int32_t* n_eff_samples, int n_samples, int64_t n_alive,
+                          float* opacity, float* depth, float* rgb, float* normal, float* normal_raw, float* sem,
+                          void* stream);
+
+/* ------------------------------------------------------------------ a6: Ref-NeRF normal losses
+ * vren.composite_refloss_fw  binding.cpp:191-208 -> ref_loss.cu:41-73
+ * vren.composite_refloss_bw  binding.cpp:211-239 -> ref_loss.cu:133-175 */
+int ngp_composite_refloss_fw(const float* sigmas, const float* normals_diff, const float* normals_ori,
+                             const float* deltas, const int64_t* rays_a, float T_threshold, int64_t n_samples,
+                             int64_t n_rays, float* loss_o, float* loss_p, void* stream);
+int ngp_composite_refloss_bw(const float* dL_dloss_o, const float* dL_dloss_p, const float* sigmas,
+                             const float* normals_diff, const float* normals_ori, const float* deltas,
+                             const int64_t* rays_a, const float* loss_o, const float* loss_p, float T_threshold,
+                             int64_t n_samples, int64_t n_rays, float* dL_dsigmas, float* dL_dnormals_diff,
+                             float* dL_dnormals_ori, void* stream);
+
+/* ------------------------------------------------------------------ a7: distortion loss
+ * vren.distortion_loss_fw  binding.cpp:287-298 -> losses.cu:62-107
+ * vren.distortion_loss_bw  binding.cpp:301-320 -> losses.cu:143-173 */
+int ngp_distortion_loss_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a,
+                           int64_t n_samples, int64_t n_rays, float* loss, float* ws_inclusive_scan,
+                           float* wts_inclusive_scan, void* stream);
+int ngp_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan,
+                           const float* ws, const float* deltas, const float* ts, const int64_t* rays_a,
+                           int64_t n_samples, int64_t n_rays, float* dL_dws, void* stream);
+
+/* ------------------------------------------------------------------ a10: hash-grid encoding
+ * tcnn.Encoding(3, {"otype":"Grid"|"HashGrid", ...})  models/networks.py:40-52, 67-76
+ * (tiny-cuda-nn is an un-vendored dependency of the reference; semantics per SURVEY.md App. B).
+ * table_dtype: 0 = f32, 1 = f16.  Gradients are always fp32. */
+int64_t ngp_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                            float per_level_scale, uint32_t* offsets /*L+1*/, uint32_t* sizes, uint32_t* resolutions,
+                            float* scales, uint8_t* dense);
+int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, int n_levels, int n_features,
+                    int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n, float* y,
+                    void* stream);
+int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_levels, int n_features, int log2_hashmap_size,
+                           int base_resolution, float per_level_scale, int64_t n, float* dtable, void* stream);
+int ngp_hashgrid_bw_input(const float* x, const float* dL_dy, const void* table, int table_dtype, int n_levels,
+                          int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
+                          float* dL_dx, void* stream);
+int ngp_hashgrid_bwbw_input(const float* x, const float* g2, const float* dL_dy, const void* table, int table_dtype,
+                            int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                            float per_level_scale, int64_t n, float* dtable, float* d_dL_dy, void* stream);
+
+/* ------------------------------------------------------------------ a11: SH direction encoding
+ * tcnn.Encoding(3, {"otype":"SphericalHarmonics","degree":4|3})  models/networks.py:78-85,128-135 */
+int ngp_sh_fw(const float* v, int degree, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------ a12: fused MLP (tcgen05/TMEM)
+ * tcnn.Network(n_in, n_out, {"otype":"CutlassMLP", ...})  models/networks.py:89-162
+ * Input = concatenation of up to 3 segments (kind 0: fp32 rows; kind 1: SH4 of normalised dirs).
+ * Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp. */
+int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_out);
+int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+               const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out, int act_hidden,
+               int act_out, int64_t n, float* out, int64_t out_stride, void* stream);
+int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+               const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out, int act_hidden,
+               int act_out, int64_t n, const float* dL_dout, int64_t dout_stride, float* dparams,
+               float* const* dseg_ptr, const int64_t* dseg_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H_ */

@@ -1,0 +1,98 @@
+// Shared device helpers for the ngp_b200 C-ABI kernels (sm_100a only).
+//
+// Arithmetic in this header follows the reference's per-ray scalar recurrences
+// (models/csrc/raymarching.cu:4-60) because per-ray sample counts / t / dt are a bit-exact
+// parity target.  Every floating-point step that the reference build contracts into an FMA
+// is spelt with an explicit __fmaf_rn here, and every step it does NOT contract uses
+// __fmul_rn/__fadd_rn, so the result does not depend on this file's optimisation flags
+// (see DESIGN.md "bit-exact marching" for the SASS evidence the sequence was read from).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#ifndef NGP_API
+#define NGP_API extern "C" __attribute__((visibility("default")))
+#endif
+
+namespace ngp {
+
+constexpr float kSqrt3 = 1.73205080757f;   // raymarching.cu:4
+constexpr int kSMs = 148;                  // B200
+
+int set_error(cudaError_t e, const char* where);   // api.cu
+int set_error_msg(const char* msg);
+
+#define NGP_LAUNCH_CHECK(where)                                   \
+  do {                                                            \
+    cudaError_t _e = cudaGetLastError();                          \
+    if (_e != cudaSuccess) return ngp::set_error(_e, where);      \
+  } while (0)
+
+__host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- morton (raymarching.cu:35-60)
+__host__ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) {
+  return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_invert(uint32_t x) {
+  x = x & 0x49249249u;
+  x = (x | (x >> 2)) & 0xc30c30c3u;
+  x = (x | (x >> 4)) & 0x0f00f00fu;
+  x = (x | (x >> 8)) & 0xff0000ffu;
+  x = (x | (x >> 16)) & 0x0000ffffu;
+  return x;
+}
+
+// ---------------------------------------------------------------- marching scalar helpers
+// Loop-invariant pieces of calc_dt (raymarching.cu:11-13):
+//   clamp(t*esf, SQRT3/max_samples, SQRT3*2*scale/grid_size), clamp(f,a,b)=fmaxf(a,fminf(f,b))
+struct DtParams {
+  float esf, dt_min, dt_max;
+};
+__host__ __device__ __forceinline__ DtParams make_dt_params(float esf, int max_samples, int grid_size,
+                                                            float scale_arg) {
+  DtParams p;
+  p.esf = esf;
+#ifdef __CUDA_ARCH__
+  p.dt_min = __fdiv_rn(kSqrt3, (float)max_samples);
+  p.dt_max = __fdiv_rn(__fmul_rn(kSqrt3 * 2, scale_arg), (float)grid_size);
+#else
+  p.dt_min = kSqrt3 / (float)max_samples;
+  p.dt_max = ((kSqrt3 * 2) * scale_arg) / (float)grid_size;
+#endif
+  return p;
+}
+__device__ __forceinline__ float calc_dt(float t, const DtParams& p) {
+  return fmaxf(p.dt_min, fminf(__fmul_rn(t, p.esf), p.dt_max));
+}
+// frexpf exponent of a finite float (0 -> 0), matching CUDA's frexpf incl. denormals.
+__device__ __forceinline__ int frexp_exponent(float v) {
+  int e;
+  frexpf(v, &e);
+  return e;
+}
+__device__ __forceinline__ int mip_from_pos(float x, float y, float z, int cascades) {
+  const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+  return min(cascades - 1, max(0, frexp_exponent(mx) + 1));
+}
+__device__ __forceinline__ int mip_from_dt(float dt, int grid_size, int cascades) {
+  return min(cascades - 1, max(0, frexp_exponent(__fmul_rn(dt, (float)grid_size))));
+}
+
+// ---------------------------------------------------------------- warp utilities
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ngp

@@ -1,0 +1,393 @@
+// Multiresolution hash-grid encoding: forward, parameter gradient (atomic scatter), input gradient
+// and the double-backward of the input gradient.
+//
+// Semantics follow tiny-cuda-nn's GridEncoding (type Hash, interpolation Linear) as the reference
+// uses it (models/networks.py:40-52, 67-76).  tiny-cuda-nn is NOT part of
+// /root/reference, so this half of the path is written from its published algorithm:
+//   scale_l = exp2(l*log2(per_level_scale))*base_resolution - 1 ; res_l = ceil(scale_l)+1
+//   n_l     = min(next_multiple(res_l^3, 8), 2^log2_T)      (dense while res_l^3 <= n_l)
+//   pos     = fma(scale_l, x, 0.5) ; cell = floor(pos) ; w = pos - cell
+//   index   = dense ? x + y*res + z*res^2 : x ^ y*2654435761 ^ z*805459861        (mod n_l)
+//   y[l*F+f]= sum_corners prod_d (c_d ? w_d : 1-w_d) * table[offset_l + index][f]
+//
+// B200 mapping: one thread owns (sample, chunk of LC consecutive levels) with LC*F >= 8 floats, so
+// the thread issues 8*LC independent vector gathers (ld.global.nc.v2/v4) before it needs any of
+// them, and writes one full 32-byte sector of the (N, L*F) output.  blockIdx.y walks level chunks,
+// so at any instant a CTA's gathers hit one or two levels (coarse levels stay L1/L2 resident; the
+// 43 MB fp32 table of the L16/F2/T2^19 shape fits the 126 MB L2 outright).  Gradients are
+// scattered with vector reductions (red.global.add.v2/v4.f32).
+#include "common.cuh"
+
+namespace ngp {
+
+constexpr int kMaxLevels = 32;
+
+struct GridMeta {
+  int n_levels;
+  int n_features;          // F
+  uint32_t offset[kMaxLevels + 1];  // in entries (each entry = F params)
+  uint32_t size[kMaxLevels];        // entries in level (hashmap size)
+  uint32_t res[kMaxLevels];
+  float scale[kMaxLevels];
+  uint8_t dense[kMaxLevels];
+};
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size,
+                                               bool dense) {
+  if (dense) {
+    uint32_t i = x + y * res + z * res * res;
+    if (i >= size) i -= size;  // == i % size for the reachable range (x,y,z <= res)
+    return i;
+  }
+  const uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
+  return (size & (size - 1)) == 0 ? (h & (size - 1)) : (h % size);
+}
+
+template <int F, typename TP> struct Vec;
+template <> struct Vec<1, float> { static __device__ __forceinline__ void ld(const float* p, float* o) { o[0] = __ldg(p); } };
+template <> struct Vec<2, float> { static __device__ __forceinline__ void ld(const float* p, float* o) { const float2 v = __ldg((const float2*)p); o[0] = v.x; o[1] = v.y; } };
+template <> struct Vec<4, float> { static __device__ __forceinline__ void ld(const float* p, float* o) { const float4 v = __ldg((const float4*)p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; } };
+template <> struct Vec<8, float> { static __device__ __forceinline__ void ld(const float* p, float* o) {
+  const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; } };
+template <> struct Vec<1, __half> { static __device__ __forceinline__ void ld(const __half* p, float* o) { o[0] = __half2float(__ldg(p)); } };
+template <> struct Vec<2, __half> { static __device__ __forceinline__ void ld(const __half* p, float* o) { const float2 v = __half22float2(__ldg((const __half2*)p)); o[0] = v.x; o[1] = v.y; } };
+template <> struct Vec<4, __half> { static __device__ __forceinline__ void ld(const __half* p, float* o) {
+  const uint2 r = __ldg((const uint2*)p);
+  const float2 a = __half22float2(*(const __half2*)&r.x), b = __half22float2(*(const __half2*)&r.y);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; } };
+template <> struct Vec<8, __half> { static __device__ __forceinline__ void ld(const __half* p, float* o) {
+  const uint4 r = __ldg((const uint4*)p);
+  const float2 a = __half22float2(*(const __half2*)&r.x), b = __half22float2(*(const __half2*)&r.y);
+  const float2 c = __half22float2(*(const __half2*)&r.z), d = __half22float2(*(const __half2*)&r.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y; } };
+
+template <int F> __device__ __forceinline__ void red_add(float* p, const float* v) {
+  if constexpr (F == 1) atomicAdd(p, v[0]);
+  else if constexpr (F == 2) atomicAdd((float2*)p, make_float2(v[0], v[1]));
+  else if constexpr (F == 4) atomicAdd((float4*)p, make_float4(v[0], v[1], v[2], v[3]));
+  else { atomicAdd((float4*)p, make_float4(v[0], v[1], v[2], v[3])); atomicAdd((float4*)p + 1, make_float4(v[4], v[5], v[6], v[7])); }
+}
+
+struct Cell { uint32_t px, py, pz; float wx, wy, wz; };
+__device__ __forceinline__ Cell locate(float x, float y, float z, float scale) {
+  Cell c;
+  float fx = fmaf(scale, x, 0.5f), fy = fmaf(scale, y, 0.5f), fz = fmaf(scale, z, 0.5f);
+  const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+  c.px = (uint32_t)(int)gx; c.py = (uint32_t)(int)gy; c.pz = (uint32_t)(int)gz;
+  c.wx = fx - gx; c.wy = fy - gy; c.wz = fz - gz;
+  return c;
+}
+
+template <int F> constexpr int levels_per_thread() { return F >= 8 ? 1 : 8 / F; }
+
+// ----------------------------------------------------------------------------------- forward
+template <int F, typename TP>
+__global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
+                                                          GridMeta m, int64_t n, float* __restrict__ y) {
+  constexpr int LC = levels_per_thread<F>();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l0 = blockIdx.y * LC;
+  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  float out[LC * F];
+#pragma unroll
+  for (int k = 0; k < LC * F; k++) out[k] = 0.f;
+#pragma unroll
+  for (int li = 0; li < LC; li++) {
+    const int l = l0 + li;
+    if (l < m.n_levels) {
+      const Cell c = locate(xx, xy, xz, m.scale[l]);
+      const TP* base = table + (size_t)m.offset[l] * F;
+      const uint32_t res = m.res[l], size = m.size[l];
+      const bool dense = m.dense[l];
+      float v[8][F];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
+        Vec<F, TP>::ld(base + (size_t)idx * F, v[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+#pragma unroll
+        for (int f = 0; f < F; f++) out[li * F + f] = fmaf(w, v[k][f], out[li * F + f]);
+      }
+    }
+  }
+  const int LF = m.n_levels * F;
+  float* dst = y + i * LF + (int64_t)l0 * F;
+  if (l0 + LC <= m.n_levels && (LF % 4) == 0 && ((l0 * F) % 4) == 0) {
+#pragma unroll
+    for (int k = 0; k < LC * F; k += 4) *(float4*)(dst + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < LC * F; k++) if (l0 * F + k < LF) dst[k] = out[k];
+  }
+}
+
+// ----------------------------------------------------------------------------------- bw (params)
+// dL/dtable[corner] += w_corner * dL/dy  (fp32 accumulation regardless of the table's storage type)
+template <int F>
+__global__ void __launch_bounds__(256) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 GridMeta m, int64_t n, float* __restrict__ dtable) {
+  constexpr int LC = levels_per_thread<F>();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l0 = blockIdx.y * LC;
+  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  const int LF = m.n_levels * F;
+  const float* src = dy + i * LF + (int64_t)l0 * F;
+  float g[LC * F];
+#pragma unroll
+  for (int k = 0; k < LC * F; k++) g[k] = (l0 * F + k < LF) ? __ldg(src + k) : 0.f;
+#pragma unroll
+  for (int li = 0; li < LC; li++) {
+    const int l = l0 + li;
+    if (l < m.n_levels) {
+      bool any = false;
+#pragma unroll
+      for (int f = 0; f < F; f++) any |= g[li * F + f] != 0.f;
+      if (!any) continue;  // samples past early termination carry exactly-zero gradients
+      const Cell c = locate(xx, xy, xz, m.scale[l]);
+      float* base = dtable + (size_t)m.offset[l] * F;
+      const uint32_t res = m.res[l], size = m.size[l];
+      const bool dense = m.dense[l];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+        const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
+        float v[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) v[f] = w * g[li * F + f];
+        red_add<F>(base + (size_t)idx * F, v);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- bw (input)
+// dL/dx_d = sum_l scale_l * sum_f dL/dy_{l,f} * sum_{corners of the other two dims} w_other * (v[d=1]-v[d=0])
+template <int F, typename TP>
+__global__ void __launch_bounds__(256) hashgrid_bw_input_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                const TP* __restrict__ table, GridMeta m, int64_t n,
+                                                                float* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  const int LF = m.n_levels * F;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int l = 0; l < m.n_levels; l++) {
+    const Cell c = locate(xx, xy, xz, m.scale[l]);
+    const TP* base = table + (size_t)m.offset[l] * F;
+    const uint32_t res = m.res[l], size = m.size[l];
+    const bool dense = m.dense[l];
+    float g[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) g[f] = __ldg(dy + i * LF + l * F + f);
+    float d[8];  // d[k] = sum_f g_f * v[k][f]
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
+      float v[F];
+      Vec<F, TP>::ld(base + (size_t)idx * F, v);
+      float a = 0.f;
+#pragma unroll
+      for (int f = 0; f < F; f++) a = fmaf(g[f], v[f], a);
+      d[k] = a;
+    }
+    const float ax = 1.f - c.wx, ay = 1.f - c.wy, az = 1.f - c.wz;
+    const float s = m.scale[l];
+    // k bit0 = x, bit1 = y, bit2 = z
+    gx += s * (ay * az * (d[1] - d[0]) + c.wy * az * (d[3] - d[2]) + ay * c.wz * (d[5] - d[4]) + c.wy * c.wz * (d[7] - d[6]));
+    gy += s * (ax * az * (d[2] - d[0]) + c.wx * az * (d[3] - d[1]) + ax * c.wz * (d[6] - d[4]) + c.wx * c.wz * (d[7] - d[5]));
+    gz += s * (ax * ay * (d[4] - d[0]) + c.wx * ay * (d[5] - d[1]) + ax * c.wy * (d[6] - d[2]) + c.wx * c.wy * (d[7] - d[3]));
+  }
+  dx[3 * i] = gx; dx[3 * i + 1] = gy; dx[3 * i + 2] = gz;
+}
+
+// ----------------------------------------------------------------------------------- double bw
+// Given g2 = dL/d(dL/dx) (N,3) and the first-order upstream gy = dL/dy (N, L*F):
+//   dL/dtable[corner c] += gy * scale * sum_d g2_d * sign_d(c) * prod_{d' != d} w_{d'}(c)
+//   dL/d(gy)_{l,f}       = sum_d g2_d * dy_{l,f}/dx_d
+// (second derivatives of the trilinear kernel w.r.t. x itself are not propagated: x is a leaf
+// produced by the marcher under no_grad in the reference, models/rendering.py:207-212).
+template <int F, typename TP>
+__global__ void __launch_bounds__(256) hashgrid_bwbw_kernel(const float* __restrict__ x, const float* __restrict__ g2,
+                                                            const float* __restrict__ gy_in, const TP* __restrict__ table,
+                                                            GridMeta m, int64_t n, float* __restrict__ dtable,
+                                                            float* __restrict__ dgy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = blockIdx.y;
+  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  const float hx = __ldg(g2 + 3 * i), hy = __ldg(g2 + 3 * i + 1), hz = __ldg(g2 + 3 * i + 2);
+  const int LF = m.n_levels * F;
+  const Cell c = locate(xx, xy, xz, m.scale[l]);
+  const uint32_t res = m.res[l], size = m.size[l];
+  const bool dense = m.dense[l];
+  const float s = m.scale[l];
+  float g[F];
+#pragma unroll
+  for (int f = 0; f < F; f++) g[f] = gy_in ? __ldg(gy_in + i * LF + l * F + f) : 0.f;
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; f++) acc[f] = 0.f;
+  const bool zero_h = (hx == 0.f && hy == 0.f && hz == 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
+    const float wx = bx ? c.wx : 1.f - c.wx, wy = by ? c.wy : 1.f - c.wy, wz = bz ? c.wz : 1.f - c.wz;
+    // coefficient of v[k] in sum_d g2_d * dy/dx_d
+    const float coef = s * (hx * (bx ? 1.f : -1.f) * wy * wz + hy * (by ? 1.f : -1.f) * wx * wz + hz * (bz ? 1.f : -1.f) * wx * wy);
+    const uint32_t idx = grid_index(c.px + bx, c.py + by, c.pz + bz, res, size, dense);
+    if (dgy) {
+      float v[F];
+      Vec<F, TP>::ld(table + ((size_t)m.offset[l] + idx) * F, v);
+#pragma unroll
+      for (int f = 0; f < F; f++) acc[f] = fmaf(coef, v[f], acc[f]);
+    }
+    if (dtable && !zero_h) {
+      float v[F];
+#pragma unroll
+      for (int f = 0; f < F; f++) v[f] = coef * g[f];
+      red_add<F>(dtable + ((size_t)m.offset[l] + idx) * F, v);
+    }
+  }
+  if (dgy) {
+#pragma unroll
+    for (int f = 0; f < F; f++) dgy[i * LF + l * F + f] = acc[f];
+  }
+}
+
+static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res, float per_level_scale) {
+  if (n_levels < 1 || n_levels > kMaxLevels) return -1;
+  if (!(F == 1 || F == 2 || F == 4 || F == 8)) return -1;
+  m.n_levels = n_levels; m.n_features = F;
+  const float log2_pls = log2f(per_level_scale);
+  uint32_t off = 0;
+  for (int l = 0; l < n_levels; l++) {
+    const float scale = exp2f(l * log2_pls) * base_res - 1.0f;   // tcnn grid_scale
+    const uint32_t res = (uint32_t)ceilf(scale) + 1;             // tcnn grid_resolution
+    const uint64_t dense_n = (uint64_t)res * res * res;
+    const uint64_t cap = 1ull << log2_T;
+    uint64_t sz = (dense_n + 7) / 8 * 8;
+    if (sz > cap) sz = cap;
+    m.offset[l] = off; m.size[l] = (uint32_t)sz; m.res[l] = res; m.scale[l] = scale;
+    m.dense[l] = dense_n <= sz ? 1 : 0;
+    off += (uint32_t)sz;
+  }
+  m.offset[n_levels] = off;
+  return 0;
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+// Level table of a tcnn-shaped grid.  Fills offsets (L+1, in entries), sizes, resolutions, scales,
+// dense flags (each L) and returns the total number of parameters (entries*F), or -1 on bad config.
+// Replaces the constructor-side bookkeeping of tcnn.Encoding({"otype":"Grid"/"HashGrid"}) used at
+// models/networks.py:40-52,67-76.
+NGP_API int64_t ngp_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                                    float per_level_scale, uint32_t* offsets, uint32_t* sizes, uint32_t* resolutions,
+                                    float* scales, uint8_t* dense) {
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale)) {
+    set_error_msg("ngp_hashgrid_layout: need 1<=n_levels<=32 and n_features in {1,2,4,8}");
+    return -1;
+  }
+  for (int l = 0; l < n_levels; l++) {
+    if (offsets) offsets[l] = m.offset[l];
+    if (sizes) sizes[l] = m.size[l];
+    if (resolutions) resolutions[l] = m.res[l];
+    if (scales) scales[l] = m.scale[l];
+    if (dense) dense[l] = m.dense[l];
+  }
+  if (offsets) offsets[n_levels] = m.offset[n_levels];
+  return (int64_t)m.offset[n_levels] * n_features;
+}
+
+#define NGP_F_DISPATCH(F_, ...)                                 \
+  switch (F_) {                                                 \
+    case 1: { constexpr int F = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int F = 2; __VA_ARGS__; } break;        \
+    case 4: { constexpr int F = 4; __VA_ARGS__; } break;        \
+    default: { constexpr int F = 8; __VA_ARGS__; } break;       \
+  }
+
+// y (N, L*F) f32 = encode(x (N,3) f32 in [0,1]).  table_dtype: 0 = f32, 1 = f16.
+// Replaces tcnn.Encoding.forward for the Grid encoding (called from models/networks.py:177,182).
+NGP_API int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, int n_levels, int n_features,
+                            int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n, float* y,
+                            void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+    return set_error_msg("ngp_hashgrid_fw: bad grid config");
+  cudaStream_t st = (cudaStream_t)stream;
+  NGP_F_DISPATCH(n_features, {
+    constexpr int LC = levels_per_thread<F>();
+    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n_levels, LC));
+    if (table_dtype == 0) hashgrid_fw_kernel<F, float><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
+    else hashgrid_fw_kernel<F, __half><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_fw");
+  return 0;
+}
+
+// dtable (n_params) f32 += scatter(dL/dy).  The caller zeroes dtable (or accumulates on purpose).
+NGP_API int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_levels, int n_features,
+                                   int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
+                                   float* dtable, void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+    return set_error_msg("ngp_hashgrid_bw_params: bad grid config");
+  NGP_F_DISPATCH(n_features, {
+    constexpr int LC = levels_per_thread<F>();
+    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n_levels, LC));
+    hashgrid_bw_params_kernel<F><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
+  return 0;
+}
+
+// dx (N,3) f32 = (dy/dx)^T dL/dy
+NGP_API int ngp_hashgrid_bw_input(const float* x, const float* dL_dy, const void* table, int table_dtype, int n_levels,
+                                  int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                                  int64_t n, float* dL_dx, void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+    return set_error_msg("ngp_hashgrid_bw_input: bad grid config");
+  cudaStream_t st = (cudaStream_t)stream;
+  NGP_F_DISPATCH(n_features, {
+    const unsigned grid = (unsigned)ceil_div(n, 256);
+    if (table_dtype == 0) hashgrid_bw_input_kernel<F, float><<<grid, 256, 0, st>>>(x, dL_dy, (const float*)table, m, n, dL_dx);
+    else hashgrid_bw_input_kernel<F, __half><<<grid, 256, 0, st>>>(x, dL_dy, (const __half*)table, m, n, dL_dx);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_input");
+  return 0;
+}
+
+// Double backward of ngp_hashgrid_bw_input: g2 = dL/d(dL_dx) (N,3).
+//   dtable += d(g2 . dL_dx)/dtable   (skipped when dtable == NULL)
+//   d_dL_dy = d(g2 . dL_dx)/d(dL_dy) (skipped when d_dL_dy == NULL; dL_dy may then be NULL too)
+NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* g2, const float* dL_dy, const void* table,
+                                    int table_dtype, int n_levels, int n_features, int log2_hashmap_size,
+                                    int base_resolution, float per_level_scale, int64_t n, float* dtable,
+                                    float* d_dL_dy, void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+    return set_error_msg("ngp_hashgrid_bwbw_input: bad grid config");
+  cudaStream_t st = (cudaStream_t)stream;
+  NGP_F_DISPATCH(n_features, {
+    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)n_levels);
+    if (table_dtype == 0) hashgrid_bwbw_kernel<F, float><<<grid, 256, 0, st>>>(x, g2, dL_dy, (const float*)table, m, n, dtable, d_dL_dy);
+    else hashgrid_bwbw_kernel<F, __half><<<grid, 256, 0, st>>>(x, g2, dL_dy, (const __half*)table, m, n, dtable, d_dL_dy);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bwbw_input");
+  return 0;
+}

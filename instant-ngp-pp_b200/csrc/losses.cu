@@ -1,0 +1,222 @@
+// Per-ray losses over packed samples: mip-NeRF-360 distortion loss (DVGO-v2 prefix-sum form) and
+// the Ref-NeRF orientation / prediction normal losses.
+// Replaces reference models/csrc/losses.cu:7-173 (distortion_loss_fw_cu / _bw_cu) and
+// models/csrc/ref_loss.cu:4-175 (composite_refloss_fw_cu / _bw_cu).
+//
+// Reference distortion fw: ws*ts temp + 4 device-side *sequential* thrust scans per ray into 4
+// (S) temporaries + a torch elementwise expression + a per-ray sequential reduce (7 passes over S).
+// Here: one kernel; a G-lane group scans ws and ws*ts in registers, emits the two inclusive scans
+// the backward needs, and reduces the loss — one read of (ws, ts, deltas), two writes per sample.
+#include "scan.cuh"
+
+namespace ngp {
+
+int pick_group(int64_t n_samples, int64_t n_rays);  // composite.cu
+
+template <int G>
+__global__ void __launch_bounds__(256) distortion_fw_kernel(
+    const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
+    const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ loss, float* __restrict__ ws_incl,
+    float* __restrict__ wts_incl) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int j = (int)(gtid % G);
+  const Seg sg = load_seg(rays_a, row, n_rays);
+  float cw = 0.f, cwt = 0.f, acc = 0.f;
+  for (int base = 0; warp_any(base < sg.n); base += G) {
+    const bool valid = base + j < sg.n;
+    const int64_t s = sg.start + base + j;
+    float w = 0.f, t = 0.f, dl = 0.f;
+    if (valid) { w = __ldg(ws + s); t = __ldg(ts + s); dl = __ldg(deltas + s); }
+    const float wt = w * t;
+    const float iw = cw + group_incl_sum<G>(w, j);
+    const float iwt = cwt + group_incl_sum<G>(wt, j);
+    float ew = __shfl_up_sync(kFull, iw, 1, G), ewt = __shfl_up_sync(kFull, iwt, 1, G);
+    if (j == 0) { ew = cw; ewt = cwt; }
+    cw = group_bcast<G>(iw, G - 1); cwt = group_bcast<G>(iwt, G - 1);
+    if (valid) {
+      ws_incl[s] = iw; wts_incl[s] = iwt;
+      // losses.cu:92-93: 2*(wts_incl*ws_excl - ws_incl*wts_excl) + 1.0f/3*ws*ws*deltas
+      acc += 2.0f * (iwt * ew - iw * ewt) + (1.0f / 3) * w * w * dl;
+    }
+  }
+  acc = group_sum<G>(acc);
+  if (j == 0 && sg.ray >= 0) loss[sg.ray] = acc;
+}
+
+// losses.cu:110-140
+template <int G>
+__global__ void __launch_bounds__(256) distortion_bw_kernel(
+    const float* __restrict__ dL_dloss, const float* __restrict__ ws_incl, const float* __restrict__ wts_incl,
+    const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
+    const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ dL_dws) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int j = (int)(gtid % G);
+  const Seg sg = load_seg(rays_a, row, n_rays);
+  if (sg.n <= 0) return;
+  const int64_t end = sg.start + sg.n - 1;
+  const float ws_sum = __ldg(ws_incl + end), wts_sum = __ldg(wts_incl + end);
+  const float g = __ldg(dL_dloss + sg.ray);
+  const float g23 = g * 2.0f / 3;  // losses.cu:138 parses as ((dL_dloss*2)/3)*ws*deltas
+  for (int k = j; k < sg.n; k += G) {
+    const int64_t s = sg.start + k;
+    const float t = __ldg(ts + s), iw = __ldg(ws_incl + s), iwt = __ldg(wts_incl + s);
+    const float before = k == 0 ? 0.f : (t * __ldg(ws_incl + s - 1) - __ldg(wts_incl + s - 1));
+    float v = g * 2 * (before + (wts_sum - iwt - t * (ws_sum - iw)));
+    v += g23 * __ldg(ws + s) * __ldg(deltas + s);
+    dL_dws[s] = v;
+  }
+}
+
+// ref_loss.cu:4-38
+template <int G>
+__global__ void __launch_bounds__(256) refloss_fw_kernel(
+    const float* __restrict__ sigmas, const float* __restrict__ ndiff, const float* __restrict__ nori,
+    const float* __restrict__ deltas, const int64_t* __restrict__ rays_a, float T_thr, int64_t n_rays,
+    float* __restrict__ loss_o, float* __restrict__ loss_p) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int j = (int)(gtid % G);
+  const Seg sg = load_seg(rays_a, row, n_rays);
+  float ax = 0.f, ay = 0.f, az = 0.f, ao = 0.f;
+  TState st;
+  for (int base = 0; warp_any(base < sg.n); base += G) {
+    const bool valid = base + j < sg.n;
+    const int64_t s = sg.start + base + j;
+    float a = 0.f;
+    if (valid) a = sample_alpha(__ldg(sigmas + s), __ldg(deltas + s));
+    float Tb, Ta; bool active;
+    chunk_transmittance<G>(st, a, valid, j, base, T_thr, Tb, Ta, active);
+    if (active) {
+      const float w = a * Tb;
+      ax = fmaf(w, __ldg(ndiff + 3 * s), ax); ay = fmaf(w, __ldg(ndiff + 3 * s + 1), ay); az = fmaf(w, __ldg(ndiff + 3 * s + 2), az);
+      ao = fmaf(w, __ldg(nori + s), ao);
+    }
+  }
+  ax = group_sum<G>(ax); ay = group_sum<G>(ay); az = group_sum<G>(az); ao = group_sum<G>(ao);
+  if (j == 0 && sg.ray >= 0) {
+    loss_o[sg.ray] = ao;
+    loss_p[3 * sg.ray] = ax; loss_p[3 * sg.ray + 1] = ay; loss_p[3 * sg.ray + 2] = az;
+  }
+}
+
+// ref_loss.cu:76-130
+template <int G>
+__global__ void __launch_bounds__(256) refloss_bw_kernel(
+    const float* __restrict__ dL_dloss_o, const float* __restrict__ dL_dloss_p, const float* __restrict__ sigmas,
+    const float* __restrict__ ndiff, const float* __restrict__ nori, const float* __restrict__ deltas,
+    const int64_t* __restrict__ rays_a, const float* __restrict__ loss_o, const float* __restrict__ loss_p,
+    float T_thr, int64_t n_rays, float* __restrict__ dL_dsigmas, float* __restrict__ dL_dndiff,
+    float* __restrict__ dL_dnori) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gtid / G;
+  const int j = (int)(gtid % G);
+  const Seg sg = load_seg(rays_a, row, n_rays);
+  const int64_t r = sg.ray < 0 ? 0 : sg.ray;
+  float gO = 0.f, gX = 0.f, gY = 0.f, gZ = 0.f, O = 0.f, X = 0.f, Y = 0.f, Z = 0.f;
+  if (sg.n > 0) {
+    gO = __ldg(dL_dloss_o + r);
+    gX = __ldg(dL_dloss_p + 3 * r); gY = __ldg(dL_dloss_p + 3 * r + 1); gZ = __ldg(dL_dloss_p + 3 * r + 2);
+    O = __ldg(loss_o + r);
+    X = __ldg(loss_p + 3 * r); Y = __ldg(loss_p + 3 * r + 1); Z = __ldg(loss_p + 3 * r + 2);
+  }
+  TState st;
+  float cx = 0.f, cy = 0.f, cz = 0.f, co = 0.f;
+  for (int base = 0; warp_any(base < sg.n); base += G) {
+    const bool valid = base + j < sg.n;
+    const int64_t s = sg.start + base + j;
+    float a = 0.f, dl = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, no = 0.f;
+    if (valid) {
+      dl = __ldg(deltas + s);
+      a = sample_alpha(__ldg(sigmas + s), dl);
+      d0 = __ldg(ndiff + 3 * s); d1 = __ldg(ndiff + 3 * s + 1); d2 = __ldg(ndiff + 3 * s + 2);
+      no = __ldg(nori + s);
+    }
+    float Tb, Ta; bool active;
+    chunk_transmittance<G>(st, a, valid, j, base, T_thr, Tb, Ta, active);
+    const float w = active ? a * Tb : 0.f;
+    const float px = cx + group_incl_sum<G>(w * d0, j);
+    const float py = cy + group_incl_sum<G>(w * d1, j);
+    const float pz = cz + group_incl_sum<G>(w * d2, j);
+    const float po = co + group_incl_sum<G>(w * no, j);
+    cx = group_bcast<G>(px, G - 1); cy = group_bcast<G>(py, G - 1); cz = group_bcast<G>(pz, G - 1);
+    co = group_bcast<G>(po, G - 1);
+    if (valid) {
+      dL_dndiff[3 * s] = gX * w; dL_dndiff[3 * s + 1] = gY * w; dL_dndiff[3 * s + 2] = gZ * w;
+      dL_dnori[s] = gO * w;
+      dL_dsigmas[s] = active ? dl * (gX * (d0 * Ta - (X - px)) + gY * (d1 * Ta - (Y - py)) +
+                                     gZ * (d2 * Ta - (Z - pz)) + gO * (no * Ta - (O - po)))
+                             : 0.f;
+    }
+  }
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+#define NGP_GROUP_DISPATCH(G_, ...)                                  \
+  switch (G_) {                                                      \
+    case 32: { constexpr int G = 32; __VA_ARGS__; } break;           \
+    case 16: { constexpr int G = 16; __VA_ARGS__; } break;           \
+    case 8:  { constexpr int G = 8;  __VA_ARGS__; } break;           \
+    default: { constexpr int G = 4;  __VA_ARGS__; } break;           \
+  }
+
+// Replaces vren.distortion_loss_fw (binding.cpp:287-298 -> losses.cu:62-107).
+NGP_API int ngp_distortion_loss_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a,
+                                   int64_t n_samples, int64_t n_rays, float* loss, float* ws_inclusive_scan,
+                                   float* wts_inclusive_scan, void* stream) {
+  if (n_rays <= 0) return 0;
+  NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
+    distortion_fw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+        ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan);
+  });
+  NGP_LAUNCH_CHECK("ngp_distortion_loss_fw");
+  return 0;
+}
+
+// Replaces vren.distortion_loss_bw (binding.cpp:301-320 -> losses.cu:143-173).
+NGP_API int ngp_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan,
+                                   const float* wts_inclusive_scan, const float* ws, const float* deltas,
+                                   const float* ts, const int64_t* rays_a, int64_t n_samples, int64_t n_rays,
+                                   float* dL_dws, void* stream) {
+  if (n_rays <= 0) return 0;
+  NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
+    distortion_bw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+        dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts, rays_a, n_rays, dL_dws);
+  });
+  NGP_LAUNCH_CHECK("ngp_distortion_loss_bw");
+  return 0;
+}
+
+// Replaces vren.composite_refloss_fw (binding.cpp:191-208 -> ref_loss.cu:41-73).  `ts` of the
+// reference signature is unused by its kernel and not part of this entry point.
+NGP_API int ngp_composite_refloss_fw(const float* sigmas, const float* normals_diff, const float* normals_ori,
+                                     const float* deltas, const int64_t* rays_a, float T_threshold,
+                                     int64_t n_samples, int64_t n_rays, float* loss_o, float* loss_p, void* stream) {
+  if (n_rays <= 0) return 0;
+  NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
+    refloss_fw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+        sigmas, normals_diff, normals_ori, deltas, rays_a, T_threshold, n_rays, loss_o, loss_p);
+  });
+  NGP_LAUNCH_CHECK("ngp_composite_refloss_fw");
+  return 0;
+}
+
+// Replaces vren.composite_refloss_bw (binding.cpp:211-239 -> ref_loss.cu:133-175).
+NGP_API int ngp_composite_refloss_bw(const float* dL_dloss_o, const float* dL_dloss_p, const float* sigmas,
+                                     const float* normals_diff, const float* normals_ori, const float* deltas,
+                                     const int64_t* rays_a, const float* loss_o, const float* loss_p,
+                                     float T_threshold, int64_t n_samples, int64_t n_rays, float* dL_dsigmas,
+                                     float* dL_dnormals_diff, float* dL_dnormals_ori, void* stream) {
+  if (n_rays <= 0) return 0;
+  NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
+    refloss_bw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+        dL_dloss_o, dL_dloss_p, sigmas, normals_diff, normals_ori, deltas, rays_a, loss_o, loss_p, T_threshold,
+        n_rays, dL_dsigmas, dL_dnormals_diff, dL_dnormals_ori);
+  });
+  NGP_LAUNCH_CHECK("ngp_composite_refloss_bw");
+  return 0;
+}

@@ -1,0 +1,330 @@
+// Occupancy-bitfield ray marching, training and test time.
+// Replaces reference models/csrc/raymarching.cu:166-332 (raymarching_train_cu) and :335-454
+// (raymarching_test_cu).
+//
+// Reference structure: one kernel, thread per ray, two serial passes joined by two independent
+// global atomics (nondeterministic, mutually inconsistent sample order), behind a host-side zero
+// fill of N_rays*max_samples rows of every output (8.6 GB at 2^18 rays).
+//
+// Here (training): three launches, no atomics, no fill, deterministic ray-index order
+//   1. march_count   : pass 1 per ray -> n_samples[r], jittered start t[r]; block sum of counts
+//   2. block_scan    : one CTA scans the per-block sums -> block offsets, total (device resident)
+//   3. march_write   : block-local exclusive scan of counts + block offset = start_idx; pass 2
+//                      writes rays_a / xyzs / dirs / deltas / ts at their final packed positions.
+// The per-ray float recurrence (t += dt, cell lookup, empty-cell skip) is the reference's, step by
+// step, with the FMA contractions of the reference build made explicit (common.cuh).
+#include "common.cuh"
+
+namespace ngp {
+
+constexpr int kMarchBlock = 256;
+
+struct MarchParams {
+  const uint8_t* __restrict__ bitfield;
+  int cascades;
+  int grid_size;
+  float scale;      // used for mip_bound (raymarching.cu:211)
+  DtParams dt;      // calc_dt constants (built with `scale` for train, `cascades` for test — raymarching.cu:370)
+  float grid_f;     // (float)grid_size
+  float grid_inv;   // 1.0f/grid_size
+  float grid_m1;    // grid_size-1.0f
+  uint32_t grid3;
+};
+
+struct Ray {
+  float ox, oy, oz, dx, dy, dz, dx_inv, dy_inv, dz_inv, sx, sy, sz;
+};
+
+__device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t r) {
+  Ray q;
+  q.ox = __ldg(rays_o + 3 * r); q.oy = __ldg(rays_o + 3 * r + 1); q.oz = __ldg(rays_o + 3 * r + 2);
+  q.dx = __ldg(rays_d + 3 * r); q.dy = __ldg(rays_d + 3 * r + 1); q.dz = __ldg(rays_d + 3 * r + 2);
+  q.dx_inv = __fdiv_rn(1.0f, q.dx); q.dy_inv = __fdiv_rn(1.0f, q.dy); q.dz_inv = __fdiv_rn(1.0f, q.dz);
+  // 0.5f*signf(d)  (signf = copysignf(1,d), raymarching.cu:7)
+  q.sx = copysignf(0.5f, q.dx); q.sy = copysignf(0.5f, q.dy); q.sz = copysignf(0.5f, q.dz);
+  return q;
+}
+
+// One marching step at parameter t (raymarching.cu:205-232).  Returns true when the cell is occupied
+// (then dt is the step to take and x,y,z the sample); otherwise advances t past the empty cell.
+__device__ __forceinline__ bool march_step(const Ray& q, const MarchParams& p, float& t, float& x, float& y,
+                                           float& z, float& dt) {
+  x = __fmaf_rn(t, q.dx, q.ox); y = __fmaf_rn(t, q.dy, q.oy); z = __fmaf_rn(t, q.dz, q.oz);
+  dt = calc_dt(t, p.dt);
+  const int mip = max(mip_from_pos(x, y, z, p.cascades), mip_from_dt(dt, p.grid_size, p.cascades));
+  const float mip_bound = fminf(scalbnf(1.0f, mip - 1), p.scale);
+  const float mip_bound_inv = __fdiv_rn(1.0f, mip_bound);
+  // round down to the containing cell: (int)clamp(0.5f*(x*inv+1)*G, 0, G-1)
+  const int nx = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
+  const int ny = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
+  const int nz = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(z, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
+  const uint32_t idx = (uint32_t)mip * p.grid3 + morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+  const bool occ = __ldg(p.bitfield + (idx >> 3)) & (1u << (idx & 7u));
+  if (occ) return true;
+  // distance to the far faces of this cell along the ray
+  const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), q.sx), p.grid_inv), 2.0f, -1.0f), mip_bound, -x), q.dx_inv);
+  const float ty = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), q.sy), p.grid_inv), 2.0f, -1.0f), mip_bound, -y), q.dy_inv);
+  const float tz = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), q.sz), p.grid_inv), 2.0f, -1.0f), mip_bound, -z), q.dz_inv);
+  const float t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+  do { t = __fadd_rn(t, calc_dt(t, p.dt)); } while (t < t_target);
+  return false;
+}
+
+// Block-wide exclusive scan of one int per thread (kMarchBlock threads).  Returns the exclusive
+// prefix; *total receives the block sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[kMarchBlock / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < kMarchBlock / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kMarchBlock / 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += n;
+    }
+    if (lane < kMarchBlock / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const int warp_off = wid == 0 ? 0 : warp_sums[wid - 1];
+  *total = warp_sums[kMarchBlock / 32 - 1];
+  return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+    const float* __restrict__ noise, MarchParams p, int max_samples, int64_t n_rays,
+    int32_t* __restrict__ n_samples, float* __restrict__ t_start, int32_t* __restrict__ block_sums) {
+  const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  int N = 0;
+  if (r < n_rays) {
+    const Ray q = load_ray(rays_o, rays_d, r);
+    float t1 = __ldg(hits_t + 2 * r);
+    const float t2 = __ldg(hits_t + 2 * r + 1);
+    if (t1 >= 0) t1 = __fmaf_rn(calc_dt(t1, p.dt), __ldg(noise + r), t1);  // raymarching.cu:195-198
+    t_start[r] = t1;
+    float t = t1, x, y, z, dt;
+    while (0 <= t && t < t2 && N < max_samples) {
+      if (march_step(q, p, t, x, y, z, dt)) { t = __fadd_rn(t, dt); N++; }
+    }
+    n_samples[r] = N;
+  }
+  int total;
+  block_exclusive_scan(N, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// One CTA: exclusive scan of n_blocks block sums (int64 to survive R*max_samples > 2^31).
+// counter[0] = total samples, counter[1] = n_rays (raymarching.cu:237-238 leaves the same pair).
+__global__ void __launch_bounds__(1024) block_scan_kernel(const int32_t* __restrict__ block_sums, int n_blocks,
+                                                          int64_t* __restrict__ block_offsets,
+                                                          int32_t* __restrict__ counter, int64_t n_rays,
+                                                          int64_t* __restrict__ total_out) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int64_t v = i < n_blocks ? (int64_t)block_sums[i] : 0;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int64_t s = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t n = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += n;
+      }
+      warp_tot[lane] = s;
+    }
+    __syncthreads();
+    const int64_t carry = carry_s;
+    const int64_t off = carry + (wid == 0 ? 0 : warp_tot[wid - 1]) + inc - v;
+    if (i < n_blocks) block_offsets[i] = off;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int64_t tot = carry_s;
+    if (counter) { counter[0] = (int32_t)tot; counter[1] = (int32_t)n_rays; }
+    if (total_out) *total_out = tot;
+  }
+}
+
+__global__ void __launch_bounds__(kMarchBlock) march_write_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+    MarchParams p, int64_t n_rays, const int32_t* __restrict__ n_samples, const float* __restrict__ t_start,
+    const int64_t* __restrict__ block_offsets, int64_t capacity, int64_t* __restrict__ rays_a,
+    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts) {
+  const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  const int N = r < n_rays ? n_samples[r] : 0;
+  int total;
+  const int64_t start = block_offsets[blockIdx.x] + block_exclusive_scan(N, &total);
+  if (r >= n_rays) return;
+  rays_a[3 * r] = r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = N;
+  if (N == 0) return;
+  const Ray q = load_ray(rays_o, rays_d, r);
+  const float t2 = __ldg(hits_t + 2 * r + 1);
+  float t = t_start[r], x, y, z, dt;
+  int s = 0;
+  while (t < t2 && s < N) {
+    if (march_step(q, p, t, x, y, z, dt)) {
+      const int64_t o = start + s;
+      if (o < capacity) {
+        xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+        dirs[3 * o] = q.dx; dirs[3 * o + 1] = q.dy; dirs[3 * o + 2] = q.dz;
+        ts[o] = t; deltas[o] = dt;
+      }
+      t = __fadd_rn(t, dt); s++;
+    }
+  }
+}
+
+// raymarching.cu:335-404.  Thread per alive ray; dense (N_alive, N_samples, .) outputs; unused
+// slots are written as zeros by the owning thread (the reference pre-zeroes the tensors on the
+// host and models/rendering.py:91 relies on dirs==0 to find them).
+__global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t,
+    const int64_t* __restrict__ alive, MarchParams p, int n_samples_max, int64_t n_alive,
+    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts,
+    int32_t* __restrict__ n_eff) {
+  const int64_t n = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  if (n >= n_alive) return;
+  const int64_t r = alive[n];
+  const Ray q = load_ray(rays_o, rays_d, r);
+  float t = hits_t[2 * r];
+  const float t2 = hits_t[2 * r + 1];
+  float x, y, z, dt, t_mark = t;
+  int s = 0;
+  const int64_t base = n * n_samples_max;
+  while (t < t2 && s < n_samples_max) {
+    if (march_step(q, p, t, x, y, z, dt)) {
+      const int64_t o = base + s;
+      xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+      dirs[3 * o] = q.dx; dirs[3 * o + 1] = q.dy; dirs[3 * o + 2] = q.dz;
+      ts[o] = t; deltas[o] = dt;
+      t = __fadd_rn(t, dt);
+      t_mark = t;  // raymarching.cu:390: the resume point is the t right after the last ACCEPTED sample
+      s++;
+    }
+  }
+  if (s > 0) hits_t[2 * r] = t_mark;
+  n_eff[n] = s;
+  for (int k = s; k < n_samples_max; k++) {
+    const int64_t o = base + k;
+    xyzs[3 * o] = 0.f; xyzs[3 * o + 1] = 0.f; xyzs[3 * o + 2] = 0.f;
+    dirs[3 * o] = 0.f; dirs[3 * o + 1] = 0.f; dirs[3 * o + 2] = 0.f;
+    ts[o] = 0.f; deltas[o] = 0.f;
+  }
+}
+
+static MarchParams make_params(const uint8_t* bitfield, int cascades, float scale, float dt_scale, float esf,
+                               int grid_size, int max_samples) {
+  MarchParams p;
+  p.bitfield = bitfield;
+  p.cascades = cascades;
+  p.grid_size = grid_size;
+  p.scale = scale;
+  p.dt = make_dt_params(esf, max_samples, grid_size, dt_scale);
+  p.grid_f = (float)grid_size;
+  p.grid_inv = 1.0f / (float)grid_size;
+  p.grid_m1 = (float)grid_size - 1.0f;
+  p.grid3 = (uint32_t)grid_size * grid_size * grid_size;
+  return p;
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+// Workspace layout for the training marcher (caller-provided device memory):
+//   int32 n_samples[R] | float t_start[R] | int32 block_sums[B] | int64 block_offsets[B] | int64 total
+NGP_API int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays) {
+  const int64_t B = ceil_div(n_rays, kMarchBlock);
+  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
+  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256;
+}
+
+struct MarchWs { int32_t* n_samples; float* t_start; int32_t* block_sums; int64_t* block_offsets; int64_t* total; };
+static MarchWs carve(void* ws, int64_t n_rays) {
+  const int64_t B = ceil_div(n_rays, kMarchBlock);
+  auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
+  char* p = (char*)ws;
+  MarchWs w;
+  w.n_samples = (int32_t*)p; p += al(n_rays * 4);
+  w.t_start = (float*)p; p += al(n_rays * 4);
+  w.block_sums = (int32_t*)p; p += al(B * 4);
+  w.block_offsets = (int64_t*)p; p += al(B * 8);
+  w.total = (int64_t*)p;
+  return w;
+}
+
+// Phase 1+2 of vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:283-332): count the
+// samples of every ray and scan.  After this call `counter` = [total_samples, n_rays] on the device
+// (and ws.total as int64); the caller may read it to size the outputs exactly, or skip the
+// read-back and pass a capacity bound to ngp_raymarching_train_write.
+NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                        const uint8_t* density_bitfield, int cascades, float scale,
+                                        float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                                        int64_t n_rays, int32_t* counter, void* workspace, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_rays <= 0) { if (counter) cudaMemsetAsync(counter, 0, 8, s); return 0; }
+  const MarchWs w = carve(workspace, n_rays);
+  const MarchParams p = make_params(density_bitfield, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
+  const int B = (int)ceil_div(n_rays, kMarchBlock);
+  march_count_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays,
+                                              w.n_samples, w.t_start, w.block_sums);
+  NGP_LAUNCH_CHECK("ngp_raymarching_train_count/count");
+  block_scan_kernel<<<1, 1024, 0, s>>>(w.block_sums, B, w.block_offsets, counter, n_rays, w.total);
+  NGP_LAUNCH_CHECK("ngp_raymarching_train_count/scan");
+  return 0;
+}
+
+// Phase 3: write rays_a (R,3) i64 = [ray_idx, start_idx, N_samples] in ray-index order and the
+// packed samples.  Rows >= capacity are dropped (never happens when capacity >= counter[0]).
+NGP_API int ngp_raymarching_train_write(const float* rays_o, const float* rays_d, const float* hits_t,
+                                        const uint8_t* density_bitfield, int cascades, float scale,
+                                        float exp_step_factor, int grid_size, int max_samples, int64_t n_rays,
+                                        const void* workspace, int64_t capacity, int64_t* rays_a, float* xyzs,
+                                        float* dirs, float* deltas, float* ts, void* stream) {
+  if (n_rays <= 0) return 0;
+  const MarchWs w = carve((void*)workspace, n_rays);
+  const MarchParams p = make_params(density_bitfield, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
+  const int B = (int)ceil_div(n_rays, kMarchBlock);
+  march_write_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, p, n_rays, w.n_samples,
+                                                                  w.t_start, w.block_offsets, capacity, rays_a,
+                                                                  xyzs, dirs, deltas, ts);
+  NGP_LAUNCH_CHECK("ngp_raymarching_train_write");
+  return 0;
+}
+
+// Replaces vren.raymarching_test (binding.cpp:84-106 -> raymarching.cu:407-454).  hits_t (R,2) is
+// advanced in place.  Reproduces the reference's calc_dt(..., cascades) argument (raymarching.cu:370,399).
+NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                                 const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                                 int grid_size, int max_samples, int n_samples, int64_t n_alive, float* xyzs,
+                                 float* dirs, float* deltas, float* ts, int32_t* n_eff_samples, void* stream) {
+  if (n_alive <= 0) return 0;
+  const MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  const int B = (int)ceil_div(n_alive, kMarchBlock);
+  march_test_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples,
+                                                                 n_alive, xyzs, dirs, deltas, ts, n_eff_samples);
+  NGP_LAUNCH_CHECK("ngp_raymarching_test");
+  return 0;
+}

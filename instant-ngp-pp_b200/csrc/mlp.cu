@@ -1,0 +1,550 @@
+// Fused small-MLP forward / backward on the 5th-gen tensor cores (tcgen05.mma, accumulators in
+// TMEM), one 128-sample tile at a time, activations never leaving shared memory / TMEM between
+// layers.
+//
+// Replaces tcnn.Network({"otype":"CutlassMLP"|"FullyFusedMLP", ...}) as the reference uses it
+// (models/networks.py:89-162: rgb_net, norm_pred_header, semantic_header, skybox_rgb_net,
+// tonemapper_net_*; bias-free, ReLU hidden, None/Sigmoid output) — the reference runs one CUTLASS
+// GEMM launch per layer with every activation round-tripping HBM.  tiny-cuda-nn is not in
+// /root/reference; semantics follow SURVEY.md Appendix B.
+//
+// Parameter layout (flat fp32, row-major (out,in) per layer, layers concatenated):
+//   W_0 [width x k0] | W_1.. [width x width] (n_hidden-1 of them) | W_out [n_out_pad16 x width]
+//
+// Kernel shape: CTA = 128 threads = 4 warps; thread t owns tile row (sample) t for staging and for
+// the TMEM->register epilogues (warp w can read TMEM lanes 32w..32w+31).  Thread 0 issues every
+// tcgen05.mma and commits to one mbarrier; the CTA loops over tiles with stride gridDim.x, and
+// 2-5 co-resident CTAs per SM overlap each other's load / MMA / epilogue phases.
+//   forward : X -> [MMA -> act -> bf16 smem]* -> MMA -> act_out -> global
+//   backward: recompute the forward chain (hidden activations stay in smem), then per layer, top
+//             down:  wgrad (accumulated in TMEM for the CTA's whole lifetime, flushed once with
+//             fp32 atomics) and dgrad, both reading the SAME smem tiles as MN-major operands.
+// Operand tiles use the no-swizzle layout documented in tc05.cuh.
+#include "common.cuh"
+#include "tc05.cuh"
+#include <stdio.h>
+#include <string.h>
+
+namespace ngp {
+using namespace tc05;
+
+constexpr int kTile = 128;
+constexpr int kMaxSeg = 3;
+constexpr int kMaxHidden = 6;
+
+enum Act { kActNone = 0, kActReLU = 1, kActSigmoid = 2, kActExp = 3 };
+enum SegKind { kSegPlain = 0, kSegSH4 = 1 };
+
+struct MlpCfg {
+  int n_seg;
+  int seg_w[kMaxSeg];
+  int seg_kind[kMaxSeg];
+  int64_t seg_stride[kMaxSeg];   // in floats
+  int k0, k0p;                   // input width / padded to 16
+  int w, wp;                     // hidden width / padded to 64 or 128
+  int nh;                        // hidden layers >= 1
+  int no, nop;                   // output width / padded to 16
+  int act_h, act_o;
+  // shared-memory byte offsets
+  uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]
+  uint32_t off_x, off_h[kMaxHidden], off_dz;
+  uint32_t smem_bytes;
+  // TMEM column offsets
+  uint32_t tm_cols;                  // allocation (power of two)
+  uint32_t tm_wg[kMaxHidden + 1];    // wgrad accumulators (backward only)
+  // parameter offsets (floats)
+  int64_t p_off[kMaxHidden + 1];
+};
+
+struct SegPtrs { const float* p[kMaxSeg]; };
+struct SegGrads { float* p[kMaxSeg]; int64_t stride[kMaxSeg]; };
+
+__device__ __forceinline__ float act_apply(int a, float z) {
+  switch (a) {
+    case kActReLU: return fmaxf(z, 0.f);
+    case kActSigmoid: return 1.f / (1.f + __expf(-z));
+    case kActExp: return __expf(z);
+    default: return z;
+  }
+}
+// derivative expressed through the activation's OUTPUT y (what is kept in shared memory)
+__device__ __forceinline__ float act_grad_from_out(int a, float y) {
+  switch (a) {
+    case kActReLU: return y > 0.f ? 1.f : 0.f;
+    case kActSigmoid: return y * (1.f - y);
+    case kActExp: return y;
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y; o[2] = 0.48860251190291987f * z; o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy; o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz; o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2); o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2); o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2); o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__device__ __forceinline__ void st_chunk(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, const float* v) {
+  uint4 q;
+  q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(tile + tile_off(rows, r, c)) = q;
+}
+__device__ __forceinline__ void ld_chunk(const uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, float* v) {
+  const uint4 q = *reinterpret_cast<const uint4*>(tile + tile_off(rows, r, c));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void st_elem(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(tile + tile_off(rows, r, c)) = __float2bfloat16_rn(v);
+}
+
+// Thread t converts sample row `row` of every input segment to bf16 and writes tile row t.
+__device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, int64_t row, bool valid, uint32_t t,
+                                            uint8_t* Xs) {
+  int col = 0;
+  for (int s = 0; s < c.n_seg; s++) {
+    const int w = c.seg_w[s];
+    if (c.seg_kind[s] == kSegSH4) {
+      float o[16];
+      if (valid) {
+        const float* d = in.p[s] + row * c.seg_stride[s];
+        const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+        const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);  // F.normalize(eps=1e-6), networks.py:221
+        sh4(dx * inv, dy * inv, dz * inv, o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = 0.f;
+      }
+      if ((col & 7) == 0) { st_chunk(Xs, kTile, t, col, o); st_chunk(Xs, kTile, t, col + 8, o + 8); }
+      else { for (int i = 0; i < 16; i++) st_elem(Xs, kTile, t, col + i, o[i]); }
+    } else {
+      const float* src = in.p[s] + row * c.seg_stride[s];
+      const bool vec = ((col & 7) == 0) && ((w & 7) == 0) && ((c.seg_stride[s] & 3) == 0) && ((((uintptr_t)in.p[s]) & 15) == 0);
+      if (vec) {
+        for (int j = 0; j < w; j += 8) {
+          float v[8];
+          if (valid) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + j)), b = __ldg(reinterpret_cast<const float4*>(src + j + 4));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.f;
+          }
+          st_chunk(Xs, kTile, t, col + j, v);
+        }
+      } else {
+        for (int j = 0; j < w; j++) st_elem(Xs, kTile, t, col + j, valid ? __ldg(src + j) : 0.f);
+      }
+    }
+    col += w;
+  }
+  for (; col < c.k0p; col++) st_elem(Xs, kTile, t, col, 0.f);
+}
+
+// All threads: convert the fp32 parameter vector to bf16 operand tiles (zero padded).
+__device__ __forceinline__ void stage_weights(const MlpCfg& c, const float* __restrict__ params, uint8_t* smem) {
+  for (int l = 0; l <= c.nh; l++) {
+    const int rows_t = (l == c.nh) ? c.nop : c.wp;           // tile rows
+    const int cols_t = (l == 0) ? c.k0p : c.wp;              // tile cols
+    const int rows = (l == c.nh) ? c.nop : c.w;              // rows present in params
+    const int cols = (l == 0) ? c.k0 : c.w;
+    const float* W = params + c.p_off[l];
+    uint8_t* tile = smem + c.off_w[l];
+    for (int i = threadIdx.x; i < rows_t * cols_t; i += blockDim.x) {
+      const int r = i / cols_t, cc = i % cols_t;
+      const float v = (r < rows && cc < cols) ? __ldg(W + (int64_t)r * cols + cc) : 0.f;
+      st_elem(tile, rows_t, r, cc, v);
+    }
+  }
+}
+
+// ---- MMA issue helpers (single thread) ------------------------------------------------------------
+// D[128 x N] = A[128 x K] (K-major tile, 128 rows) * B[N x K]^T (K-major tile with b_rows rows)
+__device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t b_rows, int N, int K) {
+  const uint32_t id = idesc_bf16(kTile, N, 0, 0);
+  for (int k = 0; k < K; k += 16) {
+    const uint64_t da = smem_desc(a_addr + (k >> 3) * (kTile * 16), kTile * 16, 128);
+    const uint64_t db = smem_desc(b_addr + (k >> 3) * (b_rows * 16), b_rows * 16, 128);
+    mma_bf16(tmem_d, da, db, id, k > 0);
+  }
+}
+// D[128 x N] = dZ[128 x K] (K-major) * W[K x N] where W's tile is [w_rows(K) x N cols]: MN-major B.
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t w_rows, int N, int K) {
+  const uint32_t id = idesc_bf16(kTile, N, 0, 1);
+  for (int k = 0; k < K; k += 16) {
+    const uint64_t da = smem_desc(a_addr + (k >> 3) * (kTile * 16), kTile * 16, 128);
+    const uint64_t db = smem_desc(w_addr + k * 16, 128, w_rows * 16);   // LBO = next 8 rows(k), SBO = next 8 cols(n)
+    mma_bf16(tmem_d, da, db, id, k > 0);
+  }
+}
+// D[M x N] (+)= P[128 x M]^T * Q[128 x N]   (both 128-row sample tiles read MN-major, K = samples)
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t p_addr, uint32_t q_addr, int M, int N, bool accumulate) {
+  const uint32_t id = idesc_bf16(M, N, 1, 1);
+  for (int k = 0; k < kTile; k += 16) {
+    const uint64_t da = smem_desc(p_addr + k * 16, 128, kTile * 16);
+    const uint64_t db = smem_desc(q_addr + k * 16, 128, kTile * 16);
+    mma_bf16(tmem_d, da, db, id, accumulate || k > 0);
+  }
+}
+
+struct CtaCtx {
+  uint64_t* bar; uint32_t* tmem_slot; uint32_t tmem; uint32_t phase;
+};
+
+__device__ __forceinline__ void cta_setup(CtaCtx& x, uint8_t* smem, uint32_t tm_cols) {
+  x.bar = reinterpret_cast<uint64_t*>(smem);
+  x.tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
+  x.phase = 0;
+  if (threadIdx.x == 0) { mbar_init(x.bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { __syncwarp(); tmem_alloc(x.tmem_slot, tm_cols); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  x.tmem = *x.tmem_slot;
+}
+__device__ __forceinline__ void cta_teardown(CtaCtx& x, uint32_t tm_cols) {
+  fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(x.tmem, tm_cols);
+}
+// every thread: wait until all MMAs committed so far have finished
+__device__ __forceinline__ void wait_mma(CtaCtx& x) {
+  mbar_wait(x.bar, x.phase);
+  x.phase ^= 1;
+  fence_after_sync();
+}
+// every thread: smem written by this thread is ready for the tensor core, TMEM reads are done
+__device__ __forceinline__ void publish() {
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+}
+
+// =============================================================================== forward kernel
+__global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
+                                                       float* __restrict__ out, int64_t out_stride) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  CtaCtx cx;
+  cta_setup(cx, smem, c.tm_cols);
+  stage_weights(c, params, smem);
+  const uint32_t t = threadIdx.x, warp = t >> 5;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t tacc = cx.tmem;                               // accumulator columns [0, max(wp,nop))
+  const uint32_t trow = cx.tmem + ((warp * 32u) << 16);        // this warp's lanes
+  uint8_t* Xs = smem + c.off_x;
+  uint8_t* Hs = smem + c.off_h[0];
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * kTile + t;
+    const bool valid = row < n;
+    stage_input(c, in, row, valid, t, Xs);
+    publish();
+    for (int l = 0; l <= c.nh; l++) {
+      const bool last = l == c.nh;
+      const int N = last ? c.nop : c.wp;
+      const int K = l == 0 ? c.k0p : c.wp;
+      if (t == 0) {
+        fence_after_sync();
+        issue_fwd(tacc, sbase + (l == 0 ? c.off_x : c.off_h[0]), sbase + c.off_w[l], (uint32_t)N, N, K);
+        mma_commit(cx.bar);
+      }
+      wait_mma(cx);
+      if (!last) {
+        for (int c0 = 0; c0 < c.wp; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_h, v[i]);
+          st_chunk(Hs, kTile, t, c0, v);
+          st_chunk(Hs, kTile, t, c0 + 8, v + 8);
+        }
+      } else {
+        for (int c0 = 0; c0 < c.nop; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+              if (c0 + i < c.no) out[row * out_stride + c0 + i] = act_apply(c.act_o, v[i]);
+          }
+        }
+      }
+      publish();
+    }
+  }
+  cta_teardown(cx, c.tm_cols);
+}
+
+// =============================================================================== backward kernel
+__global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
+                                                       const float* __restrict__ dout, int64_t dout_stride,
+                                                       float* __restrict__ dparams, SegGrads dseg) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  CtaCtx cx;
+  cta_setup(cx, smem, c.tm_cols);
+  stage_weights(c, params, smem);
+  const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t tacc = cx.tmem;
+  const uint32_t trow = cx.tmem + ((warp * 32u) << 16);
+  uint8_t* Xs = smem + c.off_x;
+  uint8_t* dZ = smem + c.off_dz;
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  bool have_wgrad = false;
+  bool want_dx = false;
+  for (int s = 0; s < c.n_seg; s++) want_dx |= dseg.p[s] != nullptr;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * kTile + t;
+    const bool valid = row < n;
+    stage_input(c, in, row, valid, t, Xs);
+    publish();
+    // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
+    for (int l = 0; l < c.nh; l++) {
+      if (t == 0) {
+        fence_after_sync();
+        issue_fwd(tacc, sbase + (l == 0 ? c.off_x : c.off_h[l - 1]), sbase + c.off_w[l], (uint32_t)c.wp, c.wp, l == 0 ? c.k0p : c.wp);
+        mma_commit(cx.bar);
+      }
+      wait_mma(cx);
+      uint8_t* H = smem + c.off_h[l];
+      for (int c0 = 0; c0 < c.wp; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_h, v[i]);
+        st_chunk(H, kTile, t, c0, v);
+        st_chunk(H, kTile, t, c0 + 8, v + 8);
+      }
+      publish();
+    }
+    // ---- output layer pre-activation -> dZ_out = dL/dy * act_o'(z)
+    if (t == 0) {
+      fence_after_sync();
+      issue_fwd(tacc, sbase + c.off_h[c.nh - 1], sbase + c.off_w[c.nh], (uint32_t)c.nop, c.nop, c.wp);
+      mma_commit(cx.bar);
+    }
+    wait_mma(cx);
+    for (int c0 = 0; c0 < c.nop; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        float g = 0.f;
+        if (valid && c0 + i < c.no) {
+          const float y = act_apply(c.act_o, v[i]);
+          g = __ldg(dout + row * dout_stride + c0 + i) * act_grad_from_out(c.act_o, y);
+        }
+        v[i] = g;
+      }
+      st_chunk(dZ, kTile, t, c0, v);
+      st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+    }
+    publish();
+    // ---- top-down: wgrad + dgrad per layer
+    for (int l = c.nh; l >= 0; l--) {
+      const bool is_out = l == c.nh;
+      const int Nz = is_out ? c.nop : c.wp;                       // width of dZ_l
+      const int Kin = l == 0 ? c.k0p : c.wp;                      // width of the layer's input
+      const uint32_t ain = sbase + (l == 0 ? c.off_x : c.off_h[l - 1]);
+      const bool need_dgrad = l > 0 || want_dx;
+      if (t == 0) {
+        fence_after_sync();
+        if (is_out) issue_wgrad(cx.tmem + c.tm_wg[l], ain, sbase + c.off_dz, c.wp, c.nop, have_wgrad);   // D^T[in x out]
+        else issue_wgrad(cx.tmem + c.tm_wg[l], sbase + c.off_dz, ain, c.wp, Kin, have_wgrad);            // D[out x in]
+        if (need_dgrad) issue_dgrad(tacc, sbase + c.off_dz, sbase + c.off_w[l], (uint32_t)Nz, Kin, Nz);
+        mma_commit(cx.bar);
+      }
+      wait_mma(cx);
+      if (l > 0) {
+        const uint8_t* H = smem + c.off_h[l - 1];
+        for (int c0 = 0; c0 < c.wp; c0 += 16) {
+          float v[16], h[16];
+          tmem_ld16(trow + c0, v);
+          ld_chunk(H, kTile, t, c0, h);
+          ld_chunk(H, kTile, t, c0 + 8, h + 8);
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] *= act_grad_from_out(c.act_h, h[i]);
+          st_chunk(dZ, kTile, t, c0, v);
+          st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+        }
+      } else if (want_dx) {
+        int col = 0;
+        for (int s = 0; s < c.n_seg; s++) {
+          const int w = c.seg_w[s];
+          float* dst = dseg.p[s];
+          // columns [col, col+w) of the accumulator belong to this segment
+          for (int c0 = (col / 16) * 16; c0 < col + w; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
+            if (dst && valid) {
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                const int cc = c0 + i;
+                if (cc >= col && cc < col + w) dst[row * dseg.stride[s] + (cc - col)] = v[i];
+              }
+            }
+          }
+          col += w;
+        }
+      }
+      publish();
+    }
+    have_wgrad = true;
+  }
+
+  // ---- flush the TMEM-resident weight gradients with fp32 atomics
+  if (have_wgrad) {
+    fence_after_sync();
+    // accumulator row m of an M=128 tile sits in TMEM lane m; of an M=64 tile in lane (m%16)+32*(m/16)
+    const bool m128 = c.wp == 128;
+    const int m = m128 ? (int)t : (lane < 16 ? (int)(warp * 16 + lane) : -1);
+    for (int l = 0; l <= c.nh; l++) {
+      const bool is_out = l == c.nh;
+      const int ncols = is_out ? c.nop : (l == 0 ? c.k0p : c.wp);
+      const int in_true = l == 0 ? c.k0 : c.w;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c.tm_wg[l] + c0, v);
+        if (m >= 0 && m < c.w) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int cc = c0 + i;
+            if (is_out) { if (cc < c.no) atomicAdd(dparams + c.p_off[l] + (int64_t)cc * c.w + m, v[i]); }   // D^T[in=m][out=cc]
+            else if (cc < in_true) atomicAdd(dparams + c.p_off[l] + (int64_t)m * in_true + cc, v[i]);       // D[out=m][in=cc]
+          }
+        }
+      }
+    }
+  }
+  cta_teardown(cx, c.tm_cols);
+}
+
+static uint32_t next_pow2_cols(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
+
+// Fills the derived fields of cfg; returns 0 or a negative error.
+static int finalize_cfg(MlpCfg& c, bool backward) {
+  if (c.n_seg < 1 || c.n_seg > kMaxSeg) return -1;
+  c.k0 = 0;
+  for (int s = 0; s < c.n_seg; s++) {
+    if (c.seg_kind[s] == kSegSH4 && c.seg_w[s] != 16) return -2;
+    c.k0 += c.seg_w[s];
+  }
+  c.k0p = (c.k0 + 15) / 16 * 16;
+  if (c.w < 1 || c.w > 128 || c.nh < 1 || c.nh > kMaxHidden || c.no < 1 || c.no > 128 || c.k0p > 256) return -3;
+  c.wp = c.w <= 64 ? 64 : 128;
+  c.nop = (c.no + 15) / 16 * 16;
+  auto al = [](uint32_t x) { return (x + 127u) / 128u * 128u; };
+  uint32_t off = 128;  // mbarrier + tmem slot
+  int64_t poff = 0;
+  for (int l = 0; l <= c.nh; l++) {
+    const int rows_t = l == c.nh ? c.nop : c.wp, cols_t = l == 0 ? c.k0p : c.wp;
+    c.off_w[l] = off; off += al(rows_t * cols_t * 2);
+    c.p_off[l] = poff;
+    poff += (int64_t)(l == c.nh ? c.nop : c.w) * (l == 0 ? c.k0 : c.w);
+  }
+  c.off_x = off; off += al(kTile * c.k0p * 2);
+  const int n_h = backward ? c.nh : 1;
+  for (int l = 0; l < n_h; l++) { c.off_h[l] = off; off += al(kTile * c.wp * 2); }
+  for (int l = n_h; l < kMaxHidden; l++) c.off_h[l] = c.off_h[0];
+  c.off_dz = off;
+  if (backward) off += al(kTile * (c.wp > c.nop ? c.wp : c.nop) * 2);
+  c.smem_bytes = off;
+  uint32_t cols = (uint32_t)c.wp;
+  if ((uint32_t)c.nop > cols) cols = c.nop;
+  if (backward && (uint32_t)c.k0p > cols) cols = c.k0p;
+  if (backward) {
+    for (int l = 0; l <= c.nh; l++) {
+      c.tm_wg[l] = cols;
+      cols += l == c.nh ? c.nop : (l == 0 ? c.k0p : c.wp);
+    }
+  }
+  if (cols > 512) return -4;
+  c.tm_cols = next_pow2_cols(cols);
+  if (c.smem_bytes > 227 * 1024) return -5;
+  return 0;
+}
+
+static int build_cfg(MlpCfg& c, int n_seg, const int* seg_w, const int* seg_kind, const int64_t* seg_stride, int width,
+                     int n_hidden, int n_out, int act_hidden, int act_out, bool backward) {
+  memset(&c, 0, sizeof(c));
+  c.n_seg = n_seg;
+  for (int s = 0; s < n_seg && s < kMaxSeg; s++) { c.seg_w[s] = seg_w[s]; c.seg_kind[s] = seg_kind[s]; c.seg_stride[s] = seg_stride[s]; }
+  c.w = width; c.nh = n_hidden; c.no = n_out; c.act_h = act_hidden; c.act_o = act_out;
+  return finalize_cfg(c, backward);
+}
+
+static int launch_grid(const void* fn, const MlpCfg& c, int64_t n) {
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kTile, c.smem_bytes);
+  if (occ < 1) occ = 1;
+  const int by_tmem = 512 / (int)c.tm_cols;
+  if (occ > by_tmem) occ = by_tmem;
+  int64_t g = (int64_t)kSMs * occ;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (g > tiles) g = tiles;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+// Number of fp32 parameters of the MLP (layout in the header of this file).
+NGP_API int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_out) {
+  if (n_input < 1 || width < 1 || n_hidden < 1 || n_out < 1) return -1;
+  const int64_t nop = (n_out + 15) / 16 * 16;
+  return (int64_t)width * n_input + (int64_t)(n_hidden - 1) * width * width + nop * width;
+}
+
+// out (N, n_out) = MLP(cat(segments)).  Segment kinds: 0 = fp32 rows of seg_width floats at
+// seg_ptr + row*seg_stride; 1 = degree-4 SH of the normalised (N,3) direction at seg_ptr (width 16).
+// Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.
+NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+                       const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
+                       int act_hidden, int act_out, int64_t n, float* out, int64_t out_stride, void* stream) {
+  if (n <= 0) return 0;
+  MlpCfg c;
+  const int rc = build_cfg(c, n_seg, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, false);
+  if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_fw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
+  SegPtrs in; for (int s = 0; s < kMaxSeg; s++) in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
+  cudaError_t e = cudaFuncSetAttribute(mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
+  if (e != cudaSuccess) return set_error(e, "ngp_mlp_fw/attr");
+  const int grid = launch_grid((const void*)mlp_fw_kernel, c, n);
+  mlp_fw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, out, out_stride);
+  NGP_LAUNCH_CHECK("ngp_mlp_fw");
+  return 0;
+}
+
+// dparams (+=, fp32 atomics; caller zeroes) and optional per-segment input gradients
+// dseg_ptr[s] (N, seg_width[s]) with row stride dseg_stride[s] (NULL = not needed; SH segments
+// never receive one).  dL_dout is (N, n_out) with row stride dout_stride.
+NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+                       const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
+                       int act_hidden, int act_out, int64_t n, const float* dL_dout, int64_t dout_stride,
+                       float* dparams, float* const* dseg_ptr, const int64_t* dseg_stride, void* stream) {
+  if (n <= 0) return 0;
+  MlpCfg c;
+  const int rc = build_cfg(c, n_seg, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, true);
+  if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_bw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
+  SegPtrs in; SegGrads dg;
+  for (int s = 0; s < kMaxSeg; s++) {
+    in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
+    dg.p[s] = (s < n_seg && dseg_ptr && seg_kind[s] == kSegPlain) ? dseg_ptr[s] : nullptr;
+    dg.stride[s] = (s < n_seg && dseg_stride) ? dseg_stride[s] : 0;
+  }
+  cudaError_t e = cudaFuncSetAttribute(mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
+  if (e != cudaSuccess) return set_error(e, "ngp_mlp_bw/attr");
+  const int grid = launch_grid((const void*)mlp_bw_kernel, c, n);
+  mlp_bw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, dL_dout, dout_stride, dparams, dg);
+  NGP_LAUNCH_CHECK("ngp_mlp_bw");
+  return 0;
+}

@@ -1,0 +1,130 @@
+// Occupancy-grid maintenance kernels: morton3D, morton3D_invert, packbits.
+// Replaces reference models/csrc/raymarching.cu:62-161 (morton3D_cu, morton3D_invert_cu,
+// packbits_cu).  All three are HBM-streaming integer kernels; they are written as
+// grid-stride loops over a fixed, SM-multiple grid with 16-byte vector accesses.
+#include "common.cuh"
+
+namespace ngp {
+
+// coords (N,3) int32 AoS -> indices (N) int32.  Each thread handles 4 consecutive cells:
+// 3 x int4 loads (48 B) -> 1 x int4 store, fully coalesced across the warp.
+__global__ void __launch_bounds__(256) morton3D_kernel(const int32_t* __restrict__ coords, int64_t n,
+                                                       int32_t* __restrict__ indices) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    const int4* src = reinterpret_cast<const int4*>(coords) + q * 3;
+    const int4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    int4 o;
+    o.x = (int32_t)morton3D(a.x, a.y, a.z);
+    o.y = (int32_t)morton3D(a.w, b.x, b.y);
+    o.z = (int32_t)morton3D(b.z, b.w, c.x);
+    o.w = (int32_t)morton3D(c.y, c.z, c.w);
+    reinterpret_cast<int4*>(indices)[q] = o;
+  }
+  // tail (n % 4 cells)
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) indices[t] = (int32_t)morton3D(coords[3 * t], coords[3 * t + 1], coords[3 * t + 2]);
+}
+
+__global__ void __launch_bounds__(256) morton3D_invert_kernel(const int32_t* __restrict__ indices, int64_t n,
+                                                              int32_t* __restrict__ coords) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    const int4 i = __ldg(reinterpret_cast<const int4*>(indices) + q);
+    // `ind >> k` is an arithmetic shift of a signed int in the reference (raymarching.cu:97-100);
+    // the invert mask keeps only bits < 30 so the sign fill never survives.
+    int4 a, b, c;
+    a.x = morton3D_invert((uint32_t)(i.x >> 0)); a.y = morton3D_invert((uint32_t)(i.x >> 1)); a.z = morton3D_invert((uint32_t)(i.x >> 2));
+    a.w = morton3D_invert((uint32_t)(i.y >> 0)); b.x = morton3D_invert((uint32_t)(i.y >> 1)); b.y = morton3D_invert((uint32_t)(i.y >> 2));
+    b.z = morton3D_invert((uint32_t)(i.z >> 0)); b.w = morton3D_invert((uint32_t)(i.z >> 1)); c.x = morton3D_invert((uint32_t)(i.z >> 2));
+    c.y = morton3D_invert((uint32_t)(i.w >> 0)); c.z = morton3D_invert((uint32_t)(i.w >> 1)); c.w = morton3D_invert((uint32_t)(i.w >> 2));
+    int4* dst = reinterpret_cast<int4*>(coords) + q * 3;
+    dst[0] = a; dst[1] = b; dst[2] = c;
+  }
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const int32_t ind = indices[t];
+    coords[3 * t + 0] = morton3D_invert((uint32_t)(ind >> 0));
+    coords[3 * t + 1] = morton3D_invert((uint32_t)(ind >> 1));
+    coords[3 * t + 2] = morton3D_invert((uint32_t)(ind >> 2));
+  }
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+// One warp packs 32 consecutive cells per step: every lane reads one cell (coalesced 128 B),
+// `__ballot_sync` yields the 32 occupancy bits = 4 output bytes in exactly the reference's
+// bit order (bit i of byte n <-> cell 8n+i, raymarching.cu:133-140, strict '>').
+// Comparison is done in the grid's own dtype promoted to the type the reference compares in
+// (scalar_t > float  ==> float for half/float, double for double).
+template <typename T>
+__global__ void __launch_bounds__(256) packbits_kernel(const T* __restrict__ grid, int64_t n_bytes, float thr,
+                                                       uint8_t* __restrict__ bitfield) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_cells = n_bytes * 8;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_words = (n_cells + 31) >> 5;
+  for (int64_t w = warp0; w < n_words; w += n_warps) {
+    const int64_t cell = (w << 5) + lane;
+    bool occ = false;
+    if (cell < n_cells) {
+      if constexpr (sizeof(T) == 8) occ = grid[cell] > (double)thr;
+      else occ = to_f<T>(grid[cell]) > thr;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, occ);
+    if (lane < 4) {
+      const int64_t byte = (w << 2) + lane;
+      if (byte < n_bytes) bitfield[byte] = (uint8_t)(bits >> (8 * lane));
+    }
+  }
+}
+
+static inline int stream_grid(int64_t work_items, int per_block) {
+  int64_t b = ceil_div(work_items, per_block);
+  const int64_t cap = (int64_t)kSMs * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+// Replaces vren.morton3D (binding.cpp:46-50 -> raymarching.cu:72-88).
+NGP_API int ngp_morton3D(const int32_t* coords, int64_t n, int32_t* indices, void* stream) {
+  if (n <= 0) return 0;
+  morton3D_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, indices);
+  NGP_LAUNCH_CHECK("ngp_morton3D");
+  return 0;
+}
+
+// Replaces vren.morton3D_invert (binding.cpp:53-57 -> raymarching.cu:103-119).
+NGP_API int ngp_morton3D_invert(const int32_t* indices, int64_t n, int32_t* coords, void* stream) {
+  if (n <= 0) return 0;
+  morton3D_invert_kernel<<<stream_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, coords);
+  NGP_LAUNCH_CHECK("ngp_morton3D_invert");
+  return 0;
+}
+
+// Replaces vren.packbits (binding.cpp:35-43 -> raymarching.cu:143-161).
+// dtype: 0 = float32, 1 = float16, 2 = float64 (the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF).
+NGP_API int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold,
+                         uint8_t* density_bitfield, void* stream) {
+  if (n_bytes <= 0) return 0;
+  const int grid = stream_grid(n_bytes * 8, 256 * 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case 0: packbits_kernel<float><<<grid, 256, 0, s>>>((const float*)density_grid, n_bytes, density_threshold, density_bitfield); break;
+    case 1: packbits_kernel<__half><<<grid, 256, 0, s>>>((const __half*)density_grid, n_bytes, density_threshold, density_bitfield); break;
+    case 2: packbits_kernel<double><<<grid, 256, 0, s>>>((const double*)density_grid, n_bytes, density_threshold, density_bitfield); break;
+    default: return set_error_msg("ngp_packbits: dtype must be 0 (f32), 1 (f16) or 2 (f64)");
+  }
+  NGP_LAUNCH_CHECK("ngp_packbits");
+  return 0;
+}

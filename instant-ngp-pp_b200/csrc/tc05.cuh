@@ -1,0 +1,124 @@
+// Thin inline-PTX layer over the Blackwell 5th-gen tensor-core path (tcgen05 + TMEM + mbarrier),
+// sm_100a only.  Bit layouts follow the PTX ISA "tcgen05" matrix/instruction descriptors (the same
+// fields CUTLASS names in cute/arch/mma_sm100_desc.hpp).
+//
+// Shared-memory operand convention used throughout this library (no swizzle, "interleaved" 8x8
+// core matrices, 16-bit elements):
+//     tile[rows][cols] (rows = samples or weight rows, cols = reduction dim of the forward GEMM)
+//     byte_offset(r, c) = (c/8) * (rows*16) + r*16 + (c%8)*2
+// i.e. one 16-byte row chunk per (r, c/8); the 8 rows of a core matrix are 128 contiguous bytes.
+//   * read as a K-major operand  (K = cols): LBO = rows*16 (next 8 cols), SBO = 128 (next 8 rows)
+//   * read as an MN-major operand (K = rows): SBO = rows*16 (next 8 cols), LBO = 128 (next 8 rows)
+// so the SAME buffer feeds forward/dgrad GEMMs (K-major) and wgrad GEMMs (MN-major) unchanged.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tc05 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- TMEM allocation (one full warp executes these) -------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- fences -------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand fetch)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // labels are scoped by the enclosing PTX block, so every inlined copy is independent
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// arrive on `bar` once every tcgen05.mma issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, SWIZZLE_NONE, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulation.
+//   a_mn / b_mn: operand is MN-major (1) or K-major (0).
+__device__ __forceinline__ uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;          // c_format  = F32
+  d |= 1u << 7;          // a_format  = BF16
+  d |= 1u << 10;         // b_format  = BF16
+  d |= (a_mn & 1u) << 15;
+  d |= (b_mn & 1u) << 16;
+  d |= (N >> 3) << 17;
+  d |= (M >> 4) << 24;
+  return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// ---- TMEM -> registers: the calling warp reads its 32 lanes x 16 consecutive 32-bit columns ------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// byte offset of element (r, c) in a [rows][cols] bf16 tile in the layout described above
+__device__ __forceinline__ uint32_t tile_off(uint32_t rows, uint32_t r, uint32_t c) {
+  return (c >> 3) * (rows * 16u) + r * 16u + (c & 7u) * 2u;
+}
+
+}  // namespace tc05

@@ -1,0 +1,166 @@
+"""Autograd boundary of the hot path — same class names and forward/backward arities as the
+reference's models/custom_functions.py:9-244, implemented over ngp_b200.vren.
+
+    RayAABBIntersector  custom_functions.py:9-30      RaySphereIntersector  :33-53
+    RayMarcher          custom_functions.py:56-114    VolumeRenderer        :117-163
+    RefLoss             custom_functions.py:165-198   TruncExp / ReLU / TruncTanh  :200-244
+    DistortionLoss      losses.py:32-58
+"""
+import torch
+
+from . import vren
+
+
+class RayAABBIntersector(torch.autograd.Function):
+    """(rays_o, rays_d, center, half_size, max_hits) -> hit_cnt, hits_t (R,max_hits,2), hits_voxel_idx."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, center, half_size, max_hits):
+        out = vren.ray_aabb_intersect(rays_o, rays_d, center, half_size, max_hits)
+        ctx.mark_non_differentiable(*out)
+        return tuple(out)
+
+
+class RaySphereIntersector(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, center, radii, max_hits):
+        out = vren.ray_sphere_intersect(rays_o, rays_d, center, radii, max_hits)
+        ctx.mark_non_differentiable(*out)
+        return tuple(out)
+
+
+class RayMarcher(torch.autograd.Function):
+    """Occupancy-skipping sample generation.
+
+    forward(rays_o, rays_d, hits_t (R,2), density_bitfield, cascades, scale, exp_step_factor,
+            grid_size, max_samples) -> rays_a (R,3), xyzs (S,3), dirs (S,3), deltas (S), ts (S),
+            total_samples (0-dim int32 tensor)
+    The start-jitter noise is drawn here with torch.rand_like, as the reference does
+    (custom_functions.py:85), so the RNG stream advances identically.
+    """
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, grid_size,
+                max_samples):
+        noise = torch.rand_like(rays_o[:, 0])
+        rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(
+            rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples)
+        ctx.save_for_backward(rays_a, ts)
+        ctx.n_rays = rays_o.shape[0]
+        ctx.mark_non_differentiable(rays_a, deltas, ts)
+        return rays_a, xyzs, dirs, deltas, ts, counter[0]
+
+    @staticmethod
+    def backward(ctx, g_rays_a, g_xyzs, g_dirs, g_deltas, g_ts, g_total):
+        # xyz = o + t*d, dirs = d  =>  dL/do = sum_s dL/dxyz_s ; dL/dd = sum_s (t_s*dL/dxyz_s + dL/ddirs_s)
+        # (custom_functions.py:104-114; unreachable in the reference because the marcher runs under no_grad)
+        rays_a, ts = ctx.saved_tensors
+        ray_of_sample = torch.repeat_interleave(rays_a[:, 0], rays_a[:, 2])
+        g_o = torch.zeros(ctx.n_rays, 3, device=ts.device, dtype=ts.dtype).index_add_(0, ray_of_sample, g_xyzs)
+        g_d = torch.zeros_like(g_o).index_add_(0, ray_of_sample, g_xyzs * ts[:, None] + g_dirs)
+        return g_o, g_d, None, None, None, None, None, None, None
+
+
+class VolumeRenderer(torch.autograd.Function):
+    """Front-to-back compositing of packed samples (training).
+
+    forward(sigmas (S), rgbs (S,3), normals_pred (S,3), sems (S,C), deltas (S), ts (S), rays_a (R,3),
+            T_threshold, classes) -> total_samples (scalar), opacity (R), depth (R), rgb (R,3),
+            normal_pred (R,3), sem (R,C), ws (S)
+    """
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, normals_pred, sems, deltas, ts, rays_a, T_threshold, classes):
+        total, opacity, depth, rgb, normal_pred, sem, ws = vren.composite_train_fw(
+            sigmas, rgbs, normals_pred, sems, deltas, ts, rays_a, T_threshold, classes)
+        ctx.save_for_backward(sigmas, rgbs, normals_pred, deltas, ts, rays_a, opacity, depth, rgb, normal_pred, ws)
+        ctx.T_threshold, ctx.classes = T_threshold, classes
+        return total.sum(), opacity, depth, rgb, normal_pred, sem, ws
+
+    @staticmethod
+    def backward(ctx, g_total, g_opacity, g_depth, g_rgb, g_normal_pred, g_sem, g_ws):
+        sigmas, rgbs, normals_pred, deltas, ts, rays_a, opacity, depth, rgb, normal_pred, ws = ctx.saved_tensors
+        d_sig, d_rgb, d_nrm, d_sem = vren.composite_train_bw(
+            g_opacity.contiguous(), g_depth.contiguous(), g_rgb.contiguous(), g_normal_pred.contiguous(),
+            g_sem.contiguous(), g_ws.contiguous(), sigmas, rgbs, normals_pred, ws, deltas, ts, rays_a, opacity, depth,
+            rgb, normal_pred, ctx.T_threshold, ctx.classes)
+        return d_sig, d_rgb, d_nrm, d_sem, None, None, None, None, None
+
+
+class RefLoss(torch.autograd.Function):
+    """Composited Ref-NeRF normal losses: forward(sigmas, normals_diff (S,3), normals_ori (S), deltas,
+    ts, rays_a, T_threshold) -> loss_o (R), loss_p (R,3).  No gradient reaches sigmas
+    (custom_functions.py:198)."""
+
+    @staticmethod
+    def forward(ctx, sigmas, normals_diff, normals_ori, deltas, ts, rays_a, T_threshold):
+        loss_o, loss_p = vren.composite_refloss_fw(sigmas, normals_diff, normals_ori, deltas, ts, rays_a, T_threshold)
+        ctx.save_for_backward(sigmas, normals_diff, normals_ori, deltas, ts, rays_a, loss_o, loss_p)
+        ctx.T_threshold = T_threshold
+        return loss_o, loss_p
+
+    @staticmethod
+    def backward(ctx, g_loss_o, g_loss_p):
+        sigmas, normals_diff, normals_ori, deltas, ts, rays_a, loss_o, loss_p = ctx.saved_tensors
+        _, d_diff, d_ori = vren.composite_refloss_bw(g_loss_o.contiguous(), g_loss_p.contiguous(), sigmas, normals_diff,
+                                                     normals_ori, deltas, ts, rays_a, loss_o, loss_p, ctx.T_threshold)
+        return None, d_diff, d_ori, None, None, None, None
+
+
+class DistortionLoss(torch.autograd.Function):
+    """mip-NeRF-360 distortion loss per ray: forward(ws, deltas, ts, rays_a) -> loss (R)  (losses.py:32-58)."""
+
+    @staticmethod
+    def forward(ctx, ws, deltas, ts, rays_a):
+        loss, ws_inc, wts_inc = vren.distortion_loss_fw(ws, deltas, ts, rays_a)
+        ctx.save_for_backward(ws_inc, wts_inc, ws, deltas, ts, rays_a)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        ws_inc, wts_inc, ws, deltas, ts, rays_a = ctx.saved_tensors
+        return vren.distortion_loss_bw(g_loss.contiguous(), ws_inc, wts_inc, ws, deltas, ts, rays_a), None, None, None
+
+
+class TruncExp(torch.autograd.Function):
+    """exp with the backward evaluated at clamp(x, -7, 7) (custom_functions.py:200-211)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-7, 7))
+
+
+class TruncTanh(torch.autograd.Function):
+    """tanh with the backward evaluated at clamp(x, -15, 15) (custom_functions.py:231-244)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.tanh(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * (1 - torch.tanh(x.clamp(-15, 15)) ** 2)
+
+
+class ReLU(torch.autograd.Function):
+    """The reference's leaky-gradient ReLU: zero-side gradient is the constant 1e-6, not g*0
+    (custom_functions.py:213-229)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        mask = x > 0
+        ctx.save_for_backward(mask)
+        return torch.where(mask, x, torch.zeros_like(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return torch.where(mask, g, torch.full_like(g, 1e-6))

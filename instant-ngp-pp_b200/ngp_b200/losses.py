@@ -1,0 +1,83 @@
+"""Loss terms that consume the hot path's outputs (reference losses.py:7-152).
+
+Only DistortionLoss touches a kernel; the rest is elementwise torch on (N_rays, .) tensors and is
+kept so that a training step produces exactly the upstream gradients the reference's step does
+(SURVEY.md §3.1 "which gradients actually flow").
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .custom_functions import DistortionLoss  # noqa: F401  (re-exported: losses.py:32-58)
+
+
+def compute_scale_and_shift(prediction, target):
+    """Least-squares (scale, shift) aligning prediction to target (losses.py:7-30), sync-free."""
+    a00, a01 = (prediction * prediction).sum(), prediction.sum()
+    a11 = torch.tensor(float(prediction.numel()), device=prediction.device)
+    b0, b1 = (prediction * target).sum(), target.sum()
+    det = a00 * a11 - a01 * a01
+    ok = det != 0
+    safe = torch.where(ok, det, torch.ones_like(det))
+    return torch.where(ok, (a11 * b0 - a01 * b1) / safe, torch.zeros_like(det)), \
+        torch.where(ok, (-a01 * b0 + a00 * b1) / safe, torch.zeros_like(det))
+
+
+class ExponentialAnnealingWeight:
+    def __init__(self, max, min, k):
+        self.max, self.min, self.k = max, min, k
+
+    def getWeight(self, Tcur):
+        return max(self.min, self.max * math.exp(-Tcur * self.k))
+
+
+class NeRFLoss(nn.Module):
+    """Per-ray loss dictionary; weights as in losses.py:75-83."""
+
+    def __init__(self, lambda_opa=2e-4, lambda_distortion=3e-4):
+        super().__init__()
+        self.lambda_opa = lambda_opa
+        self.lambda_distortion = lambda_distortion
+        self.lambda_depth_mono = 1
+        self.lambda_normal_mono = 1e-3
+        self.lambda_normal_ref_rp = 1e-3
+        self.lambda_normal_ref_ro = 1e-3
+        self.lambda_sky = 1e-1
+        self.lambda_semantic = 4e-2
+        self.Annealing = ExponentialAnnealingWeight(max=1, min=6e-2, k=1e-3)
+        self.CrossEntropyLoss = nn.CrossEntropyLoss(ignore_index=256)
+
+    def forward(self, results, target, **kwargs):
+        d = {}
+        if kwargs.get("embed_msk", False):
+            m = kwargs["mask"]
+            d["r_ms"] = torch.mean(m ** 2) * self.Annealing.getWeight(kwargs["step"])
+            d["rgb"] = (1 - m) * (results["rgb"] - target["rgb"]) ** 2
+        else:
+            d["rgb"] = (results["rgb"] - target["rgb"]) ** 2
+        o = results["opacity"] + 1e-10
+        d["opacity"] = self.lambda_opa * (-o * torch.log(o))
+        if self.lambda_distortion > 0:
+            d["distortion"] = self.lambda_distortion * DistortionLoss.apply(
+                results["ws"], results["deltas"], results["ts"], results["rays_a"])
+        if kwargs.get("normal_ref", False):
+            d["normal_ref_rp"] = self.lambda_normal_ref_rp * results["Rp"]
+            d["normal_ref_ro"] = self.lambda_normal_ref_ro * results["Ro"]
+        if kwargs.get("normal_mono", False):
+            n_pred = F.normalize(results["normal_pred"], dim=-1)
+            n_gt = F.normalize(target["normal"], dim=-1)
+            d["normal_mono"] = self.lambda_normal_mono * (torch.abs(n_pred - n_gt) + 0.1 * (-(n_pred * n_gt)))
+        if kwargs.get("semantic", False):
+            d["CELoss"] = self.lambda_semantic * self.CrossEntropyLoss(results["semantic"], target["label"])
+            sky = torch.where(target["label"] == 4, 1., 0.)
+            d["sky_depth"] = self.lambda_sky * sky * torch.exp(-results["depth"])
+        if kwargs.get("depth_mono", False):
+            depth_2d = target["depth"] / 25
+            w = (depth_2d > 0).float()
+            pred = results["depth"].detach()
+            scale, shift = compute_scale_and_shift(pred * w, depth_2d * w)
+            d["depth_mono"] = w * self.lambda_depth_mono * torch.exp(-pred / kwargs.get("scale", 1)) * \
+                (scale * results["depth"] + shift - depth_2d) ** 2
+        return d

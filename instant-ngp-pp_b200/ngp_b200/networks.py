@@ -1,0 +1,282 @@
+"""Field models of the hot path.
+
+NGP         — the reference's literal model (models/networks.py:13-425): two F=8 hash grids
+              (xyz T=2^19, rgb T=2^21), torch density MLP 128->128->1 with Softplus (double
+              backward for autograd normals), bias-free heads rgb_net / norm_pred_header /
+              semantic_header, optional skybox; same attribute and state-dict key names
+              (xyz_encoder.params, xyz_net.0.weight, rgb_net.params, density_bitfield, ...).
+NGPCompact  — the ngp_pl-shaped model BASELINE.json's headline config names ("16-level hash
+              grid, 2^19 table, 64-wide MLP"): one F=2 grid -> 64-wide MLP -> 16 features,
+              sigma = exp(h0); rgb = MLP(SH4(d) | h).
+
+Both expose density / forward / forward_test / update_density_grid with the reference's
+argument meaning.  What changed relative to the reference's glue:
+  * the input gradient of the density (normals) is obtained with ONE extra input-gradient kernel
+    of the xyz grid instead of a generic autograd.grad through both encoders — the rgb grid
+    never computes dy/dx (the reference does and discards it);
+  * SH + concatenation are assembled inside the MLP kernel (no dir_encoder / torch.cat pass);
+  * update_density_grid has no host sync: the mean density is reduced on the device and the
+    packbits threshold is read by the kernel's caller from a 0-dim tensor only once per update.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import tcnn, vren
+from .custom_functions import TruncExp
+from .tcnn import _GridBwFn
+
+NEAR_DISTANCE = 0.01   # models/rendering.py:10
+
+
+def _cascades(scale):
+    return max(1 + int(np.ceil(np.log2(2 * scale))), 1)     # networks.py:29
+
+
+class _OccupancyMixin:
+    """Occupancy-grid maintenance shared by both models (networks.py:284-408)."""
+
+    grid_size = 128
+
+    def _init_occupancy(self, scale):
+        self.scale = scale
+        self.cascades = _cascades(scale)
+        G = self.grid_size
+        self.register_buffer("center", torch.zeros(1, 3))
+        self.register_buffer("xyz_min", -torch.ones(1, 3) * scale)
+        self.register_buffer("xyz_max", torch.ones(1, 3) * scale)
+        self.register_buffer("half_size", (self.xyz_max - self.xyz_min) / 2)
+        self.register_buffer("density_bitfield", torch.zeros(self.cascades * G ** 3 // 8, dtype=torch.uint8))
+        # the reference registers these two from train.py:128-132
+        self.register_buffer("density_grid", torch.zeros(self.cascades, G ** 3))
+        ax = torch.arange(G, dtype=torch.int32)
+        self.register_buffer("grid_coords", torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3))
+
+    @torch.no_grad()
+    def get_all_cells(self):
+        """[(indices, coords)] * cascades — every cell of the 128^3 lattice (networks.py:294-305)."""
+        indices = vren.morton3D(self.grid_coords).long()
+        return [(indices, self.grid_coords)] * self.cascades
+
+    @torch.no_grad()
+    def sample_uniform_and_occupied_cells(self, M, density_threshold):
+        """M uniform + M occupied cells per cascade (networks.py:308-333)."""
+        G, dev = self.grid_size, self.density_grid.device
+        cells = []
+        for c in range(self.cascades):
+            coords1 = torch.randint(G, (M, 3), dtype=torch.int32, device=dev)
+            indices1 = vren.morton3D(coords1).long()
+            indices2 = torch.nonzero(self.density_grid[c] > density_threshold)[:, 0]
+            if len(indices2) > 0:
+                indices2 = indices2[torch.randint(len(indices2), (M,), device=dev)]
+            coords2 = vren.morton3D_invert(indices2.int())
+            cells.append((torch.cat([indices1, indices2]), torch.cat([coords1, coords2])))
+        return cells
+
+    @torch.no_grad()
+    def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
+        """density_grid = -1 for cells no camera sees (networks.py:336-376)."""
+        N_cams = poses.shape[0]
+        self.count_grid = torch.zeros_like(self.density_grid)
+        w2c_R = poses[:, :3, :3].transpose(1, 2)
+        w2c_T = -w2c_R @ poses[:, :3, 3:]
+        cells = self.get_all_cells()
+        G = self.grid_size
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            hgs = s / G
+            for i in range(0, len(indices), chunk):
+                xyzs = coords[i:i + chunk] / (G - 1) * 2 - 1
+                xyzs_w = (xyzs * (s - hgs)).T
+                uvd = K @ (w2c_R @ xyzs_w + w2c_T)
+                uv = uvd[:, :2] / uvd[:, 2:]
+                in_img = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
+                covered = (uvd[:, 2] >= NEAR_DISTANCE) & in_img
+                count = covered.sum(0) / N_cams
+                self.count_grid[c, indices[i:i + chunk]] = count
+                too_near = ((uvd[:, 2] < NEAR_DISTANCE) & in_img).any(0)
+                valid = (count > 0) & (~too_near)
+                self.density_grid[c, indices[i:i + chunk]] = torch.where(valid, 0., -1.)
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """EMA-max update of the occupancy grid + repack of the bitfield (networks.py:379-408)."""
+        G = self.grid_size
+        tmp = torch.zeros_like(self.density_grid)
+        cells = self.get_all_cells() if warmup else self.sample_uniform_and_occupied_cells(G ** 3 // 4, density_threshold)
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            hgs = s / G
+            xyzs_w = (coords / (G - 1) * 2 - 1) * (s - hgs)
+            xyzs_w += (torch.rand_like(xyzs_w) * 2 - 1) * hgs
+            tmp[c, indices] = self.density(xyzs_w)
+        if erode:
+            decay = torch.clamp(decay ** (1 / self.count_grid), 0.1, 0.95)
+        self.density_grid = torch.where(self.density_grid < 0, self.density_grid,
+                                        torch.maximum(self.density_grid * decay, tmp))
+        pos = self.density_grid > 0
+        mean_density = (self.density_grid * pos).sum() / pos.sum().clamp(min=1)
+        thr = torch.clamp(mean_density, max=density_threshold)     # min(mean, thr), still on the device
+        vren.packbits(self.density_grid, float(thr), self.density_bitfield)
+
+
+class NGP(nn.Module, _OccupancyMixin):
+    def __init__(self, scale, rgb_act="Sigmoid", use_skybox=False, embed_a=False, embed_a_len=12, classes=7,
+                 grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16):
+        super().__init__()
+        self.rgb_act = rgb_act
+        self.use_skybox = use_skybox
+        self.embed_a = embed_a
+        self.classes = classes
+        self._init_occupancy(scale)
+
+        L, Fe = grid_levels, grid_features
+        b = float(np.exp(np.log(2048 * scale / base_res) / (L - 1)))     # networks.py:37,64
+        grid_cfg = lambda log2_T, otype: {"otype": otype, "type": "Hash", "n_levels": L, "n_features_per_level": Fe,
+                                          "log2_hashmap_size": log2_T, "base_resolution": base_res,
+                                          "per_level_scale": b, "interpolation": "Linear"}
+        self.xyz_encoder = tcnn.Encoding(3, grid_cfg(log2_T_xyz, "Grid"))
+        self.xyz_net = nn.Sequential(nn.Linear(self.xyz_encoder.n_output_dims, 128), nn.Softplus(), nn.Linear(128, 1))
+        self.sigma_act = nn.Softplus()
+        self.rgb_encoder = tcnn.Encoding(3, grid_cfg(log2_T_rgb, "HashGrid"))
+        self.dir_encoder = tcnn.Encoding(3, {"otype": "SphericalHarmonics", "degree": 4})
+
+        feat = self.rgb_encoder.n_output_dims
+        rgb_in = feat + self.dir_encoder.n_output_dims + (embed_a_len if embed_a else 0)
+        head = lambda n_in, n_out, width, out_act: tcnn.Network(n_in, n_out, {
+            "otype": "CutlassMLP", "activation": "ReLU", "output_activation": out_act, "n_neurons": width,
+            "n_hidden_layers": 1})
+        self.rgb_net = head(rgb_in, 3, 128, rgb_act)
+        self.norm_pred_header = head(feat, 3, 32, "None")
+        self.semantic_header = head(feat, classes, 32, "None")
+        self.semantic_act = nn.Softmax(dim=-1)
+        if use_skybox:
+            self.skybox_dir_encoder = tcnn.Encoding(3, {"otype": "SphericalHarmonics", "degree": 3})
+            self.skybox_rgb_net = head(9, 3, 32, rgb_act)
+        if rgb_act == "None":
+            for i in range(3):
+                setattr(self, f"tonemapper_net_{i}", head(1, 1, 64, "Sigmoid"))
+
+    # ------------------------------------------------------------------ density / normals
+    def _normalise(self, x):
+        return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
+
+    def density(self, x, return_feat=False, grad=True, grad_feat=True):
+        """sigmas (N) [, feat_rgb (N, L*F)] for x (N,3) in [-scale, scale]  (networks.py:165-184)."""
+        xn = self._normalise(x)
+        with torch.set_grad_enabled(grad and torch.is_grad_enabled()):
+            sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(xn))[:, 0])
+        if not return_feat:
+            return sigmas
+        with torch.set_grad_enabled(grad_feat and torch.is_grad_enabled()):
+            feat_rgb = self.rgb_encoder(xn)
+        return sigmas, feat_rgb
+
+    @torch.enable_grad()
+    def grad(self, x):
+        """sigmas, feat_rgb, d sigma / d x (N,3), differentiable w.r.t. the parameters
+        (networks.py:186-196)."""
+        xn = self._normalise(x.detach())
+        enc = self.xyz_encoder(xn)
+        sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
+        (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)
+        # input gradient of the grid as a differentiable op of (g_enc, table): its backward is the
+        # double-backward kernel
+        g_xn, _ = _GridBwFn.apply(g_enc.contiguous(), xn.contiguous(), self.xyz_encoder.params, self.xyz_encoder.grid,
+                                  True, False)
+        grads = g_xn / (self.xyz_max - self.xyz_min)
+        feat_rgb = self.rgb_encoder(xn)
+        return sigmas, feat_rgb, grads
+
+    # ------------------------------------------------------------------ heads
+    def _rgb(self, d, feat_rgb, kwargs):
+        tensors, kinds = [d, feat_rgb], [1, 0]
+        if self.embed_a:
+            embed_a = kwargs["embedding_a"]
+            if embed_a.size(0) < feat_rgb.size(0):
+                embed_a = torch.repeat_interleave(embed_a, int(feat_rgb.size(0) / embed_a.size(0)), 0)
+            tensors.append(embed_a); kinds.append(0)
+        rgbs = self.rgb_net.forward_segments(tensors, kinds)
+        if self.rgb_act == "None":
+            rgbs = TruncExp.apply(rgbs) if kwargs.get("output_radiance", False) else self.log_radiance_to_rgb(rgbs, **kwargs)
+        return rgbs
+
+    def log_radiance_to_rgb(self, log_radiances, **kwargs):
+        out = [getattr(self, f"tonemapper_net_{i}")(log_radiances[:, i:i + 1]) for i in range(3)]
+        return torch.cat(out, 1)
+
+    def forward(self, x, d, **kwargs):
+        """-> sigmas (N), rgbs (N,3), normals_raw (N,3), normals_pred (N,3), semantic (N,C)  (networks.py:198-240)"""
+        sigmas, feat_rgb, grads = self.grad(x)
+        normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
+        normals_pred = -F.normalize(self.norm_pred_header(feat_rgb), p=2, dim=-1, eps=1e-6)
+        semantic = self.semantic_act(self.semantic_header(feat_rgb))
+        rgbs = self._rgb(d, feat_rgb, kwargs)
+        return sigmas, rgbs, normals_raw, normals_pred, semantic
+
+    def forward_test(self, x, d, **kwargs):
+        """Same quantities in the reference's test-time order: sigmas, rgbs, normals_pred,
+        normals_raw, semantic (networks.py:242-282).  No graph is kept."""
+        with torch.enable_grad():
+            sigmas, feat_rgb, grads = self.grad(x)
+        sigmas, feat_rgb, grads = sigmas.detach(), feat_rgb.detach(), grads.detach()
+        with torch.no_grad():
+            normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
+            normals_pred = -F.normalize(self.norm_pred_header(feat_rgb), p=2, dim=-1, eps=1e-6)
+            semantic = self.semantic_act(self.semantic_header(feat_rgb))
+            rgbs = self._rgb(d, feat_rgb, kwargs)
+        return sigmas, rgbs, normals_pred, normals_raw, semantic
+
+    def forward_skybox(self, d):
+        if not self.use_skybox:
+            return None
+        d = d / torch.norm(d, dim=1, keepdim=True)
+        return self.skybox_rgb_net(self.skybox_dir_encoder((d + 1) / 2))
+
+
+class NGPCompact(nn.Module, _OccupancyMixin):
+    """ngp_pl-shaped field: hash grid (L16,F2,T2^19) -> 64-wide MLP -> 16 ; rgb = MLP(SH4(d)|h)."""
+
+    def __init__(self, scale, rgb_act="Sigmoid", n_levels=16, n_features=2, log2_T=19, base_res=16, width=64,
+                 classes=0):
+        super().__init__()
+        self.rgb_act = rgb_act
+        self.classes = classes
+        self.use_skybox = False
+        self.embed_a = False
+        self._init_occupancy(scale)
+        b = float(np.exp(np.log(2048 * scale / base_res) / (n_levels - 1)))
+        self.xyz_encoder = tcnn.Encoding(3, {"otype": "HashGrid", "n_levels": n_levels,
+                                             "n_features_per_level": n_features, "log2_hashmap_size": log2_T,
+                                             "base_resolution": base_res, "per_level_scale": b})
+        mlp = lambda n_hidden, out_act: {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": out_act,
+                                         "n_neurons": width, "n_hidden_layers": n_hidden}
+        self.sigma_net = tcnn.Network(self.xyz_encoder.n_output_dims, 16, mlp(1, "None"))
+        self.rgb_net = tcnn.Network(32, 3, mlp(2, rgb_act))
+
+    def _normalise(self, x):
+        return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
+
+    def density(self, x, return_feat=False):
+        h = self.sigma_net(self.xyz_encoder(self._normalise(x)))
+        sigmas = TruncExp.apply(h[:, 0])
+        return (sigmas, h) if return_feat else sigmas
+
+    def forward(self, x, d, **kwargs):
+        sigmas, h = self.density(x, return_feat=True)
+        rgbs = self.rgb_net.forward_segments([d, h], [1, 0])
+        zeros3 = torch.zeros(x.shape[0], 3, device=x.device)
+        return sigmas, rgbs, zeros3, zeros3, torch.zeros(x.shape[0], self.classes, device=x.device)
+
+    def forward_test(self, x, d, **kwargs):
+        with torch.no_grad():
+            sigmas, rgbs, n_raw, n_pred, sem = self.forward(x, d, **kwargs)
+        return sigmas, rgbs, n_pred, n_raw, sem
+
+    def forward_skybox(self, d):
+        return None

@@ -1,0 +1,155 @@
+"""Renderer orchestration: AABB -> march -> field -> composite, training and test time.
+
+Same entry point and result keys as the reference's models/rendering.py:13-251
+(`render(model, rays_o, rays_d, **kwargs)` with kwargs test_time, exp_step_factor, T_threshold,
+num_classes, use_skybox, random_bg, embedding_a, max_samples, to_cpu, to_numpy).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import vren
+from .custom_functions import RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer
+
+MAX_SAMPLES = 1024      # models/rendering.py:9
+NEAR_DISTANCE = 0.01    # models/rendering.py:10
+
+
+def render(model, rays_o, rays_d, **kwargs):
+    rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+    _, hits_t, _ = RayAABBIntersector.apply(rays_o, rays_d, model.center, model.half_size, 1)
+    # rays that start inside the box begin at the near plane (rendering.py:30) — one fused where
+    t1 = hits_t[:, 0, 0]
+    hits_t[:, 0, 0] = torch.where((t1 >= 0) & (t1 < NEAR_DISTANCE), torch.full_like(t1, NEAR_DISTANCE), t1)
+
+    fn = _render_rays_test if kwargs.get("test_time", False) else _render_rays_train
+    results = fn(model, rays_o, rays_d, hits_t, **kwargs)
+    if kwargs.get("to_cpu", False):
+        for k, v in results.items():
+            if torch.is_tensor(v):
+                v = v.cpu()
+                if kwargs.get("to_numpy", False):
+                    v = v.numpy()
+            results[k] = v
+    return results
+
+
+def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pred, normal_raw, sem, **kwargs):
+    """Adaptive test-time march/compose loop (rendering.py:46-133): while rays are alive, march each
+    alive ray to its next N_samples occupied samples, evaluate the field there, composite in place,
+    drop converged rays.  N_samples grows as rays die: max(min(N_rays//N_alive, 64), min_samples)."""
+    N_rays = len(rays_o)
+    device = rays_o.device
+    esf = kwargs.get("exp_step_factor", 0.)
+    classes = kwargs.get("num_classes", 7)
+    T_thr = kwargs.get("T_threshold", 1e-4)
+    max_samples = kwargs.get("max_samples", MAX_SAMPLES)
+    min_samples = 1 if esf == 0 else 4
+    alive = torch.arange(N_rays, device=device)
+    samples = 0
+    total_samples = torch.zeros((), dtype=torch.int64, device=device)
+
+    while samples < max_samples:
+        N_alive = len(alive)
+        if N_alive == 0:
+            break
+        N_samples = max(min(N_rays // N_alive, 64), min_samples)
+        samples += N_samples
+        xyzs, dirs, deltas, ts, N_eff = vren.raymarching_test(
+            rays_o, rays_d, hits_t, alive, model.density_bitfield, model.cascades, model.scale, esf,
+            model.grid_size, MAX_SAMPLES, N_samples)
+        total_samples += N_eff.sum()
+        # valid slots are the first N_eff of each row (the reference finds them as dirs != 0)
+        valid = torch.arange(N_samples, device=device)[None, :] < N_eff[:, None]
+        flat = valid.reshape(-1)
+        idx = torch.nonzero(flat)[:, 0]
+        if idx.numel() == 0:
+            break
+        kw = dict(kwargs)
+        if isinstance(kw.get("embedding_a", None), torch.Tensor) and kw["embedding_a"].shape[0] == N_rays:
+            ray_of_slot = alive[:, None].expand(-1, N_samples).reshape(-1)[idx]
+            kw["embedding_a"] = kw["embedding_a"][ray_of_slot]
+        _s, _c, _np, _nr, _sem = model.forward_test(xyzs.reshape(-1, 3)[idx], dirs.reshape(-1, 3)[idx], **kw)
+        n_slots = N_alive * N_samples
+        sigmas = torch.zeros(n_slots, device=device).index_copy_(0, idx, _s.detach().float())
+        rgbs = torch.zeros(n_slots, 3, device=device).index_copy_(0, idx, _c.detach().float())
+        n_pred = torch.zeros(n_slots, 3, device=device).index_copy_(0, idx, _np.detach().float())
+        n_raw = torch.zeros(n_slots, 3, device=device).index_copy_(0, idx, _nr.detach().float())
+        sems = torch.zeros(n_slots, classes, device=device)
+        if classes > 0 and _sem.shape[-1] == classes:
+            sems.index_copy_(0, idx, _sem.detach().float())
+        vren.composite_test_fw(
+            sigmas.view(N_alive, N_samples), rgbs.view(N_alive, N_samples, 3), n_pred.view(N_alive, N_samples, 3),
+            n_raw.view(N_alive, N_samples, 3), sems.view(N_alive, N_samples, classes), deltas, ts, hits_t, alive,
+            T_thr, classes, N_eff, opacity, depth, rgb, normal_pred, normal_raw, sem)
+        alive = alive[alive >= 0]
+
+    rgb_bg = model.forward_skybox(rays_d) if kwargs.get("use_skybox", False) else torch.zeros(3, device=device)
+    rgb += rgb_bg * (1 - opacity)[:, None]
+    return total_samples
+
+
+@torch.no_grad()
+def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
+    """rendering.py:135-190."""
+    hits_t = hits_t[:, 0, :].contiguous()
+    classes = kwargs.get("num_classes", 7)
+    N_rays, device = len(rays_o), rays_o.device
+    opacity = torch.zeros(N_rays, device=device)
+    depth = torch.zeros(N_rays, device=device)
+    rgb = torch.zeros(N_rays, 3, device=device)
+    normal_pred = torch.zeros(N_rays, 3, device=device)
+    normal_raw = torch.zeros(N_rays, 3, device=device)
+    sem = torch.zeros(N_rays, classes, device=device)
+    total_samples = volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pred, normal_raw, sem,
+                                  **kwargs)
+    return {
+        "opacity": opacity, "depth": depth, "rgb": rgb,
+        "normal_pred": F.normalize(normal_pred, dim=-1), "normal_raw": F.normalize(normal_raw, dim=-1),
+        "semantic": torch.argmax(sem, dim=-1, keepdim=True) if classes > 0 else torch.zeros(N_rays, 1, dtype=torch.long, device=device),
+        "total_samples": total_samples,
+        "points": rays_o + rays_d * depth.unsqueeze(-1),
+        "mask": torch.zeros(N_rays, device=device),
+    }
+
+
+def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
+    """rendering.py:193-251."""
+    esf = kwargs.get("exp_step_factor", 0.)
+    T_thr = kwargs.get("T_threshold", 1e-4)
+    classes = kwargs.get("num_classes", 7)
+    results = {}
+    with torch.no_grad():
+        rays_a, xyzs, dirs, results["deltas"], results["ts"], total_samples = RayMarcher.apply(
+            rays_o, rays_d, hits_t[:, 0].contiguous(), model.density_bitfield, model.cascades, model.scale, esf,
+            model.grid_size, MAX_SAMPLES)
+    results["rays_a"] = rays_a
+    results["total_samples"] = total_samples
+
+    kw = dict(kwargs)
+    for k, v in kwargs.items():          # per-ray tensors are repeated per sample (rendering.py:217-219)
+        if isinstance(v, torch.Tensor):
+            kw[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0, output_size=xyzs.shape[0])
+    sigmas, rgbs, normals_raw, normals_pred, sems = model(xyzs, dirs, **kw)
+    results["sigma"], results["xyzs"] = sigmas, xyzs
+
+    (results["vr_samples"], results["opacity"], results["depth"], results["rgb"], results["normal_pred"],
+     results["semantic"], results["ws"]) = VolumeRenderer.apply(
+        sigmas.contiguous(), rgbs.contiguous(), normals_pred.contiguous(), sems.contiguous(), results["deltas"],
+        results["ts"], rays_a, T_thr, classes)
+
+    if kwargs.get("use_skybox", False):
+        rgb_bg = model.forward_skybox(rays_d)
+    elif esf != 0 and kwargs.get("random_bg", False):
+        rgb_bg = torch.rand(3, device=rays_o.device)
+    else:
+        rgb_bg = torch.zeros(3, device=rays_o.device)
+    results["rgb"] = results["rgb"] + rgb_bg * (1 - results["opacity"])[:, None]
+
+    # Ref-NeRF regularisers (rendering.py:243-249)
+    normals_diff = (normals_raw - normals_pred) ** 2
+    view = F.normalize(dirs, p=2, dim=-1, eps=1e-6)
+    normals_ori = torch.clamp(torch.sum(normals_raw * view, dim=-1), min=0.) ** 2
+    results["Ro"], results["Rp"] = RefLoss.apply(sigmas.detach().contiguous(), normals_diff.contiguous(),
+                                                 normals_ori.contiguous(), results["deltas"], results["ts"], rays_a,
+                                                 T_thr)
+    return results

@@ -1,0 +1,288 @@
+"""tinycudann-shaped modules over the libngp_b200 C ABI.
+
+Mirrors the slice of tiny-cuda-nn's PyTorch binding the reference uses
+(models/networks.py:40-162, models/implicit_mask.py:16-27):
+
+    Encoding(n_input_dims, encoding_config, seed=1337, dtype=None)
+    Network(n_input_dims, n_output_dims, network_config, seed=1337)
+    NetworkWithInputEncoding(n_input_dims, n_output_dims, encoding_config, network_config)
+
+each an nn.Module with .n_input_dims, .n_output_dims, a single flat fp32 nn.Parameter `.params`
+(empty for SphericalHarmonics) and forward(x:(N,n_in)) -> (N,n_out) fp32 — the
+TCNN_HALF_PRECISION=0 build the reference's README.md:24 asks for.  The Grid encoding supports
+first- and second-order autograd w.r.t. its input (normals need it, models/networks.py:186-196).
+
+tiny-cuda-nn itself is not in /root/reference; semantics follow SURVEY.md Appendix B and parity
+for this half is pinned only against oracle/tcnn_oracle.py ("parity unpinned" by the reference).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import lib, ptr, check, stream
+
+ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
+
+
+# --------------------------------------------------------------------------------------- grid
+class GridConfig:
+    __slots__ = ("n_levels", "n_features", "log2_T", "base_res", "per_level_scale", "n_params", "offsets", "sizes",
+                 "resolutions", "scales", "dense")
+
+    def __init__(self, cfg):
+        self.n_levels = int(cfg.get("n_levels", 16))
+        self.n_features = int(cfg.get("n_features_per_level", 2))
+        self.log2_T = int(cfg.get("log2_hashmap_size", 19))
+        self.base_res = int(cfg.get("base_resolution", 16))
+        self.per_level_scale = float(cfg.get("per_level_scale", 2.0))
+        if cfg.get("interpolation", "Linear") != "Linear":
+            raise NotImplementedError("ngp_b200 Grid encoding: only Linear interpolation (the reference's choice)")
+        if cfg.get("type", "Hash") != "Hash":
+            raise NotImplementedError("ngp_b200 Grid encoding: only type=Hash (the reference's choice)")
+        L = self.n_levels
+        off = (ctypes.c_uint32 * (L + 1))()
+        siz = (ctypes.c_uint32 * L)()
+        res = (ctypes.c_uint32 * L)()
+        sc = (ctypes.c_float * L)()
+        dn = (ctypes.c_uint8 * L)()
+        n = lib.ngp_hashgrid_layout(L, self.n_features, self.log2_T, self.base_res, self.per_level_scale,
+                                    ctypes.cast(off, ctypes.c_void_p), ctypes.cast(siz, ctypes.c_void_p),
+                                    ctypes.cast(res, ctypes.c_void_p), ctypes.cast(sc, ctypes.c_void_p),
+                                    ctypes.cast(dn, ctypes.c_void_p))
+        if n < 0:
+            raise ValueError(_lib.last_error())
+        self.n_params = int(n)
+        self.offsets, self.sizes, self.resolutions = list(off), list(siz), list(res)
+        self.scales, self.dense = list(sc), [bool(d) for d in dn]
+
+    def args(self):
+        return (self.n_levels, self.n_features, self.log2_T, self.base_res, self.per_level_scale)
+
+
+def grid_forward(x, table, g: GridConfig):
+    n = x.shape[0]
+    y = torch.empty(n, g.n_levels * g.n_features, dtype=torch.float32, device=x.device)
+    check(lib.ngp_hashgrid_fw(ptr(x), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(), n, ptr(y),
+                              stream()), "hashgrid_fw")
+    return y
+
+
+def grid_backward_params(x, dy, g: GridConfig, out=None):
+    dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device) if out is None else out
+    check(lib.ngp_hashgrid_bw_params(ptr(x), ptr(dy), *g.args(), x.shape[0], ptr(dtable), stream()),
+          "hashgrid_bw_params")
+    return dtable
+
+
+def grid_backward_input(x, dy, table, g: GridConfig):
+    dx = torch.empty_like(x)
+    check(lib.ngp_hashgrid_bw_input(ptr(x), ptr(dy), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(),
+                                    x.shape[0], ptr(dx), stream()), "hashgrid_bw_input")
+    return dx
+
+
+class _GridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, g):
+        _lib.require_device()
+        x = x.contiguous()
+        ctx.g = g
+        ctx.save_for_backward(x, table)
+        return grid_forward(x.detach(), table.detach(), g)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table = ctx.saved_tensors
+        need_dx, need_dt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx, dt = _GridBwFn.apply(dy.contiguous(), x, table, ctx.g, need_dx, need_dt)
+        return (dx if need_dx else None), (dt if need_dt else None), None
+
+
+class _GridBwFn(torch.autograd.Function):
+    """First-order backward as a differentiable op, so that autograd.grad(..., create_graph=True)
+    through the encoding (models/networks.py:189-195) has a double backward."""
+
+    @staticmethod
+    def forward(ctx, dy, x, table, g, need_dx, need_dt):
+        ctx.g = g
+        ctx.save_for_backward(dy, x, table)
+        dx = grid_backward_input(x.detach(), dy.detach(), table.detach(), g) if need_dx else torch.zeros_like(x)
+        dt = grid_backward_params(x.detach(), dy.detach(), g) if need_dt else torch.zeros(0, device=x.device)
+        return dx, dt
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_dx, g_dt):
+        # only the dL/dx branch is differentiated again (g_dt: nobody differentiates the table
+        # gradient); outputs: d/d(dy), d/dx (not propagated), d/dtable
+        dy, x, table = ctx.saved_tensors
+        g = ctx.g
+        n = x.shape[0]
+        need_ddy, need_dt = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        d_dy = torch.empty_like(dy) if need_ddy else None
+        dt2 = torch.zeros(g.n_params, dtype=torch.float32, device=x.device) if need_dt else None
+        if need_ddy or need_dt:
+            check(lib.ngp_hashgrid_bwbw_input(ptr(x), ptr(g_dx.contiguous()), ptr(dy), ptr(table),
+                                              0 if table.dtype == torch.float32 else 1, *g.args(), n, ptr(dt2),
+                                              ptr(d_dy), stream()), "hashgrid_bwbw_input")
+        return d_dy, None, dt2, None, None, None
+
+
+# --------------------------------------------------------------------------------------- SH
+def sh_forward(v, degree):
+    _lib.require_device()
+    v = v.contiguous()
+    out = torch.empty(v.shape[0], degree * degree, dtype=torch.float32, device=v.device)
+    check(lib.ngp_sh_fw(ptr(v), int(degree), v.shape[0], ptr(out), stream()), "sh_fw")
+    return out
+
+
+class Encoding(nn.Module):
+    """tcnn.Encoding for otype Grid / HashGrid / SphericalHarmonics (models/networks.py:40-85,128-135)."""
+
+    def __init__(self, n_input_dims, encoding_config, seed=1337, dtype=None):
+        super().__init__()
+        self.n_input_dims = int(n_input_dims)
+        self.encoding_config = dict(encoding_config)
+        self.seed = seed
+        otype = encoding_config["otype"]
+        if otype in ("Grid", "HashGrid"):
+            if self.n_input_dims != 3:
+                raise NotImplementedError("ngp_b200 Grid encoding: 3-D inputs only (the hot path's case)")
+            self.kind = "grid"
+            self.grid = GridConfig(encoding_config)
+            self.n_output_dims = self.grid.n_levels * self.grid.n_features
+            gen = torch.Generator().manual_seed(seed)
+            init = (torch.rand(self.grid.n_params, generator=gen) * 2 - 1) * 1e-4   # tcnn: U(-1e-4, 1e-4)
+            self.params = nn.Parameter(init)
+        elif otype == "SphericalHarmonics":
+            self.kind = "sh"
+            self.degree = int(encoding_config.get("degree", 4))
+            self.n_output_dims = self.degree ** 2
+            self.params = nn.Parameter(torch.zeros(0))
+        else:
+            raise NotImplementedError(f"ngp_b200.tcnn.Encoding: otype {otype!r} is not on the hot path")
+
+    def forward(self, x):
+        if self.kind == "grid":
+            return _GridFn.apply(x.float(), self.params, self.grid)
+        return sh_forward(x.float().detach(), self.degree)
+
+
+# --------------------------------------------------------------------------------------- MLP
+class MlpConfig:
+    __slots__ = ("n_in", "width", "n_hidden", "n_out", "act_h", "act_o", "n_params")
+
+    def __init__(self, n_in, n_out, cfg):
+        self.n_in, self.n_out = int(n_in), int(n_out)
+        self.width = int(cfg.get("n_neurons", 128))
+        self.n_hidden = int(cfg.get("n_hidden_layers", 1))
+        self.act_h = ACT[cfg.get("activation", "ReLU")]
+        self.act_o = ACT[cfg.get("output_activation", "None")]
+        self.n_params = int(lib.ngp_mlp_param_count(self.n_in, self.width, self.n_hidden, self.n_out))
+
+    def layer_shapes(self):
+        nop = (self.n_out + 15) // 16 * 16
+        return [(self.width, self.n_in)] + [(self.width, self.width)] * (self.n_hidden - 1) + [(nop, self.width)]
+
+
+def _seg_arrays(segs):
+    """segs: list of (tensor, width, kind) -> ctypes arrays (ptrs, widths, kinds, strides)."""
+    k = len(segs)
+    P = (ctypes.c_void_p * k)(*[ptr(t) for t, _, _ in segs])
+    W = (ctypes.c_int * k)(*[int(w) for _, w, _ in segs])
+    K = (ctypes.c_int * k)(*[int(kd) for _, _, kd in segs])
+    S = (ctypes.c_int64 * k)(*[int(t.stride(0)) for t, _, _ in segs])
+    return P, W, K, S
+
+
+def mlp_forward(segs, params, m: MlpConfig):
+    """segs: [(tensor (N,w) fp32 | dirs (N,3), width, kind)]; kind 0 plain, 1 SH4-of-normalised-dirs."""
+    n = segs[0][0].shape[0]
+    out = torch.empty(n, m.n_out, dtype=torch.float32, device=params.device)
+    P, W, K, S = _seg_arrays(segs)
+    check(lib.ngp_mlp_fw(len(segs), P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n,
+                         ptr(out), out.stride(0), stream()), "mlp_fw")
+    return out
+
+
+def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg):
+    n = segs[0][0].shape[0]
+    dparams = torch.zeros_like(params)
+    P, W, K, S = _seg_arrays(segs)
+    dsegs = [torch.empty(n, w, dtype=torch.float32, device=params.device) if (nd and kd == 0) else None
+             for (_, w, kd), nd in zip(segs, need_dseg)]
+    k = len(segs)
+    DP = (ctypes.c_void_p * k)(*[ptr(d) for d in dsegs])
+    DS = (ctypes.c_int64 * k)(*[int(d.stride(0)) if d is not None else 0 for d in dsegs])
+    dout = dout.contiguous()
+    check(lib.ngp_mlp_bw(k, P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n, ptr(dout),
+                         dout.stride(0), ptr(dparams), DP, DS, stream()), "mlp_bw")
+    return dparams, dsegs
+
+
+class _MlpFn(torch.autograd.Function):
+    """out = MLP(cat(segments)); segments are passed flat as (t0, t1, ...) after the static args."""
+
+    @staticmethod
+    def forward(ctx, params, m, kinds, *tensors):
+        _lib.require_device()
+        tensors = tuple(t.contiguous() for t in tensors)
+        segs = [(t.detach(), (16 if kd == 1 else t.shape[1]), kd) for t, kd in zip(tensors, kinds)]
+        ctx.m, ctx.kinds = m, kinds
+        ctx.save_for_backward(params, *tensors)
+        return mlp_forward(segs, params.detach(), m)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        params, *tensors = ctx.saved_tensors
+        m, kinds = ctx.m, ctx.kinds
+        segs = [(t, (16 if kd == 1 else t.shape[1]), kd) for t, kd in zip(tensors, kinds)]
+        need = [ctx.needs_input_grad[3 + i] for i in range(len(tensors))]
+        dparams, dsegs = mlp_backward(segs, params, m, dout, need)
+        return (dparams if ctx.needs_input_grad[0] else None, None, None, *dsegs)
+
+
+def xavier_uniform_flat(shapes, seed):
+    gen = torch.Generator().manual_seed(seed)
+    parts = []
+    for (o, i) in shapes:
+        s = math.sqrt(6.0 / (i + o))
+        parts.append(((torch.rand(o, i, generator=gen) * 2 - 1) * s).reshape(-1))
+    return torch.cat(parts)
+
+
+class Network(nn.Module):
+    """tcnn.Network with otype CutlassMLP / FullyFusedMLP (models/networks.py:89-162): bias-free."""
+
+    def __init__(self, n_input_dims, n_output_dims, network_config, seed=1337):
+        super().__init__()
+        self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
+        self.network_config = dict(network_config)
+        self.seed = seed
+        self.mlp = MlpConfig(n_input_dims, n_output_dims, network_config)
+        self.params = nn.Parameter(xavier_uniform_flat(self.mlp.layer_shapes(), seed))
+
+    def forward(self, x):
+        return _MlpFn.apply(self.params, self.mlp, (0,), x.float())
+
+    def forward_segments(self, tensors, kinds):
+        """Fused input assembly: MLP(cat(segments)) without materialising the concatenation
+        (replaces torch.cat + dir_encoder at models/networks.py:221-231)."""
+        return _MlpFn.apply(self.params, self.mlp, tuple(kinds), *tensors)
+
+
+class NetworkWithInputEncoding(nn.Module):
+    def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config, seed=1337):
+        super().__init__()
+        self.encoding = Encoding(n_input_dims, encoding_config, seed=seed)
+        self.network = Network(self.encoding.n_output_dims, n_output_dims, network_config, seed=seed)
+        self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
+
+    def forward(self, x):
+        return self.network(self.encoding(x))
