@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: training rays/s (fw+bw+Adam) of the instant-ngp-pp hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Lego-shaped procedural scene (800x800, 100 views, scale 0.5),
+ngp_pl-shaped field (16-level F2 hash grid T=2^19, 64-wide MLPs), 2^18 rays per GPU per step,
+fp32 tables / bf16 tensor-core operands with fp32 accumulation.  One step = occupancy update (every
+16th) + AABB + march + hash encode + MLPs + composite + losses + backward + (all-reduce) + Adam.
+Prints ONE JSON line (see README / DESIGN.md §measurement for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "instant-ngp-pp_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+R_PER_GPU = 1 << 18
+WORKLOAD = "lego-shaped 800x800x100 views, scale 0.5, hashgrid L16 F2 T2^19 + 64-wide MLPs, 2^18 rays/GPU/step"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(steps, warmup, rays_per_step=4096):
+    """The reference-side CPU implementation of the same workload (oracle port): C restatement of the
+    reference's vren kernels + PyTorch restatement of the tcnn operators, all host threads."""
+    from oracle.cpu_pipeline import CPUPipeline
+    from ngp_b200.synthetic import BoxScene, scene_density_grid, pack_bitfield_torch
+    sc = BoxScene("lego")
+    bf = pack_bitfield_torch(scene_density_grid(sc), 0.5).numpy()
+    pipe = CPUPipeline(bf, scale=0.5)
+    poses = sc.poses(100)
+    gen = torch.Generator().manual_seed(20220806)
+    batches = []
+    for _ in range(2):
+        ro, rd = sc.sample_rays(rays_per_step, poses, gen)
+        rgb, *_ = sc.shade(ro, rd)
+        batches.append((ro.numpy(), rd.numpy(), rgb.numpy()))
+    for i in range(warmup):
+        pipe.train_step(*batches[i % 2])
+    t0 = time.perf_counter()
+    samples = 0
+    for i in range(steps):
+        _, s = pipe.train_step(*batches[i % 2]); samples += s
+    dt = time.perf_counter() - t0
+    return {"value": rays_per_step * steps / dt, "unit": "rays/s", "cores": pipe.threads, "kind": "port",
+            "sample": f"{steps} steps x {rays_per_step} rays of the same workload (fw+bw+Adam), {samples / max(steps, 1) / rays_per_step:.1f} samples/ray, "
+                      f"C oracle single-thread + torch CPU ops on {pipe.threads} threads"}, dt / max(steps, 1)
+
+
+# ------------------------------------------------------------------------------------------ kernel timing
+def time_kernel(fn, iters=10):
+    fn(); torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3
+
+
+def kernel_breakdown(model, xyzs, dirs):
+    """Times the individual hot kernels on the step's real sample set; returns {name: (seconds, algorithmic bytes or flops, unit)}."""
+    from ngp_b200 import tcnn
+    S = xyzs.shape[0]
+    g = model.xyz_encoder.grid
+    LF = g.n_levels * g.n_features
+    xn = ((xyzs - model.xyz_min) / (model.xyz_max - model.xyz_min)).contiguous()
+    table = model.xyz_encoder.params.detach()
+    y = tcnn.grid_forward(xn, table, g)
+    dy = torch.randn_like(y)
+    dtab = torch.zeros_like(table)
+    out = {}
+    # fw 12 + 8*L*F*s_p + L*F*s_o ; bw(params) 12 + L*F*s_o + 2*8*L*F*s_g   (s = 4 bytes here)
+    out["hashgrid_fw"] = (time_kernel(lambda: tcnn.grid_forward(xn, table, g)), S * (12 + 8 * LF * 4 + LF * 4), "B")
+    out["hashgrid_bw_params"] = (time_kernel(lambda: tcnn.grid_backward_params(xn, dy, g, out=dtab)), S * (12 + LF * 4 + 16 * LF * 4), "B")
+    m1, m2 = model.sigma_net.mlp, model.rgb_net.mlp
+    h = tcnn.mlp_forward([(y, LF, 0)], model.sigma_net.params.detach(), m1)
+    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
+    out["mlp_sigma_fw"] = (time_kernel(lambda: tcnn.mlp_forward([(y, LF, 0)], model.sigma_net.params.detach(), m1)), S * flops(m1, LF), "F")
+    dh = torch.randn_like(h)
+    out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(y, LF, 0)], model.sigma_net.params.detach(), m1, dh, [True])), S * flops(m1, LF) * 3, "F")
+    segs = [(dirs, 16, 1), (h, 16, 0)]
+    rgb = tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)
+    out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)), S * flops(m2, 32), "F")
+    drgb = torch.randn_like(rgb)
+    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True])), S * flops(m2, 32) * 3, "F")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def gpu_arm(args):
+    import torch.distributed as dist
+    from ngp_b200 import _lib, vren
+    from ngp_b200.networks import NGPCompact
+    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    from ngp_b200.trainer import Trainer, psnr
+    from ngp_b200.rendering import render
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(20220806); np.random.seed(20220806)          # train.py:402-404
+
+    scene = BoxScene("lego", device=dev)
+    poses = scene.poses(100)
+    model = NGPCompact(scale=0.5).to(dev)
+    model.density_grid.copy_(scene_density_grid(scene))             # converged-occupancy proxy; maintained by update_density_grid afterwards
+    vren.packbits(model.density_grid, 0.5, model.density_bitfield)
+    tr = Trainer(model, lr=1e-2, render_kwargs=dict(exp_step_factor=0.0, num_classes=0), world_size=world)
+
+    R = R_PER_GPU
+    n_batches = 8
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)       # each rank draws its own shard of the global batch
+    pool_o, pool_d, pool_c = [], [], []
+    for _ in range(n_batches):
+        ro, rd = scene.sample_rays(R, poses, gen)
+        c, *_ = scene.shade(ro, rd)
+        pool_o.append(ro); pool_d.append(rd); pool_c.append(c)
+    host = [(o.cpu().pin_memory(), d.cpu().pin_memory(), c.cpu().pin_memory()) for o, d, c in zip(pool_o, pool_d, pool_c)]
+    h2d_bytes = sum(t.numel() * 4 for t in host[0])
+
+    def step_resident(i):
+        return tr.train_step(pool_o[i % n_batches], pool_d[i % n_batches], pool_c[i % n_batches])
+
+    def step_e2e(i):
+        o, d, c = (t.to(dev, non_blocking=True) for t in host[i % n_batches])
+        loss, _ = tr.train_step(o, d, c)
+        return float(loss)                                           # device -> host read of the step's result
+
+    # pre-train so that the occupancy grid / sample count are at their steady state
+    for i in range(args.pretrain):
+        step_resident(i)
+    for i in range(args.warmup):
+        step_resident(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        calls0 = _lib.lib_calls() if hasattr(_lib, "lib_calls") else 0
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        calls = (_lib.lib_calls() if hasattr(_lib, "lib_calls") else 0) - calls0
+        return float(ms) * 1e-3, (sampler.stop() if rank == 0 else None), calls
+
+    t_res, clocks, launches = timed(step_resident, args.steps)
+    t_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # steady-state quality + sample statistics (outside the timed regions)
+    with torch.no_grad():
+        ro, rd = scene.sample_rays(1 << 16, poses, gen)
+        gt, *_ = scene.shade(ro, rd)
+        out = render(model, ro, rd, exp_step_factor=0.0, num_classes=0)
+        q = float(psnr(out["rgb"], gt))
+        spr = float(out["total_samples"]) / ro.shape[0]
+        rays_a, xyzs, dirs = out["rays_a"], out["xyzs"], None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # per-kernel roofline on this step's real samples (rank 0, after the timed regions)
+    from ngp_b200.custom_functions import RayMarcher
+    from ngp_b200.rendering import MAX_SAMPLES
+    with torch.no_grad():
+        _, hits_t, _ = vren.ray_aabb_intersect(pool_o[0], pool_d[0], model.center, model.half_size, 1)
+        ra, xyzs, dirs, deltas, ts, tot = RayMarcher.apply(pool_o[0], pool_d[0], hits_t[:, 0].contiguous(), model.density_bitfield,
+                                                           model.cascades, model.scale, 0.0, model.grid_size, MAX_SAMPLES)
+        kb = kernel_breakdown(model, xyzs, dirs)
+    pk, pk_src = peaks()
+    kern = {}
+    for k, (sec, work, unit) in kb.items():
+        if unit == "B":
+            kern[k] = {"ms": sec * 1e3, "achieved_GBs": work / sec / 1e9, "frac_hbm": work / sec / 1e9 / pk["hbm_gbs"]}
+        else:
+            kern[k] = {"ms": sec * 1e3, "achieved_TFLOPs": work / sec / 1e12, "frac_tensor": work / sec / 1e12 / pk["bf16_tflops_sustained"]}
+    dom = max(kb, key=lambda k: kb[k][0])
+    sec, work, unit = kb[dom]
+    roof = {"kernel": dom, "bound": "hbm" if unit == "B" else "tensor", "achieved": work / sec / (1e9 if unit == "B" else 1e12),
+            "peak": pk["hbm_gbs"] if unit == "B" else pk["bf16_tflops_sustained"], "unit": "GB/s" if unit == "B" else "TFLOP/s",
+            "peak_source": pk_src, "traffic": None, "samples_per_launch": int(xyzs.shape[0])}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+
+    cpu, _ = cpu_arm(steps=4, warmup=1)
+    value = world * R * args.steps / t_res
+    line = {
+        "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32 (bf16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr,
+                   "pretrain_steps": args.pretrain, "psnr_after_pretrain": q, "l2": "inputs_exceed_l2 (>250 MB of samples per step)",
+                   "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of table+MLP gradients" if world > 1 else "single GPU",
+                   "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
+        "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--pretrain", type=int, default=300)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        steps = max(1, min(args.steps, 8))
+        cpu, per_step = cpu_arm(steps=steps, warmup=min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "train rays/s (fw+bw)", "value": cpu["value"], "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": cpu["sample"]},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,18 @@ def last_error() -> str:
     return lib.ngp_last_error().decode()
 
 
+_KERNELS_PER_CALL = {"raymarching_train/count": 2}     # count + block scan; every other entry point = 1 launch
+_launches = 0
+
+
+def lib_calls() -> int:
+    """Number of libngp_b200 kernels launched by this process so far (bench.py's gpu_launches)."""
+    return _launches
+
+
 def check(status: int, what: str = ""):
+    global _launches
+    _launches += _KERNELS_PER_CALL.get(what, 1)
     if status != 0:
         raise RuntimeError(f"ngp_b200 {what}: {last_error()} (status {status})")
 

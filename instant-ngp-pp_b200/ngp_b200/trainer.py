@@ -1,0 +1,61 @@
+"""One optimiser step of the hot path (reference train.py:268-345 `training_step` minus Lightning):
+occupancy update every 16 steps -> render (AABB, march, field, composite) -> NeRFLoss -> backward
+-> gradient all-reduce across ranks (rays are sharded, parameters replicated) -> Adam.
+
+Multi-GPU follows the reference's data-parallel semantics (Lightning DDPPlugin, train.py:431): every
+rank holds the full model and an R/N slice of the ray batch; per-rank mean losses are averaged by
+averaging gradients.  The all-reduce is issued per parameter tensor on torch.distributed (NCCL over
+NVLink on the GPU box, gloo in the CPU tests) — hash-table gradients first, since they dominate.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .losses import NeRFLoss
+from .rendering import render
+
+
+class Trainer:
+    def __init__(self, model, lr=1e-2, eps=1e-15, update_interval=16, warmup_steps=256, density_threshold=0.01 * 1024 / 3 ** 0.5,
+                 lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1):
+        self.model = model
+        self.loss_fn = NeRFLoss(lambda_opa=lambda_opa, lambda_distortion=lambda_distortion)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=eps)     # train.py:244 (eps=1e-15 as ngp_pl)
+        self.update_interval, self.warmup_steps = update_interval, warmup_steps
+        self.density_threshold = density_threshold
+        self.render_kwargs = dict(render_kwargs or {})
+        self.world_size = world_size
+        self.step = 0
+        self.last_samples = None
+
+    def allreduce_grads(self):
+        if self.world_size <= 1:
+            return
+        # largest tensors first: the hash tables are > 99 % of the bytes
+        ps = sorted((p for p in self.model.parameters() if p.grad is not None), key=lambda p: -p.numel())
+        works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
+        for w in works:
+            w.wait()
+        for p in ps:
+            p.grad.div_(self.world_size)
+
+    def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True):
+        """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count."""
+        m = self.model
+        if update_grid and self.step % self.update_interval == 0:
+            m.update_density_grid(self.density_threshold, warmup=self.step < self.warmup_steps)
+        results = render(m, rays_o, rays_d, **self.render_kwargs)
+        losses = self.loss_fn(results, {"rgb": rgb_gt}, **self.render_kwargs)
+        loss = sum(v.mean() for v in losses.values())
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.allreduce_grads()
+        self.opt.step()
+        self.step += 1
+        self.last_samples = results["total_samples"]
+        return loss.detach(), results
+
+
+def psnr(pred, target):
+    return -10.0 * torch.log10(torch.mean((pred - target) ** 2))

@@ -1,0 +1,165 @@
+"""GPU numerics of the tcnn-shaped half against oracle/tcnn_oracle.py
+(PyTorch restatement of tiny-cuda-nn's published algorithm — parity UNPINNED by the reference, see
+that file's header).  Tolerances: hash grid / SH fp32: rtol 1e-5 + atol 1e-6 (same fp32 maths, different
+summation order); table gradients (fp32 atomics): rtol 1e-4; MLP: operands are rounded to bf16 for
+the tcgen05 kind::f16 path, so it is compared (a) with an oracle that rounds the same operands
+(rtol 2e-3) and (b) with the exact fp32 oracle (rtol 3e-2 of the output scale)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tcnn_oracle
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [  # L, F, log2_T, base, scale-of-scene
+    (16, 2, 19, 16, 0.5),     # BASELINE shape
+    (16, 8, 19, 16, 0.5),     # reference xyz_encoder
+    (16, 8, 21, 16, 8.0),     # reference rgb_encoder at scale 8
+    (8, 4, 14, 8, 1.0),
+    (5, 1, 12, 4, 1.0),
+]
+
+
+def _grid(L, F, T, base, scale):
+    from ngp_b200 import tcnn
+    b = float(np.exp(np.log(2048 * scale / base) / (L - 1)))
+    enc = tcnn.Encoding(3, {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": T,
+                            "base_resolution": base, "per_level_scale": b}).cuda()
+    with torch.no_grad():
+        enc.params.copy_(torch.randn_like(enc.params) * 0.5)
+    return enc, (L, F, T, base, b)
+
+
+@pytest.mark.parametrize("cfg", GRIDS, ids=lambda c: f"L{c[0]}F{c[1]}T{c[2]}")
+def test_hashgrid_forward_and_first_order(cfg):
+    enc, args = _grid(*cfg)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 3001
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [1, 0, 0], [0, 1, 0], [0.5, 0.5, 0.5], [0, 0, 1], [1, 1, 0], [0.999999, 0, 1]], device="cuda")
+    x.requires_grad_(True)
+    y = enc(x)
+    xo = x.detach().clone().requires_grad_(True)
+    po = enc.params.detach().clone().requires_grad_(True)
+    yo = tcnn_oracle.grid_encode(xo, po, *args)
+    assert y.shape == yo.shape
+    assert torch.allclose(y, yo, rtol=1e-5, atol=1e-6)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    dy[::5] = 0                                              # exactly-zero upstream rows take the skip branch
+    gx, gp = torch.autograd.grad(y, (x, enc.params), dy)
+    gxo, gpo = torch.autograd.grad(yo, (xo, po), dy)
+    assert torch.allclose(gp, gpo, rtol=1e-4, atol=1e-5)
+    # dy/dx is discontinuous at cell faces: compare away from the hand-placed lattice points
+    assert torch.allclose(gx[8:], gxo[8:], rtol=1e-4, atol=1e-3 * float(gxo.abs().max()))
+
+
+def test_hashgrid_double_backward():
+    enc, args = _grid(8, 4, 14, 8, 1.0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 2000
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    W = torch.randn(32, 1, device="cuda", generator=g)
+
+    def normals_loss(encode, params, xin):
+        xin = xin.clone().requires_grad_(True)
+        s = torch.nn.functional.softplus(encode(xin, params) @ W)[:, 0]
+        (dx,) = torch.autograd.grad(s, xin, torch.ones_like(s), create_graph=True)
+        return (dx ** 2).sum() + s.sum()
+
+    from ngp_b200.tcnn import _GridFn
+    l1 = normals_loss(lambda xi, p: _GridFn.apply(xi, p, enc.grid), enc.params, x)
+    (g1,) = torch.autograd.grad(l1, enc.params)
+    po = enc.params.detach().clone().double().requires_grad_(True)
+    W = W.double()
+    l2 = normals_loss(lambda xi, p: tcnn_oracle.grid_encode(xi, p, *args), po, x.double())
+    (g2,) = torch.autograd.grad(l2, po)
+    assert torch.allclose(l1.double(), l2, rtol=1e-4)
+    assert torch.allclose(g1.double(), g2, rtol=2e-3, atol=2e-4 * float(g2.abs().max()))
+
+
+def test_sh4_and_sh3():
+    from ngp_b200 import tcnn
+    g = torch.Generator(device="cuda").manual_seed(2)
+    d = torch.nn.functional.normalize(torch.randn(5000, 3, device="cuda", generator=g), dim=-1)
+    for deg in (4, 3, 2, 1):
+        enc = tcnn.Encoding(3, {"otype": "SphericalHarmonics", "degree": deg})
+        y = enc((d + 1) / 2)
+        assert torch.allclose(y, tcnn_oracle.sh_encode((d + 1) / 2, deg), rtol=1e-5, atol=1e-6)
+
+
+MLPS = [  # n_in, width, n_hidden, n_out, act, out_act
+    (32, 64, 1, 16, "ReLU", "None"),        # BASELINE sigma net
+    (32, 64, 2, 3, "ReLU", "Sigmoid"),      # BASELINE rgb net
+    (144, 128, 1, 3, "ReLU", "Sigmoid"),    # reference rgb_net
+    (152, 128, 1, 3, "ReLU", "None"),       # reference rgb_net + embedding, HDR
+    (128, 32, 1, 3, "ReLU", "None"),        # norm_pred_header
+    (128, 32, 1, 7, "ReLU", "None"),        # semantic_header
+    (9, 32, 1, 3, "ReLU", "Sigmoid"),       # skybox
+    (1, 64, 1, 1, "ReLU", "Sigmoid"),       # tonemapper
+    (16, 16, 3, 5, "ReLU", "None"),
+]
+
+
+@pytest.mark.parametrize("cfg", MLPS, ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}x{c[3]}")
+@pytest.mark.parametrize("n", [1, 127, 128, 5000])
+def test_mlp_forward(cfg, n):
+    from ngp_b200 import tcnn
+    n_in, width, nh, n_out, act, oact = cfg
+    net = tcnn.Network(n_in, n_out, {"otype": "CutlassMLP", "activation": act, "output_activation": oact,
+                                     "n_neurons": width, "n_hidden_layers": nh}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(n, n_in, device="cuda", generator=g)
+    with torch.no_grad():
+        y = net(x)
+        yb = tcnn_oracle.mlp_forward(x, net.params, n_in, width, nh, n_out, act, oact, operand_dtype=torch.bfloat16)
+        yf = tcnn_oracle.mlp_forward(x, net.params, n_in, width, nh, n_out, act, oact)
+    assert y.shape == (n, n_out) and torch.isfinite(y).all()
+    scale = float(yf.abs().max()) + 1e-3
+    assert torch.allclose(y, yb, rtol=2e-3, atol=2e-3 * scale), float((y - yb).abs().max())
+    assert float((y - yf).abs().max()) <= 3e-2 * scale
+
+
+@pytest.mark.parametrize("cfg", MLPS, ids=lambda c: f"{c[0]}x{c[1]}x{c[2]}x{c[3]}")
+def test_mlp_backward(cfg):
+    from ngp_b200 import tcnn
+    n_in, width, nh, n_out, act, oact = cfg
+    net = tcnn.Network(n_in, n_out, {"otype": "CutlassMLP", "activation": act, "output_activation": oact,
+                                     "n_neurons": width, "n_hidden_layers": nh}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n = 128 * 37 + 5
+    x = torch.randn(n, n_in, device="cuda", generator=g, requires_grad=True)
+    dy = torch.randn(n, n_out, device="cuda", generator=g)
+    y = net(x)
+    gx, gp = torch.autograd.grad(y, (x, net.params), dy)
+    xo = x.detach().clone().requires_grad_(True); po = net.params.detach().clone().requires_grad_(True)
+    yo = tcnn_oracle.mlp_forward(xo, po, n_in, width, nh, n_out, act, oact)
+    gxo, gpo = torch.autograd.grad(yo, (xo, po), dy)
+    # bf16 operands: compare in aggregate (relative L2) rather than elementwise
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))
+    assert rel(gx, gxo) < 2e-2, rel(gx, gxo)
+    assert rel(gp, gpo) < 2e-2, rel(gp, gpo)
+    pad = gp.numel() - (width * n_in + (nh - 1) * width * width + n_out * width)
+    if pad:
+        assert float(gp[-pad:].abs().max()) == 0.0          # padded output rows never receive gradient
+
+
+def test_mlp_segments_fuse_sh_and_concat():
+    from ngp_b200 import tcnn
+    net = tcnn.Network(32, 3, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid",
+                               "n_neurons": 64, "n_hidden_layers": 2}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 4099
+    dirs = torch.randn(n, 3, device="cuda", generator=g) * 3
+    h = torch.randn(n, 16, device="cuda", generator=g, requires_grad=True)
+    y = net.forward_segments([dirs, h], [1, 0])
+    d = torch.nn.functional.normalize(dirs, dim=-1)
+    x = torch.cat([tcnn_oracle.sh_encode((d + 1) / 2, 4), h], 1)
+    yo = tcnn_oracle.mlp_forward(x, net.params, 32, 64, 2, 3, "ReLU", "Sigmoid", operand_dtype=torch.bfloat16)
+    assert torch.allclose(y, yo, rtol=2e-3, atol=2e-3)
+    dy = torch.randn(n, 3, device="cuda", generator=g)
+    (gh,) = torch.autograd.grad(y, h, dy)
+    ho = h.detach().clone().requires_grad_(True)
+    yo = tcnn_oracle.mlp_forward(torch.cat([tcnn_oracle.sh_encode((d + 1) / 2, 4), ho], 1), net.params.detach(), 32, 64, 2, 3, "ReLU", "Sigmoid")
+    (gho,) = torch.autograd.grad(yo, ho, dy)
+    assert float((gh - gho).norm() / gho.norm()) < 2e-2

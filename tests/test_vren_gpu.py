@@ -1,0 +1,338 @@
+"""GPU parity of the vren half: our CUDA path, called through the C ABI
+(ngp_b200.vren -> ctypes -> libngp_b200.so), against
+  (1) the C oracle (oracle/ngp_oracle.c) on identical seeded inputs,
+  (2) the reference's own CUDA kernels (oracle/_ref/vren_ref.so) when that build is present,
+  (3) the committed golden vectors minted from (2) (tests/golden/*.npz).
+Bar: bit-exact for morton / packbits / AABB / per-ray counts / t / dt / xyz; for the __expf
+compositors rtol 2e-4 + atol 2e-5 on per-ray outputs and per-sample weights/gradients (ex2.approx
+vs expf and scan re-association; stated here as the north star requires)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import oracle, build_ref
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL, ATOL = 2e-4, 2e-5
+
+
+@pytest.fixture(scope="module")
+def vren():
+    from ngp_b200 import vren as v
+    return v
+
+
+@pytest.fixture(scope="module")
+def vref():
+    return build_ref.load()
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL, frac=1.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    ok = np.abs(a - b) <= atol + rtol * np.abs(b)
+    assert ok.mean() >= frac, f"mismatch frac {1 - ok.mean():.2e}, max abs {np.abs(a - b).max():.3e}"
+
+
+# ------------------------------------------------------------------------------------ a9
+def test_morton_full_lattice_and_inverse(vren):
+    ax = np.arange(128, dtype=np.int32)
+    lattice = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    m = N(vren.morton3D(T(lattice)))
+    assert (m == oracle.morton3D(lattice)).all()
+    assert sorted(m.tolist()) == list(range(128 ** 3))            # a permutation of the lattice
+    assert (N(vren.morton3D_invert(T(m))) == lattice).all()
+    for n in (0, 1, 3, 5, 4097):                                  # ragged sizes incl. empty
+        rng = np.random.RandomState(n)
+        c = rng.randint(0, 1024, (n, 3)).astype(np.int32)
+        assert (N(vren.morton3D(T(c))) == oracle.morton3D(c)).all()
+        i = rng.randint(-2 ** 31, 2 ** 31 - 1, n).astype(np.int32)
+        assert (N(vren.morton3D_invert(T(i))) == oracle.morton3D_invert(i)).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.float64])
+def test_packbits(vren, dtype):
+    rng = np.random.RandomState(3)
+    for cells in (8, 64, 1000 * 8, 128 ** 3):
+        g = rng.normal(1.0, 2.0, cells).astype(np.float32)
+        g[::7] = -1.0; g[3::11] = 1.25
+        gt = T(g).to(dtype)
+        out = torch.full((cells // 8,), 0xAA, dtype=torch.uint8, device="cuda")
+        vren.packbits(gt, 1.25, out)
+        expect = oracle.packbits(N(gt.float()) if dtype != torch.float64 else g, 1.25)
+        assert (N(out) == expect).all()
+
+
+# ------------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("scale", [0.5, 8.0])
+def test_aabb_bit_exact(vren, vref, scale):
+    o, d = cases.rays(20000, scale, seed=4)
+    c = np.zeros((1, 3), np.float32); h = np.full((1, 3), scale, np.float32)
+    cnt, t, idx = vren.ray_aabb_intersect(T(o), T(d), T(c), T(h), 1)
+    rc, rt, ri = oracle.ray_aabb_intersect(o, d, c, h, 1)
+    assert (N(cnt) == rc).all() and (N(idx) == ri).all()
+    assert (N(t).view(np.uint32) == rt.view(np.uint32)).all()
+    if vref is not None:
+        vc, vt, vi = vref.ray_aabb_intersect(T(o), T(d), T(c), T(h), 1)
+        assert (N(cnt) == N(vc)).all() and (N(idx) == N(vi)).all()
+        assert (N(t).view(np.uint32) == N(vt).view(np.uint32)).all()
+    # several voxels, max_hits > 1
+    c3 = np.array([[0, 0, 0], [0.3, 0.1, 0.0], [-0.2, 0.2, 0.1]], np.float32) * scale * 2
+    h3 = np.full((3, 3), 0.2 * scale, np.float32)
+    cnt, t, idx = vren.ray_aabb_intersect(T(o[:4096]), T(d[:4096]), T(c3), T(h3), 3)
+    rc, rt, ri = oracle.ray_aabb_intersect(o[:4096], d[:4096], c3, h3, 3)
+    assert (N(cnt) == rc).all() and (N(t).view(np.uint32) == rt.view(np.uint32)).all() and (N(idx) == ri).all()
+
+
+def test_sphere_intersect_runs(vren):
+    o, d = cases.rays(4096, 1.0, seed=9)
+    cnt, t, idx = vren.ray_sphere_intersect(T(o), T(d), T(np.zeros((1, 3), np.float32)), T(np.ones(1, np.float32)), 1)
+    co = o; a = (d * d).sum(1); hb = (d * co).sum(1); cc = (co * co).sum(1) - 1
+    disc = hb * hb - a * cc
+    t2 = (-hb + np.sqrt(np.maximum(disc, 0))) / a
+    hit = (disc >= 0) & (t2 > 0)
+    assert (N(cnt) == hit.astype(np.int32)).mean() > 0.999
+    assert np.allclose(N(t)[hit, 0, 1], t2[hit], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ a2 / a3
+def _setup(case):
+    name, kind, scale, casc, esf, n = case
+    ci = [c[0] for c in cases.MARCH_CASES].index(name)
+    bf = cases.bitfield(kind, casc, seed=1)
+    o, d = cases.rays(n, scale, seed=2 + ci)
+    cnt, ht, _ = oracle.ray_aabb_intersect(o, d, np.zeros((1, 3), np.float32), np.full((1, 3), scale, np.float32), 1)
+    h = cases.near_clamp(ht)
+    noise = np.random.RandomState(3 + ci).rand(n).astype(np.float32)
+    return ci, bf, o, d, h, noise
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("case", cases.MARCH_CASES, ids=lambda c: c[0])
+def test_raymarching_train_bit_exact(vren, vref, case):
+    name, kind, scale, casc, esf, n = case
+    ci, bf, o, d, h, noise = _setup(case)
+    rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(T(o), T(d), T(h), T(bf), casc, scale, esf, T(noise), 128, 1024)
+    ra, rx, rd, rdl, rts, rcnt = oracle.raymarching_train(o, d, h, bf, casc, scale, esf, noise, 128, 1024)
+    assert (N(counter) == rcnt).all()
+    assert (N(rays_a) == ra).all()
+    assert (bits(N(ts)) == bits(rts)).all() and (bits(N(deltas)) == bits(rdl)).all()
+    assert (bits(N(xyzs)) == bits(rx)).all() and (bits(N(dirs)) == bits(rd)).all()
+    if vref is not None:
+        va, vx, vd, vdl, vts, vc = vref.raymarching_train(T(o), T(d), T(h), T(bf), casc, scale, esf, T(noise), 128, 1024)
+        tot = int(N(vc)[0])
+        ca, cx, cd, cdl, cts = cases.canonical_order(N(va), N(vx[:tot]), N(vd[:tot]), N(vdl[:tot]), N(vts[:tot]))
+        assert tot == int(N(counter)[0]) and (ca == N(rays_a)).all()
+        assert (bits(cts) == bits(N(ts))).all() and (bits(cdl) == bits(N(deltas))).all()
+        assert (bits(cx) == bits(N(xyzs))).all() and (bits(cd) == bits(N(dirs))).all()
+    gp = os.path.join(GOLD, f"march_{name}.npz")
+    if os.path.exists(gp):
+        g = np.load(gp)
+        assert (g["n_samples"] == N(rays_a)[:, 2]).all()
+        if "ts" in g:
+            assert (bits(g["ts"]) == bits(N(ts))).all() and (bits(g["deltas"]) == bits(N(deltas))).all()
+
+
+@pytest.mark.parametrize("case", cases.MARCH_CASES, ids=lambda c: c[0])
+def test_raymarching_test_bit_exact(vren, vref, case):
+    name, kind, scale, casc, esf, n = case
+    ci, bf, o, d, h, noise = _setup(case)
+    ht = T(h.copy()); ht_o = h.copy(); ht_v = T(h.copy())
+    alive = torch.arange(n, device="cuda")
+    for rnd, ns in enumerate((8, 8, 1, 64)):
+        x, dd, dl, ts, neff = vren.raymarching_test(T(o), T(d), ht, alive, T(bf), casc, scale, esf, 128, 1024, ns)
+        ox, od, odl, ots, oneff = oracle.raymarching_test(o, d, ht_o, np.arange(n), bf, casc, scale, esf, 128, 1024, ns)
+        assert (N(neff) == oneff).all()
+        assert (bits(N(ts)) == bits(ots)).all() and (bits(N(dl)) == bits(odl)).all()
+        assert (bits(N(x)) == bits(ox)).all() and (bits(N(dd)) == bits(od)).all()
+        assert (bits(N(ht)) == bits(ht_o)).all()
+        if vref is not None:
+            vx, vd, vdl, vts, vneff = vref.raymarching_test(T(o), T(d), ht_v, alive, T(bf), casc, scale, esf, 128, 1024, ns)
+            assert (N(vneff) == N(neff)).all() and (bits(N(vts)) == bits(N(ts))).all()
+            assert (bits(N(vx)) == bits(N(x))).all() and (bits(N(ht_v)) == bits(N(ht))).all()
+    # alive subset, out of order
+    sub = torch.tensor(np.random.RandomState(1).permutation(n)[: n // 3], device="cuda")
+    ht = T(h.copy()); ht_o = h.copy()
+    x, dd, dl, ts, neff = vren.raymarching_test(T(o), T(d), ht, sub, T(bf), casc, scale, esf, 128, 1024, 4)
+    ox, od, odl, ots, oneff = oracle.raymarching_test(o, d, ht_o, N(sub), bf, casc, scale, esf, 128, 1024, 4)
+    assert (N(neff) == oneff).all() and (bits(N(ts)) == bits(ots)).all() and (bits(N(ht)) == bits(ht_o)).all()
+
+
+def test_marching_empty_and_degenerate(vren):
+    bf = T(cases.bitfield("full", 1))
+    z3 = torch.zeros(0, 3, device="cuda"); z2 = torch.zeros(0, 2, device="cuda"); z1 = torch.zeros(0, device="cuda")
+    rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(z3, z3, z2, bf, 1, 0.5, 0.0, z1, 128, 1024)
+    assert rays_a.shape == (0, 3) and xyzs.shape == (0, 3) and int(counter[0]) == 0
+    # all rays miss
+    o = torch.tensor([[5.0, 5, 5]] * 7, device="cuda"); d = torch.tensor([[1.0, 0, 0]] * 7, device="cuda")
+    h = -torch.ones(7, 2, device="cuda")
+    rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(o, d, h, bf, 1, 0.5, 0.0, torch.rand(7, device="cuda"), 128, 1024)
+    assert int(counter[0]) == 0 and (rays_a[:, 2] == 0).all() and xyzs.shape[0] == 0
+    # full grid: rays saturate at max_samples = 1024 per ray
+    o, d = cases.rays(300, 0.5, seed=1, special=False)
+    d = d * 0.001                                   # tiny |d|: t range is huge, capped by max_samples
+    cnt, ht, _ = oracle.ray_aabb_intersect(o, d, np.zeros((1, 3), np.float32), np.full((1, 3), 0.5, np.float32), 1)
+    h = cases.near_clamp(ht)
+    rays_a, *_ , counter = vren.raymarching_train(T(o), T(d), T(h), bf, 1, 0.5, 0.0, torch.zeros(300, device="cuda"), 128, 64)
+    assert int(rays_a[:, 2].max()) == 64
+
+
+# ------------------------------------------------------------------------------------ a4-a7
+def _samples(case, n=None):
+    name, kind, scale, casc, esf, nr = case
+    ci, bf, o, d, h, noise = _setup(case)
+    ra, x, dd, dl, ts, cnt = oracle.raymarching_train(o, d, h, bf, casc, scale, esf, noise, 128, 1024)
+    return ci, ra, dl, ts, int(cnt[0]), nr
+
+
+@pytest.mark.parametrize("case", [cases.MARCH_CASES[0], cases.MARCH_CASES[2], cases.MARCH_CASES[3], cases.MARCH_CASES[4]], ids=lambda c: c[0])
+@pytest.mark.parametrize("classes,thr", [(7, 1e-4), (10, 1e-2), (0, 1e-4), (19, 1e-3)])
+def test_composite_train_fw_bw(vren, vref, case, classes, thr):
+    ci, ra, dl, ts, S, R = _samples(case)
+    f = cases.sample_fields(S, classes, seed=5 + ci)
+    g = cases.ray_grads(R, classes, seed=5 + ci)
+    gws = np.random.RandomState(9).normal(size=S).astype(np.float32)
+    args = (T(f["sigmas"]), T(f["rgbs"]), T(f["normals_pred"]), T(f["sems"]), T(dl), T(ts), T(ra))
+    total, op, dep, rgb, nrm, sem, ws = vren.composite_train_fw(*args, thr, classes)
+    o_total, o_op, o_dep, o_rgb, o_nrm, o_sem, o_ws = oracle.composite_train_fw(
+        f["sigmas"], f["rgbs"], f["normals_pred"], f["sems"], dl, ts, ra, thr, classes)
+    assert (N(total) == o_total).mean() > 0.995          # a rounding tie at T == T_threshold may move one stop
+    same = N(total) == o_total
+    ray = np.repeat(ra[:, 0], ra[:, 2])
+    close(N(op)[same], o_op[same]); close(N(dep)[same], o_dep[same]); close(N(rgb)[same], o_rgb[same])
+    close(N(nrm)[same], o_nrm[same]); close(N(sem)[same], o_sem[same])
+    close(N(ws)[same[ray]], o_ws[same[ray]])
+    bw_args = (T(g["dL_dopacity"]), T(g["dL_ddepth"]), T(g["dL_drgb"]), T(g["dL_dnormal_pred"]), T(g["dL_dsem"]), T(gws))
+    dsig, drgb, dnrm, dsem = vren.composite_train_bw(*bw_args, args[0], args[1], args[2], ws, args[4], args[5], args[6],
+                                                     op, dep, rgb, nrm, thr, classes)
+    o_dsig, o_drgb, o_dnrm, o_dsem = oracle.composite_train_bw(
+        g["dL_dopacity"], g["dL_ddepth"], g["dL_drgb"], g["dL_dnormal_pred"], g["dL_dsem"], gws, f["sigmas"], f["rgbs"],
+        f["normals_pred"], o_ws, dl, ts, ra, o_op, o_dep, o_rgb, o_nrm, thr, classes)
+    m = same[ray]
+    close(N(drgb)[m], o_drgb[m]); close(N(dnrm)[m], o_dnrm[m]); close(N(dsem)[m], o_dsem[m])
+    # dsigma sums many cancelling terms: scale the absolute tolerance by the per-ray gradient magnitude
+    scale_ = np.abs(o_dsig[m]).max() + 1e-6
+    close(N(dsig)[m], o_dsig[m], rtol=2e-3, atol=2e-5 * scale_, frac=0.999)
+    if vref is not None and classes > 0:
+        v = vref.composite_train_fw(*args, thr, classes)
+        vs = N(v[0]) == N(total)
+        assert vs.mean() > 0.995
+        for a, b in zip((op, dep, rgb, nrm, sem), v[1:6]):
+            close(N(a)[vs], N(b)[vs])
+        close(N(ws)[vs[ray]], N(v[6])[vs[ray]])
+        vb = vref.composite_train_bw(*bw_args, args[0], args[1], args[2], v[6], args[4], args[5], args[6], v[1], v[2], v[3], v[4], thr, classes)
+        mv = vs[ray]
+        close(N(drgb)[mv], N(vb[1])[mv]); close(N(dsem)[mv], N(vb[3])[mv])
+        close(N(dsig)[mv], N(vb[0])[mv], rtol=2e-3, atol=2e-5 * scale_, frac=0.999)
+
+
+def test_composite_alpha_refloss_distortion(vren, vref):
+    case = cases.MARCH_CASES[2]
+    ci, ra, dl, ts, S, R = _samples(case)
+    f = cases.sample_fields(S, 1, seed=5 + ci); g = cases.ray_grads(R, 1, seed=5 + ci)
+    thr = 1e-4
+    al, ws = vren.composite_alpha_fw(T(f["sigmas"]), T(dl), T(ra), thr)
+    o_al, o_ws = oracle.composite_alpha_fw(f["sigmas"], dl, ra, thr)
+    close(N(al), o_al, frac=0.999); close(N(ws), o_ws, frac=0.999)
+    lo, lp = vren.composite_refloss_fw(T(f["sigmas"]), T(f["normals_diff"]), T(f["normals_ori"]), T(dl), T(ts), T(ra), thr)
+    o_lo, o_lp = oracle.composite_refloss_fw(f["sigmas"], f["normals_diff"], f["normals_ori"], dl, ts, ra, thr)
+    close(N(lo), o_lo, frac=0.995); close(N(lp), o_lp, frac=0.995)
+    ds, dd, do = vren.composite_refloss_bw(T(g["dL_dloss_o"]), T(g["dL_dloss_p"]), T(f["sigmas"]), T(f["normals_diff"]),
+                                           T(f["normals_ori"]), T(dl), T(ts), T(ra), lo, lp, thr)
+    o_ds, o_dd, o_do = oracle.composite_refloss_bw(g["dL_dloss_o"], g["dL_dloss_p"], f["sigmas"], f["normals_diff"],
+                                                   f["normals_ori"], dl, ts, ra, o_lo, o_lp, thr)
+    close(N(dd), o_dd, frac=0.998); close(N(do), o_do, frac=0.998)
+    close(N(ds), o_ds, rtol=2e-3, atol=2e-5 * (np.abs(o_ds).max() + 1e-6), frac=0.998)
+    # distortion: inputs are the oracle's ws so both sides see identical bytes
+    loss, wi, wti = vren.distortion_loss_fw(T(o_ws), T(dl), T(ts), T(ra))
+    o_loss, o_wi, o_wti = oracle.distortion_loss_fw(o_ws, dl, ts, ra)
+    close(N(loss), o_loss, rtol=1e-3, atol=1e-6); close(N(wi), o_wi, rtol=1e-5, atol=1e-7); close(N(wti), o_wti, rtol=1e-5, atol=1e-7)
+    dws = vren.distortion_loss_bw(T(g["dL_dloss"]), T(o_wi), T(o_wti), T(o_ws), T(dl), T(ts), T(ra))
+    o_dws = oracle.distortion_loss_bw(g["dL_dloss"], o_wi, o_wti, o_ws, dl, ts, ra)
+    close(N(dws), o_dws, rtol=1e-5, atol=1e-6)
+    if vref is not None:
+        v_loss, v_wi, v_wti = vref.distortion_loss_fw(T(o_ws), T(dl), T(ts), T(ra))
+        close(N(loss), N(v_loss), rtol=1e-3, atol=1e-6); close(N(wi), N(v_wi), rtol=1e-5, atol=1e-7)
+        v_dws = vref.distortion_loss_bw(T(g["dL_dloss"]), T(o_wi), T(o_wti), T(o_ws), T(dl), T(ts), T(ra))
+        close(N(dws), N(v_dws), rtol=1e-5, atol=1e-6)
+        v_lo, v_lp = vref.composite_refloss_fw(T(f["sigmas"]), T(f["normals_diff"]), T(f["normals_ori"]), T(dl), T(ts), T(ra), thr)
+        close(N(lo), N(v_lo), frac=0.995); close(N(lp), N(v_lp), frac=0.995)
+
+
+@pytest.mark.parametrize("classes", [7, 19])
+def test_composite_test_fw(vren, vref, classes):
+    case = cases.MARCH_CASES[4]
+    name, kind, scale, casc, esf, n = case
+    ci, bf, o, d, h, noise = _setup(case)
+    ht = h.copy()
+    x, dd, dl, ts, neff = oracle.raymarching_test(o, d, ht, np.arange(n), bf, casc, scale, esf, 128, 1024, 8)
+    ft = cases.sample_fields(n * 8, classes, seed=50)
+    rngs = np.random.RandomState(60)
+    st = dict(opacity=(rngs.rand(n) * 0.5).astype(np.float32), depth=rngs.rand(n).astype(np.float32),
+              rgb=rngs.rand(n, 3).astype(np.float32), normal=rngs.rand(n, 3).astype(np.float32),
+              normal_raw=rngs.rand(n, 3).astype(np.float32), sem=rngs.rand(n, classes).astype(np.float32))
+    ours = {k: T(v) for k, v in st.items()}; orc = {k: v.copy() for k, v in st.items()}
+    alive = torch.arange(n, device="cuda"); alive_o = np.arange(n, dtype=np.int64)
+    sh = lambda a, *s: T(a).view(n, 8, *s)
+    vren.composite_test_fw(sh(ft["sigmas"]), sh(ft["rgbs"], 3), sh(ft["normals_pred"], 3), sh(ft["normals_raw"], 3),
+                           sh(ft["sems"], classes), T(dl), T(ts), T(ht), alive, 1e-2, classes, T(neff), ours["opacity"],
+                           ours["depth"], ours["rgb"], ours["normal"], ours["normal_raw"], ours["sem"])
+    oracle.composite_test_fw(ft["sigmas"].reshape(n, 8), ft["rgbs"].reshape(n, 8, 3), ft["normals_pred"].reshape(n, 8, 3),
+                             ft["normals_raw"].reshape(n, 8, 3), ft["sems"].reshape(n, 8, classes), dl, ts, ht, alive_o, 1e-2,
+                             classes, neff, orc["opacity"], orc["depth"], orc["rgb"], orc["normal"], orc["normal_raw"], orc["sem"])
+    same = N(alive) == alive_o
+    assert same.mean() > 0.995
+    for k in st:
+        close(N(ours[k])[same], orc[k][same])
+
+
+# ------------------------------------------------------------------------------------ goldens (reference CUDA outputs)
+def test_against_committed_goldens(vren):
+    files = [f for f in os.listdir(GOLD) if f.endswith(".npz")] if os.path.isdir(GOLD) else []
+    if not files:
+        pytest.skip("no golden vectors committed yet (tests/golden/make_golden.py)")
+    g = np.load(os.path.join(GOLD, "occupancy.npz"))
+    assert (N(vren.morton3D(T(g["coords"]))) == g["morton"]).all()
+    assert (N(vren.morton3D_invert(T(g["inv_in"]))) == g["inv_out"]).all()
+    out = torch.zeros(g["bits_f32"].shape[0], dtype=torch.uint8, device="cuda")
+    vren.packbits(T(g["grid"]), float(g["thr"]), out)
+    assert (N(out) == g["bits_f32"]).all()
+    vren.packbits(T(g["grid"]).half(), float(g["thr"]), out)
+    assert (N(out) == g["bits_f16"]).all()
+    for ci, (name, kind, scale, casc, esf, n) in enumerate(cases.MARCH_CASES):
+        p = os.path.join(GOLD, f"march_{name}.npz")
+        if not os.path.exists(p):
+            continue
+        g = np.load(p)
+        o, d = cases.rays(n, scale, seed=2 + ci)
+        cnt, t, idx = vren.ray_aabb_intersect(T(o), T(d), T(np.zeros((1, 3), np.float32)), T(np.full((1, 3), scale, np.float32)), 1)
+        assert (N(cnt) == g["hit_cnt"]).all() and (bits(N(t)) == bits(g["hits_t"])).all()
+        if "fw_t4_opacity" in g:
+            C = 7
+            bf = cases.bitfield(kind, casc, seed=1)
+            h = cases.near_clamp(g["hits_t"])
+            noise = np.random.RandomState(3 + ci).rand(n).astype(np.float32)
+            rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(T(o), T(d), T(h), T(bf), casc, scale, esf, T(noise), 128, 1024)
+            S = int(counter[0])
+            f = cases.sample_fields(S, C, seed=5 + ci)
+            for tag, thr in (("t4", 1e-4), ("t2", 1e-2)):
+                total, op, dep, rgb, nrm, sem, ws = vren.composite_train_fw(T(f["sigmas"]), T(f["rgbs"]), T(f["normals_pred"]),
+                                                                            T(f["sems"]), deltas, ts, rays_a, thr, C)
+                same = N(total) == g[f"fw_{tag}_total"]
+                assert same.mean() > 0.995
+                close(N(op)[same], g[f"fw_{tag}_opacity"][same]); close(N(rgb)[same], g[f"fw_{tag}_rgb"][same])
+                close(N(sem)[same], g[f"fw_{tag}_sem"][same]); close(N(dep)[same], g[f"fw_{tag}_depth"][same])
