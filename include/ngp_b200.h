@@ -151,6 +151,13 @@ int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, con
                int act_out, int64_t n, const float* dL_dout, int64_t dout_stride, float* dparams,
                float* const* dseg_ptr, const int64_t* dseg_stride, void* stream);
 
+/* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
+ * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */
+int ngp_grad_sumsq(const float* g, int64_t n, float* accum, void* stream);
+int ngp_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream);
+int ngp_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

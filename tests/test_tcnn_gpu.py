@@ -31,51 +31,72 @@ def _grid(L, F, T, base, scale):
     return enc, (L, F, T, base, b)
 
 
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
 @pytest.mark.parametrize("cfg", GRIDS, ids=lambda c: f"L{c[0]}F{c[1]}T{c[2]}")
 def test_hashgrid_forward_and_first_order(cfg):
+    """Against the oracle evaluated in float64 on the same float32 inputs.  The encoding's condition
+    number grows with the level resolution (pos = x*scale + 0.5 is rounded at magnitude `scale`), so the
+    forward bound is per level: |err| <= 8 * eps_fp32 * scale_l * max|table| + 1e-6; gradients are
+    compared in relative L2 (1e-4 table, 1e-3 input)."""
     enc, args = _grid(*cfg)
+    L, F = cfg[0], cfg[1]
     g = torch.Generator(device="cuda").manual_seed(0)
     n = 3001
     x = torch.rand(n, 3, device="cuda", generator=g)
     x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [1, 0, 0], [0, 1, 0], [0.5, 0.5, 0.5], [0, 0, 1], [1, 1, 0], [0.999999, 0, 1]], device="cuda")
     x.requires_grad_(True)
     y = enc(x)
-    xo = x.detach().clone().requires_grad_(True)
-    po = enc.params.detach().clone().requires_grad_(True)
+    xo = x.detach().double().requires_grad_(True)
+    po = enc.params.detach().double().requires_grad_(True)
     yo = tcnn_oracle.grid_encode(xo, po, *args)
-    assert y.shape == yo.shape
-    assert torch.allclose(y, yo, rtol=1e-5, atol=1e-6)
+    assert y.shape == yo.shape == (n, L * F)
+    vmax = float(enc.params.abs().max())
+    scales = torch.tensor(enc.grid.scales, device="cuda").repeat_interleave(F)
+    bound = 8 * 6e-8 * scales * vmax + 1e-6
+    err = (y.double() - yo).abs()
+    assert bool((err <= bound[None, :]).all()), float((err / bound[None, :]).max())
     dy = torch.randn(y.shape, device="cuda", generator=g)
     dy[::5] = 0                                              # exactly-zero upstream rows take the skip branch
     gx, gp = torch.autograd.grad(y, (x, enc.params), dy)
-    gxo, gpo = torch.autograd.grad(yo, (xo, po), dy)
-    assert torch.allclose(gp, gpo, rtol=1e-4, atol=1e-5)
+    gxo, gpo = torch.autograd.grad(yo, (xo, po), dy.double())
+    assert rel(gp, gpo) < 1e-4, rel(gp, gpo)
     # dy/dx is discontinuous at cell faces: compare away from the hand-placed lattice points
-    assert torch.allclose(gx[8:], gxo[8:], rtol=1e-4, atol=1e-3 * float(gxo.abs().max()))
+    assert rel(gx[8:], gxo[8:]) < 1e-3, rel(gx[8:], gxo[8:])
 
 
 def test_hashgrid_double_backward():
-    enc, args = _grid(8, 4, 14, 8, 1.0)
+    """Normals-style second order: loss = |d softplus(y.W)/dx|^2 + sum; gradient w.r.t. the table goes
+    through the double-backward kernel.  Low resolutions keep the fp32 problem well conditioned."""
+    from ngp_b200 import tcnn
+    from ngp_b200.tcnn import _GridFn
+    L, F, T, base, b = 6, 4, 11, 4, 1.45
+    enc = tcnn.Encoding(3, {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": T,
+                            "base_resolution": base, "per_level_scale": b}).cuda()
+    assert enc.grid.dense[0] and not enc.grid.dense[-1]
+    with torch.no_grad():
+        enc.params.copy_(torch.randn_like(enc.params) * 0.5)
+    args = (L, F, T, base, b)
     g = torch.Generator(device="cuda").manual_seed(1)
-    n = 2000
+    n = 4000
     x = torch.rand(n, 3, device="cuda", generator=g)
-    W = torch.randn(32, 1, device="cuda", generator=g)
+    W = torch.randn(L * F, 1, device="cuda", generator=g) * 0.3
 
-    def normals_loss(encode, params, xin):
+    def normals_loss(encode, params, xin, Wm):
         xin = xin.clone().requires_grad_(True)
-        s = torch.nn.functional.softplus(encode(xin, params) @ W)[:, 0]
+        s = torch.nn.functional.softplus(encode(xin, params) @ Wm)[:, 0]
         (dx,) = torch.autograd.grad(s, xin, torch.ones_like(s), create_graph=True)
         return (dx ** 2).sum() + s.sum()
 
-    from ngp_b200.tcnn import _GridFn
-    l1 = normals_loss(lambda xi, p: _GridFn.apply(xi, p, enc.grid), enc.params, x)
+    l1 = normals_loss(lambda xi, p: _GridFn.apply(xi, p, enc.grid), enc.params, x, W)
     (g1,) = torch.autograd.grad(l1, enc.params)
-    po = enc.params.detach().clone().double().requires_grad_(True)
-    W = W.double()
-    l2 = normals_loss(lambda xi, p: tcnn_oracle.grid_encode(xi, p, *args), po, x.double())
+    po = enc.params.detach().double().requires_grad_(True)
+    l2 = normals_loss(lambda xi, p: tcnn_oracle.grid_encode(xi, p, *args), po, x.double(), W.double())
     (g2,) = torch.autograd.grad(l2, po)
-    assert torch.allclose(l1.double(), l2, rtol=1e-4)
-    assert torch.allclose(g1.double(), g2, rtol=2e-3, atol=2e-4 * float(g2.abs().max()))
+    assert abs(float(l1) - float(l2)) <= 1e-4 * abs(float(l2))
+    assert rel(g1, g2) < 1e-3, rel(g1, g2)
 
 
 def test_sh4_and_sh3():
@@ -132,13 +153,17 @@ def test_mlp_backward(cfg):
     dy = torch.randn(n, n_out, device="cuda", generator=g)
     y = net(x)
     gx, gp = torch.autograd.grad(y, (x, net.params), dy)
+    # the forward operands are rounded to bf16 exactly as the kernel does (straight-through gradient), so
+    # both sides see the same ReLU masks; what remains is the bf16 rounding of the backward operands.
     xo = x.detach().clone().requires_grad_(True); po = net.params.detach().clone().requires_grad_(True)
-    yo = tcnn_oracle.mlp_forward(xo, po, n_in, width, nh, n_out, act, oact)
+    yo = tcnn_oracle.mlp_forward(xo, po, n_in, width, nh, n_out, act, oact, operand_dtype=torch.bfloat16)
     gxo, gpo = torch.autograd.grad(yo, (xo, po), dy)
-    # bf16 operands: compare in aggregate (relative L2) rather than elementwise
-    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))
-    assert rel(gx, gxo) < 2e-2, rel(gx, gxo)
-    assert rel(gp, gpo) < 2e-2, rel(gp, gpo)
+    assert rel(gx, gxo) < 1.5e-2, rel(gx, gxo)
+    assert rel(gp, gpo) < 1.5e-2, rel(gp, gpo)
+    # and against exact fp32 maths (mask flips near z=0 dominate: sqrt(fraction flipped))
+    yf = tcnn_oracle.mlp_forward(xo, po, n_in, width, nh, n_out, act, oact)
+    gxf, gpf = torch.autograd.grad(yf, (xo, po), dy)
+    assert rel(gx, gxf) < 8e-2 and rel(gp, gpf) < 8e-2, (rel(gx, gxf), rel(gp, gpf))
     pad = gp.numel() - (width * n_in + (nh - 1) * width * width + n_out * width)
     if pad:
         assert float(gp[-pad:].abs().max()) == 0.0          # padded output rows never receive gradient
@@ -162,4 +187,4 @@ def test_mlp_segments_fuse_sh_and_concat():
     ho = h.detach().clone().requires_grad_(True)
     yo = tcnn_oracle.mlp_forward(torch.cat([tcnn_oracle.sh_encode((d + 1) / 2, 4), ho], 1), net.params.detach(), 32, 64, 2, 3, "ReLU", "Sigmoid")
     (gho,) = torch.autograd.grad(yo, ho, dy)
-    assert float((gh - gho).norm() / gho.norm()) < 2e-2
+    assert float((gh - gho).norm() / gho.norm()) < 8e-2

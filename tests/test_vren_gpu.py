@@ -41,6 +41,9 @@ def N(t):
 
 def close(a, b, rtol=RTOL, atol=ATOL, frac=1.0):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    if a.size == 0:
+        return
     ok = np.abs(a - b) <= atol + rtol * np.abs(b)
     assert ok.mean() >= frac, f"mismatch frac {1 - ok.mean():.2e}, max abs {np.abs(a - b).max():.3e}"
 
