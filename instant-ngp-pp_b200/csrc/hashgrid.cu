@@ -127,42 +127,103 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
 }
 
 // ----------------------------------------------------------------------------------- bw (params)
-// dL/dtable[corner] += w_corner * dL/dy  (fp32 accumulation regardless of the table's storage type)
+// dL/dtable[corner] += w_corner * dL/dy  (fp32 accumulation regardless of the table's storage type).
+//
+// The scatter is bound by L2 atomic throughput (one red per corner per level per sample = 128 per
+// sample for L=16), so the kernel is organised to issue FEWER reds, not faster ones:
+//  * a thread owns SPT consecutive samples (consecutive samples of a ray are packed together, and at a
+//    level whose cells are wider than the marching step they fall into the same cell): contributions
+//    to the same cell are merged in registers and flushed once per run;
+//  * the two x-neighbours of a corner pair are adjacent entries whenever the lower index is even
+//    (always for hashed levels with even x: h(x+1) = h(x)^1), so for F=2 the pair goes out as ONE
+//    16-byte red.global.add.v4.f32 instead of two 8-byte ones;
+//  * exactly-zero upstream rows (samples past early termination) are skipped.
+constexpr int kSPT = 4;
+
+template <int F> struct CellAcc {
+  uint32_t px, py, pz;
+  bool has;
+  float a[8][F];
+};
+
 template <int F>
-__global__ void __launch_bounds__(256) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__device__ __forceinline__ void flush_cell(const CellAcc<F>& c, float* __restrict__ base, uint32_t res, uint32_t size, bool dense) {
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    const uint32_t i0 = grid_index(c.px, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+    const uint32_t i1 = grid_index(c.px + 1, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+    if constexpr (F == 2) {
+      if (i1 == i0 + 1 && (i0 & 1u) == 0) {
+        atomicAdd(reinterpret_cast<float4*>(base + (size_t)i0 * 2),
+                  make_float4(c.a[2 * p][0], c.a[2 * p][1], c.a[2 * p + 1][0], c.a[2 * p + 1][1]));
+        continue;
+      }
+    }
+    red_add<F>(base + (size_t)i0 * F, c.a[2 * p]);
+    red_add<F>(base + (size_t)i1 * F, c.a[2 * p + 1]);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable) {
   constexpr int LC = levels_per_thread<F>();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kSPT;
+  if (s0 >= n) return;
   const int l0 = blockIdx.y * LC;
-  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
   const int LF = m.n_levels * F;
-  const float* src = dy + i * LF + (int64_t)l0 * F;
-  float g[LC * F];
+  CellAcc<F> acc[LC];
 #pragma unroll
-  for (int k = 0; k < LC * F; k++) g[k] = (l0 * F + k < LF) ? __ldg(src + k) : 0.f;
+  for (int li = 0; li < LC; li++) acc[li].has = false;
+
+#pragma unroll 1
+  for (int j = 0; j < kSPT; j++) {
+    const int64_t i = s0 + j;
+    if (i >= n) break;
+    const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+    const float* src = dy + i * LF + (int64_t)l0 * F;
+    float g[LC * F];
+    if (l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0) {
 #pragma unroll
-  for (int li = 0; li < LC; li++) {
-    const int l = l0 + li;
-    if (l < m.n_levels) {
+      for (int k = 0; k < LC * F; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+        g[k] = v.x; g[k + 1] = v.y; g[k + 2] = v.z; g[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < LC * F; k++) g[k] = (l0 * F + k < LF) ? __ldg(src + k) : 0.f;
+    }
+#pragma unroll
+    for (int li = 0; li < LC; li++) {
+      const int l = l0 + li;
       bool any = false;
 #pragma unroll
       for (int f = 0; f < F; f++) any |= g[li * F + f] != 0.f;
-      if (!any) continue;  // samples past early termination carry exactly-zero gradients
-      const Cell c = locate(xx, xy, xz, m.scale[l]);
-      float* base = dtable + (size_t)m.offset[l] * F;
-      const uint32_t res = m.res[l], size = m.size[l];
-      const bool dense = m.dense[l];
+      if (l < m.n_levels && any) {
+        const Cell c = locate(xx, xy, xz, m.scale[l]);
+        CellAcc<F>& A = acc[li];
+        if (!A.has || A.px != c.px || A.py != c.py || A.pz != c.pz) {
+          if (A.has) flush_cell<F>(A, dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
+          A.px = c.px; A.py = c.py; A.pz = c.pz; A.has = true;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
-        const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
-        float v[F];
+          for (int k = 0; k < 8; k++)
 #pragma unroll
-        for (int f = 0; f < F; f++) v[f] = w * g[li * F + f];
-        red_add<F>(base + (size_t)idx * F, v);
+            for (int f = 0; f < F; f++) A.a[k][f] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+#pragma unroll
+          for (int f = 0; f < F; f++) A.a[k][f] = fmaf(w, g[li * F + f], A.a[k][f]);
+        }
       }
     }
+  }
+#pragma unroll
+  for (int li = 0; li < LC; li++) {
+    const int l = l0 + li;
+    if (l < m.n_levels && acc[li].has)
+      flush_cell<F>(acc[li], dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
   }
 }
 
@@ -346,8 +407,8 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_lev
     return set_error_msg("ngp_hashgrid_bw_params: bad grid config");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n_levels, LC));
-    hashgrid_bw_params_kernel<F><<<grid, 256, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable);
+    const dim3 grid((unsigned)ceil_div(ceil_div(n, kSPT), 128), (unsigned)ceil_div(n_levels, LC));
+    hashgrid_bw_params_kernel<F><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
   return 0;

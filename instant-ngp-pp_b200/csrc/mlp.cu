@@ -47,7 +47,7 @@ struct MlpCfg {
   int act_h, act_o;
   // shared-memory byte offsets
   uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]
-  uint32_t off_x, off_h[kMaxHidden], off_dz;
+  uint32_t off_x, off_h[kMaxHidden], off_dz, off_stg;
   uint32_t smem_bytes;
   // TMEM column offsets
   uint32_t tm_cols;                  // allocation (power of two)
@@ -90,30 +90,45 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
   o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
+// Operand tiles: layout of tc05.cuh with the chunk stride padded by 64 B (keeps 8-byte staging stores
+// at the 2-wavefront minimum): byte_offset(r,c) = (c/8)*CS(rows) + r*16 + (c%8)*2.
+__host__ __device__ __forceinline__ uint32_t chunk_stride(uint32_t rows) { return rows * 16u + 64u; }
+__device__ __forceinline__ uint32_t toff(uint32_t rows, uint32_t r, uint32_t c) {
+  return (c >> 3) * chunk_stride(rows) + r * 16u + (c & 7u) * 2u;
+}
 __device__ __forceinline__ void st_chunk(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, const float* v) {
   uint4 q;
   q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(tile + tile_off(rows, r, c)) = q;
+  *reinterpret_cast<uint4*>(tile + toff(rows, r, c)) = q;
+}
+__device__ __forceinline__ void st_quad(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, float4 v) {
+  uint2 q;
+  q.x = pack_bf16(v.x, v.y); q.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(tile + toff(rows, r, c)) = q;
 }
 __device__ __forceinline__ void ld_chunk(const uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, float* v) {
-  const uint4 q = *reinterpret_cast<const uint4*>(tile + tile_off(rows, r, c));
+  const uint4 q = *reinterpret_cast<const uint4*>(tile + toff(rows, r, c));
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 __device__ __forceinline__ void st_elem(uint8_t* tile, uint32_t rows, uint32_t r, uint32_t c, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(tile + tile_off(rows, r, c)) = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(tile + toff(rows, r, c)) = __float2bfloat16_rn(v);
 }
 
-// Thread t converts sample row `row` of every input segment to bf16 and writes tile row t.
-__device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, int64_t row, bool valid, uint32_t t,
+// All 128 threads stage rows [row0, row0+128) of every input segment as bf16 into the X tile.
+// Plain segments are read as a flat run of float4 units (consecutive threads -> consecutive 16-byte
+// units of the same row, then the next row: fully coalesced when stride == width), converted and
+// written with 8-byte stores; SH segments are evaluated by the row's owner thread.
+__device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, int64_t row0, int64_t n, uint32_t t,
                                             uint8_t* Xs) {
   int col = 0;
   for (int s = 0; s < c.n_seg; s++) {
     const int w = c.seg_w[s];
     if (c.seg_kind[s] == kSegSH4) {
+      const int64_t row = row0 + t;
       float o[16];
-      if (valid) {
+      if (row < n) {
         const float* d = in.p[s] + row * c.seg_stride[s];
         const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
         const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);  // F.normalize(eps=1e-6), networks.py:221
@@ -125,27 +140,52 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
       if ((col & 7) == 0) { st_chunk(Xs, kTile, t, col, o); st_chunk(Xs, kTile, t, col + 8, o + 8); }
       else { for (int i = 0; i < 16; i++) st_elem(Xs, kTile, t, col + i, o[i]); }
     } else {
-      const float* src = in.p[s] + row * c.seg_stride[s];
-      const bool vec = ((col & 7) == 0) && ((w & 7) == 0) && ((c.seg_stride[s] & 3) == 0) && ((((uintptr_t)in.p[s]) & 15) == 0);
+      const float* base = in.p[s];
+      const int64_t stride = c.seg_stride[s];
+      const bool vec = ((col & 3) == 0) && ((w & 3) == 0) && ((stride & 3) == 0) && ((((uintptr_t)base) & 15) == 0);
       if (vec) {
-        for (int j = 0; j < w; j += 8) {
-          float v[8];
-          if (valid) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + j)), b = __ldg(reinterpret_cast<const float4*>(src + j + 4));
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = 0.f;
-          }
-          st_chunk(Xs, kTile, t, col + j, v);
+        const int upr = w >> 2;                       // float4 units per row
+        for (int u = t; u < kTile * upr; u += kTile) {
+          const int r = u / upr, c4 = u - r * upr;
+          const int64_t row = row0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < n) v = __ldg(reinterpret_cast<const float4*>(base + row * stride) + c4);
+          st_quad(Xs, kTile, r, col + c4 * 4, v);
         }
       } else {
-        for (int j = 0; j < w; j++) st_elem(Xs, kTile, t, col + j, valid ? __ldg(src + j) : 0.f);
+        for (int u = t; u < kTile * w; u += kTile) {
+          const int r = u / w, cc = u - r * w;
+          const int64_t row = row0 + r;
+          st_elem(Xs, kTile, r, col + cc, row < n ? __ldg(base + row * stride + cc) : 0.f);
+        }
       }
     }
     col += w;
   }
-  for (; col < c.k0p; col++) st_elem(Xs, kTile, t, col, 0.f);
+  if (col < c.k0p) {
+    const int padw = c.k0p - col;
+    for (int u = t; u < kTile * padw; u += kTile) st_elem(Xs, kTile, u / padw, col + u % padw, 0.f);
+  }
+}
+
+// Coalesced copy-out of a [128 x ncols] fp32 panel held in the staging buffer (row pitch kStgPitch).
+constexpr int kStgPitch = 33;
+__device__ __forceinline__ void panel_store(const float* stg, int ncols_valid, int64_t row0, int64_t n, float* dst,
+                                            int64_t dst_stride, int dst_col0, uint32_t t) {
+  for (int u = t; u < kTile * ncols_valid; u += kTile) {
+    const int r = u / ncols_valid, cc = u - r * ncols_valid;
+    const int64_t row = row0 + r;
+    if (row < n) dst[row * dst_stride + dst_col0 + cc] = stg[r * kStgPitch + cc];
+  }
+}
+// Coalesced load of a [128 x ncols] fp32 panel into the staging buffer (zeros past n).
+__device__ __forceinline__ void panel_load(float* stg, int ncols_valid, int64_t row0, int64_t n, const float* src,
+                                           int64_t src_stride, int src_col0, uint32_t t) {
+  for (int u = t; u < kTile * ncols_valid; u += kTile) {
+    const int r = u / ncols_valid, cc = u - r * ncols_valid;
+    const int64_t row = row0 + r;
+    stg[r * kStgPitch + cc] = row < n ? __ldg(src + row * src_stride + src_col0 + cc) : 0.f;
+  }
 }
 
 // All threads: convert the fp32 parameter vector to bf16 operand tiles (zero padded).
@@ -170,8 +210,8 @@ __device__ __forceinline__ void stage_weights(const MlpCfg& c, const float* __re
 __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t b_rows, int N, int K) {
   const uint32_t id = idesc_bf16(kTile, N, 0, 0);
   for (int k = 0; k < K; k += 16) {
-    const uint64_t da = smem_desc(a_addr + (k >> 3) * (kTile * 16), kTile * 16, 128);
-    const uint64_t db = smem_desc(b_addr + (k >> 3) * (b_rows * 16), b_rows * 16, 128);
+    const uint64_t da = smem_desc(a_addr + (k >> 3) * chunk_stride(kTile), chunk_stride(kTile), 128);
+    const uint64_t db = smem_desc(b_addr + (k >> 3) * chunk_stride(b_rows), chunk_stride(b_rows), 128);
     mma_bf16(tmem_d, da, db, id, k > 0);
   }
 }
@@ -179,8 +219,8 @@ __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t w_rows, int N, int K) {
   const uint32_t id = idesc_bf16(kTile, N, 0, 1);
   for (int k = 0; k < K; k += 16) {
-    const uint64_t da = smem_desc(a_addr + (k >> 3) * (kTile * 16), kTile * 16, 128);
-    const uint64_t db = smem_desc(w_addr + k * 16, 128, w_rows * 16);   // LBO = next 8 rows(k), SBO = next 8 cols(n)
+    const uint64_t da = smem_desc(a_addr + (k >> 3) * chunk_stride(kTile), chunk_stride(kTile), 128);
+    const uint64_t db = smem_desc(w_addr + k * 16, 128, chunk_stride(w_rows));   // LBO = next 8 rows(k), SBO = next 8 cols(n)
     mma_bf16(tmem_d, da, db, id, k > 0);
   }
 }
@@ -188,8 +228,8 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_addr, ui
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t p_addr, uint32_t q_addr, int M, int N, bool accumulate) {
   const uint32_t id = idesc_bf16(M, N, 1, 1);
   for (int k = 0; k < kTile; k += 16) {
-    const uint64_t da = smem_desc(p_addr + k * 16, 128, kTile * 16);
-    const uint64_t db = smem_desc(q_addr + k * 16, 128, kTile * 16);
+    const uint64_t da = smem_desc(p_addr + k * 16, 128, chunk_stride(kTile));
+    const uint64_t db = smem_desc(q_addr + k * 16, 128, chunk_stride(kTile));
     mma_bf16(tmem_d, da, db, id, accumulate || k > 0);
   }
 }
@@ -240,12 +280,12 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
   const uint32_t trow = cx.tmem + ((warp * 32u) << 16);        // this warp's lanes
   uint8_t* Xs = smem + c.off_x;
   uint8_t* Hs = smem + c.off_h[0];
+  float* stg = reinterpret_cast<float*>(smem + c.off_stg);
   const int64_t n_tiles = (n + kTile - 1) / kTile;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * kTile + t;
-    const bool valid = row < n;
-    stage_input(c, in, row, valid, t, Xs);
+    const int64_t row0 = tile * kTile;
+    stage_input(c, in, row0, n, t, Xs);
     publish();
     for (int l = 0; l <= c.nh; l++) {
       const bool last = l == c.nh;
@@ -266,18 +306,22 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
           st_chunk(Hs, kTile, t, c0, v);
           st_chunk(Hs, kTile, t, c0 + 8, v + 8);
         }
+        publish();
       } else {
-        for (int c0 = 0; c0 < c.nop; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + c0, v);
-          if (valid) {
+        // output: TMEM -> registers -> activation -> fp32 staging panel -> coalesced global stores
+        for (int p0 = 0; p0 < c.no; p0 += 32) {
+          for (int c0 = p0; c0 < p0 + 32 && c0 < c.nop; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-              if (c0 + i < c.no) out[row * out_stride + c0 + i] = act_apply(c.act_o, v[i]);
+            for (int i = 0; i < 16; i++) stg[t * kStgPitch + (c0 - p0) + i] = act_apply(c.act_o, v[i]);
           }
+          fence_before_sync();
+          __syncthreads();
+          panel_store(stg, min(32, c.no - p0), row0, n, out, out_stride, p0, t);
+          __syncthreads();
         }
       }
-      publish();
     }
   }
   cta_teardown(cx, c.tm_cols);
@@ -297,15 +341,15 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
   const uint32_t trow = cx.tmem + ((warp * 32u) << 16);
   uint8_t* Xs = smem + c.off_x;
   uint8_t* dZ = smem + c.off_dz;
+  float* stg = reinterpret_cast<float*>(smem + c.off_stg);
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   bool have_wgrad = false;
   bool want_dx = false;
   for (int s = 0; s < c.n_seg; s++) want_dx |= dseg.p[s] != nullptr;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * kTile + t;
-    const bool valid = row < n;
-    stage_input(c, in, row, valid, t, Xs);
+    const int64_t row0 = tile * kTile;
+    stage_input(c, in, row0, n, t, Xs);
     publish();
     // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
     for (int l = 0; l < c.nh; l++) {
@@ -314,6 +358,8 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
         issue_fwd(tacc, sbase + (l == 0 ? c.off_x : c.off_h[l - 1]), sbase + c.off_w[l], (uint32_t)c.wp, c.wp, l == 0 ? c.k0p : c.wp);
         mma_commit(cx.bar);
       }
+      // overlap the (coalesced) load of this tile's upstream gradient with the first MMA
+      if (l == 0) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
       wait_mma(cx);
       uint8_t* H = smem + c.off_h[l];
       for (int c0 = 0; c0 < c.wp; c0 += 16) {
@@ -333,20 +379,27 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
       mma_commit(cx.bar);
     }
     wait_mma(cx);
-    for (int c0 = 0; c0 < c.nop; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + c0, v);
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        float g = 0.f;
-        if (valid && c0 + i < c.no) {
-          const float y = act_apply(c.act_o, v[i]);
-          g = __ldg(dout + row * dout_stride + c0 + i) * act_grad_from_out(c.act_o, y);
-        }
-        v[i] = g;
+    for (int p0 = 0; p0 < c.nop; p0 += 32) {
+      if (p0 > 0) {     // n_out > 32: bring in the next 32 columns of dL/dy (panel 0 was loaded under the first MMA)
+        __syncthreads();
+        panel_load(stg, min(32, c.no - p0), row0, n, dout, dout_stride, p0, t);
+        __syncthreads();
       }
-      st_chunk(dZ, kTile, t, c0, v);
-      st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+      for (int c0 = p0; c0 < p0 + 32 && c0 < c.nop; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          float g = 0.f;
+          if (c0 + i < c.no) {
+            const float y = act_apply(c.act_o, v[i]);
+            g = stg[t * kStgPitch + (c0 - p0) + i] * act_grad_from_out(c.act_o, y);
+          }
+          v[i] = g;
+        }
+        st_chunk(dZ, kTile, t, c0, v);
+        st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+      }
     }
     publish();
     // ---- top-down: wgrad + dgrad per layer
@@ -376,27 +429,32 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
           st_chunk(dZ, kTile, t, c0, v);
           st_chunk(dZ, kTile, t, c0 + 8, v + 8);
         }
-      } else if (want_dx) {
-        int col = 0;
-        for (int s = 0; s < c.n_seg; s++) {
-          const int w = c.seg_w[s];
-          float* dst = dseg.p[s];
-          // columns [col, col+w) of the accumulator belong to this segment
-          for (int c0 = (col / 16) * 16; c0 < col + w; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + c0, v);
-            if (dst && valid) {
+        publish();
+      } else {
+        if (want_dx) {
+          // input gradient: 32-column panels through the staging buffer, coalesced per segment
+          for (int p0 = 0; p0 < c.k0; p0 += 32) {
+            for (int c0 = p0; c0 < p0 + 32 && c0 < c.k0p; c0 += 16) {
+              float v[16];
+              tmem_ld16(trow + c0, v);
 #pragma unroll
-              for (int i = 0; i < 16; i++) {
-                const int cc = c0 + i;
-                if (cc >= col && cc < col + w) dst[row * dseg.stride[s] + (cc - col)] = v[i];
-              }
+              for (int i = 0; i < 16; i++) stg[t * kStgPitch + (c0 - p0) + i] = v[i];
             }
+            fence_before_sync();
+            __syncthreads();
+            int col = 0;
+            for (int s = 0; s < c.n_seg; s++) {
+              const int w = c.seg_w[s];
+              const int lo = max(col, p0), hi = min(col + w, p0 + 32);     // overlap of this segment with the panel
+              if (dseg.p[s] && lo < hi)
+                panel_store(stg + (lo - p0), hi - lo, row0, n, dseg.p[s], dseg.stride[s], lo - col, t);
+              col += w;
+            }
+            __syncthreads();
           }
-          col += w;
         }
+        publish();
       }
-      publish();
     }
     have_wgrad = true;
   }
@@ -443,20 +501,22 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   c.wp = c.w <= 64 ? 64 : 128;
   c.nop = (c.no + 15) / 16 * 16;
   auto al = [](uint32_t x) { return (x + 127u) / 128u * 128u; };
+  auto tile_bytes = [](int rows, int cols) { return (uint32_t)(cols / 8) * chunk_stride((uint32_t)rows); };
   uint32_t off = 128;  // mbarrier + tmem slot
   int64_t poff = 0;
   for (int l = 0; l <= c.nh; l++) {
     const int rows_t = l == c.nh ? c.nop : c.wp, cols_t = l == 0 ? c.k0p : c.wp;
-    c.off_w[l] = off; off += al(rows_t * cols_t * 2);
+    c.off_w[l] = off; off += al(tile_bytes(rows_t, cols_t));
     c.p_off[l] = poff;
     poff += (int64_t)(l == c.nh ? c.nop : c.w) * (l == 0 ? c.k0 : c.w);
   }
-  c.off_x = off; off += al(kTile * c.k0p * 2);
+  c.off_x = off; off += al(tile_bytes(kTile, c.k0p));
   const int n_h = backward ? c.nh : 1;
-  for (int l = 0; l < n_h; l++) { c.off_h[l] = off; off += al(kTile * c.wp * 2); }
+  for (int l = 0; l < n_h; l++) { c.off_h[l] = off; off += al(tile_bytes(kTile, c.wp)); }
   for (int l = n_h; l < kMaxHidden; l++) c.off_h[l] = c.off_h[0];
   c.off_dz = off;
-  if (backward) off += al(kTile * (c.wp > c.nop ? c.wp : c.nop) * 2);
+  if (backward) off += al(tile_bytes(kTile, c.wp > c.nop ? c.wp : c.nop));
+  c.off_stg = off; off += al(kTile * kStgPitch * 4);
   c.smem_bytes = off;
   uint32_t cols = (uint32_t)c.wp;
   if ((uint32_t)c.nop > cols) cols = c.nop;
