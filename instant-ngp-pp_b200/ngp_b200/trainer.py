@@ -13,15 +13,21 @@ import torch
 import torch.distributed as dist
 
 from .losses import NeRFLoss
+from .optim import FusedAdam
 from .rendering import render
 
 
 class Trainer:
     def __init__(self, model, lr=1e-2, eps=1e-15, update_interval=16, warmup_steps=256, density_threshold=0.01 * 1024 / 3 ** 0.5,
-                 lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1):
+                 lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1, max_grad_norm=None):
         self.model = model
         self.loss_fn = NeRFLoss(lambda_opa=lambda_opa, lambda_distortion=lambda_distortion)
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, eps=eps)     # train.py:244 (eps=1e-15 as ngp_pl)
+        params = [p for p in model.parameters() if p.numel() > 0]
+        on_gpu = len(params) > 0 and params[0].is_cuda
+        # train.py:244-251,435: Adam + global-norm clip, fused (device-resident clip coefficient, 1/world averaging)
+        self.opt = (FusedAdam(params, lr=lr, eps=eps, max_grad_norm=max_grad_norm, grad_scale=1.0 / world_size) if on_gpu
+                    else torch.optim.Adam(params, lr=lr, eps=eps))
+        self.fused = on_gpu
         self.update_interval, self.warmup_steps = update_interval, warmup_steps
         self.density_threshold = density_threshold
         self.render_kwargs = dict(render_kwargs or {})
@@ -37,8 +43,9 @@ class Trainer:
         works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
         for w in works:
             w.wait()
-        for p in ps:
-            p.grad.div_(self.world_size)
+        if not self.fused:                     # the fused optimiser folds 1/world_size into its gradient scale
+            for p in ps:
+                p.grad.div_(self.world_size)
 
     def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True):
         """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count."""
