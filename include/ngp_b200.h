@@ -141,15 +141,16 @@ int ngp_sh_fw(const float* v, int degree, int64_t n, float* out, void* stream);
 /* ------------------------------------------------------------------ a12: fused MLP (tcgen05/TMEM)
  * tcnn.Network(n_in, n_out, {"otype":"CutlassMLP", ...})  models/networks.py:89-162
  * Input = concatenation of up to 3 segments (kind 0: fp32 rows; kind 1: SH4 of normalised dirs).
- * Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp. */
+ * Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.  aux_exp_out / dL_daux_exp (optional): the density head
+ * sigma = TruncExp(out[:,0]) of the ngp_pl-shaped field (custom_functions.py:200-211) fused into the epilogues. */
 int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_out);
 int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out, int act_hidden,
-               int act_out, int64_t n, float* out, int64_t out_stride, void* stream);
+               int act_out, int64_t n, float* out, int64_t out_stride, float* aux_exp_out, void* stream);
 int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out, int act_hidden,
                int act_out, int64_t n, const float* dL_dout, int64_t dout_stride, float* dparams,
-               float* const* dseg_ptr, const int64_t* dseg_stride, void* stream);
+               float* const* dseg_ptr, const int64_t* dseg_stride, const float* dL_daux_exp, void* stream);
 
 /* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
  * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */

@@ -48,6 +48,9 @@ struct MlpCfg {
   // shared-memory byte offsets
   uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]
   uint32_t off_x, off_h[kMaxHidden], off_dz, off_stg;
+  // raw fp32 landing zone of the next tile (bulk copies): per segment, then dL/dy (backward)
+  uint32_t off_raw[kMaxSeg], off_raw_dout, raw_bytes[kMaxSeg], raw_dout_bytes;
+  int bulk, bulk_dout;             // set by the host when every segment (resp. dL/dy) is contiguous + 16-B aligned
   uint32_t smem_bytes;
   // TMEM column offsets
   uint32_t tm_cols;                  // allocation (power of two)
@@ -188,6 +191,55 @@ __device__ __forceinline__ void panel_load(float* stg, int ncols_valid, int64_t 
   }
 }
 
+// ---- next-tile prefetch: one thread arms `full` and fires one bulk copy per segment (+ dL/dy) ------
+__device__ __forceinline__ bool tile_is_bulk(const MlpCfg& c, int64_t tile, int64_t n) {
+  return c.bulk && (tile + 1) * kTile <= n;
+}
+__device__ __forceinline__ void issue_prefetch(const MlpCfg& c, const SegPtrs& in, const float* dout, int64_t tile,
+                                               uint8_t* smem, uint64_t* full) {
+  const int64_t row0 = tile * kTile;
+  uint32_t total = 0;
+  for (int s = 0; s < c.n_seg; s++) total += c.raw_bytes[s];
+  if (c.bulk_dout && dout) total += c.raw_dout_bytes;
+  mbar_expect_tx(full, total);
+  for (int s = 0; s < c.n_seg; s++)
+    bulk_g2s(smem + c.off_raw[s], in.p[s] + row0 * c.seg_stride[s], c.raw_bytes[s], full);
+  if (c.bulk_dout && dout) bulk_g2s(smem + c.off_raw_dout, dout + row0 * c.no, c.raw_dout_bytes, full);
+}
+// All threads: raw fp32 landing zone -> bf16 operand tile (flat, conflict-free 16-byte smem reads).
+__device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem, uint32_t t, uint8_t* Xs) {
+  int col = 0;
+  for (int s = 0; s < c.n_seg; s++) {
+    const int w = c.seg_w[s];
+    const float* raw = reinterpret_cast<const float*>(smem + c.off_raw[s]);
+    if (c.seg_kind[s] == kSegSH4) {
+      const float dx = raw[3 * t], dy = raw[3 * t + 1], dz = raw[3 * t + 2];
+      const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
+      float o[16];
+      sh4(dx * inv, dy * inv, dz * inv, o);
+      if ((col & 7) == 0) { st_chunk(Xs, kTile, t, col, o); st_chunk(Xs, kTile, t, col + 8, o + 8); }
+      else { for (int i = 0; i < 16; i++) st_elem(Xs, kTile, t, col + i, o[i]); }
+    } else if (((col | w) & 3) == 0) {
+      const int upr = w >> 2, total = kTile * upr;
+#pragma unroll 4
+      for (int u = t; u < total; u += kTile) {
+        const int r = u / upr, c4 = u - r * upr;
+        st_quad(Xs, kTile, r, col + c4 * 4, reinterpret_cast<const float4*>(raw)[u]);
+      }
+    } else {
+      for (int u = t; u < kTile * w; u += kTile) st_elem(Xs, kTile, u / w, col + u % w, raw[u]);
+    }
+    col += w;
+  }
+}
+// All threads: zero the padding columns [k0, k0p) of the X tile once (segments never touch them).
+__device__ __forceinline__ void zero_pad_cols(const MlpCfg& c, uint32_t t, uint8_t* Xs) {
+  if (c.k0 < c.k0p) {
+    const int padw = c.k0p - c.k0;
+    for (int u = t; u < kTile * padw; u += kTile) st_elem(Xs, kTile, u / padw, c.k0 + u % padw, 0.f);
+  }
+}
+
 // All threads: convert the fp32 parameter vector to bf16 operand tiles (zero padded).
 __device__ __forceinline__ void stage_weights(const MlpCfg& c, const float* __restrict__ params, uint8_t* smem) {
   for (int l = 0; l <= c.nh; l++) {
@@ -235,14 +287,15 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t p_addr, ui
 }
 
 struct CtaCtx {
-  uint64_t* bar; uint32_t* tmem_slot; uint32_t tmem; uint32_t phase;
+  uint64_t* bar; uint64_t* full; uint32_t* tmem_slot; uint32_t tmem; uint32_t phase; uint32_t fphase;
 };
 
 __device__ __forceinline__ void cta_setup(CtaCtx& x, uint8_t* smem, uint32_t tm_cols) {
   x.bar = reinterpret_cast<uint64_t*>(smem);
-  x.tmem_slot = reinterpret_cast<uint32_t*>(smem + 8);
-  x.phase = 0;
-  if (threadIdx.x == 0) { mbar_init(x.bar, 1); mbar_fence_init(); }
+  x.full = reinterpret_cast<uint64_t*>(smem + 8);
+  x.tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+  x.phase = 0; x.fphase = 0;
+  if (threadIdx.x == 0) { mbar_init(x.bar, 1); mbar_init(x.full, 1); mbar_fence_init(); }
   if (threadIdx.x < 32) { __syncwarp(); tmem_alloc(x.tmem_slot, tm_cols); }
   fence_before_sync();
   __syncthreads();
@@ -268,8 +321,11 @@ __device__ __forceinline__ void publish() {
 }
 
 // =============================================================================== forward kernel
+// aux_exp (optional): aux_exp[row] = exp(z_out[row][0]) — the density head of the ngp_pl-shaped field
+// (sigma = TruncExp(h[:,0])) produced by the same epilogue instead of a strided select + exp pass.
 __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
-                                                       float* __restrict__ out, int64_t out_stride) {
+                                                       float* __restrict__ out, int64_t out_stride,
+                                                       float* __restrict__ aux_exp) {
   extern __shared__ __align__(128) uint8_t smem[];
   CtaCtx cx;
   cta_setup(cx, smem, c.tm_cols);
@@ -283,10 +339,17 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
   float* stg = reinterpret_cast<float*>(smem + c.off_stg);
   const int64_t n_tiles = (n + kTile - 1) / kTile;
 
+  zero_pad_cols(c, t, Xs);
+  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, nullptr, blockIdx.x, smem, cx.full);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
-    stage_input(c, in, row0, n, t, Xs);
+    if (tile_is_bulk(c, tile, n)) { mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1; convert_raw(c, smem, t, Xs); }
+    else stage_input(c, in, row0, n, t, Xs);
     publish();
+    {   // the landing zone is free again: fetch the next tile while this one is computed
+      const int64_t nxt = tile + gridDim.x;
+      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, nullptr, nxt, smem, cx.full);
+    }
     for (int l = 0; l <= c.nh; l++) {
       const bool last = l == c.nh;
       const int N = last ? c.nop : c.wp;
@@ -313,6 +376,7 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
           for (int c0 = p0; c0 < p0 + 32 && c0 < c.nop; c0 += 16) {
             float v[16];
             tmem_ld16(trow + c0, v);
+            if (aux_exp && c0 == 0 && row0 + t < n) aux_exp[row0 + t] = __expf(v[0]);
 #pragma unroll
             for (int i = 0; i < 16; i++) stg[t * kStgPitch + (c0 - p0) + i] = act_apply(c.act_o, v[i]);
           }
@@ -330,7 +394,8 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
 // =============================================================================== backward kernel
 __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
                                                        const float* __restrict__ dout, int64_t dout_stride,
-                                                       float* __restrict__ dparams, SegGrads dseg) {
+                                                       float* __restrict__ dparams, SegGrads dseg,
+                                                       const float* __restrict__ d_aux_exp) {
   extern __shared__ __align__(128) uint8_t smem[];
   CtaCtx cx;
   cta_setup(cx, smem, c.tm_cols);
@@ -347,10 +412,27 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
   bool want_dx = false;
   for (int s = 0; s < c.n_seg; s++) want_dx |= dseg.p[s] != nullptr;
 
+  zero_pad_cols(c, t, Xs);
+  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, dout, blockIdx.x, smem, cx.full);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
-    stage_input(c, in, row0, n, t, Xs);
+    const bool bulk = tile_is_bulk(c, tile, n);
+    if (bulk) {
+      mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1;
+      convert_raw(c, smem, t, Xs);
+      if (c.bulk_dout) {                                    // dL/dy rows -> staging panel (pitch 33)
+        const float* rd = reinterpret_cast<const float*>(smem + c.off_raw_dout);
+        for (int u = t; u < kTile * c.no; u += kTile) stg[(u / c.no) * kStgPitch + u % c.no] = rd[u];
+      }
+    } else {
+      stage_input(c, in, row0, n, t, Xs);
+    }
+    const bool dout_staged = bulk && c.bulk_dout;
     publish();
+    {
+      const int64_t nxt = tile + gridDim.x;
+      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, dout, nxt, smem, cx.full);
+    }
     // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
     for (int l = 0; l < c.nh; l++) {
       if (t == 0) {
@@ -359,7 +441,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
         mma_commit(cx.bar);
       }
       // overlap the (coalesced) load of this tile's upstream gradient with the first MMA
-      if (l == 0) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
+      if (l == 0 && !dout_staged) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
       wait_mma(cx);
       uint8_t* H = smem + c.off_h[l];
       for (int c0 = 0; c0 < c.wp; c0 += 16) {
@@ -394,6 +476,8 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
           if (c0 + i < c.no) {
             const float y = act_apply(c.act_o, v[i]);
             g = stg[t * kStgPitch + (c0 - p0) + i] * act_grad_from_out(c.act_o, y);
+            // TruncExp backward of the density head: g * exp(clamp(z, -7, 7))  (custom_functions.py:211)
+            if (d_aux_exp && c0 + i == 0 && row0 + t < n) g = fmaf(__ldg(d_aux_exp + row0 + t), __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
           }
           v[i] = g;
         }
@@ -517,6 +601,16 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   c.off_dz = off;
   if (backward) off += al(tile_bytes(kTile, c.wp > c.nop ? c.wp : c.nop));
   c.off_stg = off; off += al(kTile * kStgPitch * 4);
+  // raw landing zone (optional: dropped when it does not fit)
+  if (c.bulk) {
+    uint32_t o2 = off;
+    for (int s = 0; s < c.n_seg; s++) {
+      c.raw_bytes[s] = (uint32_t)(kTile * (c.seg_kind[s] == kSegSH4 ? 3 : c.seg_w[s]) * 4);
+      c.off_raw[s] = o2; o2 += al(c.raw_bytes[s]);
+    }
+    if (backward && c.bulk_dout) { c.raw_dout_bytes = (uint32_t)(kTile * c.no * 4); c.off_raw_dout = o2; o2 += al(c.raw_dout_bytes); }
+    if (o2 <= 227 * 1024) off = o2; else { c.bulk = 0; c.bulk_dout = 0; }
+  } else c.bulk_dout = 0;
   c.smem_bytes = off;
   uint32_t cols = (uint32_t)c.wp;
   if ((uint32_t)c.nop > cols) cols = c.nop;
@@ -533,12 +627,19 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   return 0;
 }
 
-static int build_cfg(MlpCfg& c, int n_seg, const int* seg_w, const int* seg_kind, const int64_t* seg_stride, int width,
-                     int n_hidden, int n_out, int act_hidden, int act_out, bool backward) {
+static int build_cfg(MlpCfg& c, int n_seg, const float* const* seg_ptr, const int* seg_w, const int* seg_kind,
+                     const int64_t* seg_stride, int width, int n_hidden, int n_out, int act_hidden, int act_out,
+                     bool backward, const float* dout, int64_t dout_stride) {
   memset(&c, 0, sizeof(c));
   c.n_seg = n_seg;
   for (int s = 0; s < n_seg && s < kMaxSeg; s++) { c.seg_w[s] = seg_w[s]; c.seg_kind[s] = seg_kind[s]; c.seg_stride[s] = seg_stride[s]; }
   c.w = width; c.nh = n_hidden; c.no = n_out; c.act_h = act_hidden; c.act_o = act_out;
+  c.bulk = 1;
+  for (int s = 0; s < n_seg && s < kMaxSeg; s++) {
+    const int raw_w = seg_kind[s] == kSegSH4 ? 3 : seg_w[s];
+    if (seg_stride[s] != raw_w || (((uintptr_t)seg_ptr[s]) & 15) != 0) c.bulk = 0;
+  }
+  c.bulk_dout = (dout != nullptr && dout_stride == n_out && n_out <= 32 && (((uintptr_t)dout) & 15) == 0) ? 1 : 0;
   return finalize_cfg(c, backward);
 }
 
@@ -567,19 +668,21 @@ NGP_API int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_
 
 // out (N, n_out) = MLP(cat(segments)).  Segment kinds: 0 = fp32 rows of seg_width floats at
 // seg_ptr + row*seg_stride; 1 = degree-4 SH of the normalised (N,3) direction at seg_ptr (width 16).
-// Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.
+// Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.  aux_exp_out (optional, N floats) = exp(out[:,0]) taken
+// before the output activation (the ngp_pl density head).
 NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                        const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
-                       int act_hidden, int act_out, int64_t n, float* out, int64_t out_stride, void* stream) {
+                       int act_hidden, int act_out, int64_t n, float* out, int64_t out_stride, float* aux_exp_out,
+                       void* stream) {
   if (n <= 0) return 0;
   MlpCfg c;
-  const int rc = build_cfg(c, n_seg, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, false);
+  const int rc = build_cfg(c, n_seg, seg_ptr, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, false, nullptr, 0);
   if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_fw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
   SegPtrs in; for (int s = 0; s < kMaxSeg; s++) in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
   cudaError_t e = cudaFuncSetAttribute(mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
   if (e != cudaSuccess) return set_error(e, "ngp_mlp_fw/attr");
   const int grid = launch_grid((const void*)mlp_fw_kernel, c, n);
-  mlp_fw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, out, out_stride);
+  mlp_fw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, out, out_stride, aux_exp_out);
   NGP_LAUNCH_CHECK("ngp_mlp_fw");
   return 0;
 }
@@ -590,10 +693,11 @@ NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_wi
 NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                        const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
                        int act_hidden, int act_out, int64_t n, const float* dL_dout, int64_t dout_stride,
-                       float* dparams, float* const* dseg_ptr, const int64_t* dseg_stride, void* stream) {
+                       float* dparams, float* const* dseg_ptr, const int64_t* dseg_stride, const float* dL_daux_exp,
+                       void* stream) {
   if (n <= 0) return 0;
   MlpCfg c;
-  const int rc = build_cfg(c, n_seg, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, true);
+  const int rc = build_cfg(c, n_seg, seg_ptr, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, true, dL_dout, dout_stride);
   if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_bw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
   SegPtrs in; SegGrads dg;
   for (int s = 0; s < kMaxSeg; s++) {
@@ -604,7 +708,7 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   cudaError_t e = cudaFuncSetAttribute(mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
   if (e != cudaSuccess) return set_error(e, "ngp_mlp_bw/attr");
   const int grid = launch_grid((const void*)mlp_bw_kernel, c, n);
-  mlp_bw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, dL_dout, dout_stride, dparams, dg);
+  mlp_bw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp);
   NGP_LAUNCH_CHECK("ngp_mlp_bw");
   return 0;
 }

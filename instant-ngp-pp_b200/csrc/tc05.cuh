@@ -57,6 +57,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// producer side of a bulk-copy transaction: one arrival + `bytes` expected through complete_tx
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (no tensor map needed for contiguous runs);
+// completion is signalled on `bar` as transaction bytes.  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // arrive on `bar` once every tcgen05.mma issued so far by this thread has completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -87,6 +87,44 @@ class VolumeRenderer(torch.autograd.Function):
         return d_sig, d_rgb, d_nrm, d_sem, None, None, None, None, None
 
 
+class VolumeRendererLite(torch.autograd.Function):
+    """VolumeRenderer for fields without normal / semantic heads (the ngp_pl-shaped BASELINE model):
+    same compositor kernels with the normal and semantic streams switched off (NULL pointers).
+    forward(sigmas, rgbs, deltas, ts, rays_a, T_threshold) -> total_samples, opacity, depth, rgb, ws"""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, deltas, ts, rays_a, T_threshold):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        S, R = sigmas.shape[0], rays_a.shape[0]
+        dev = sigmas.device
+        total = torch.empty(R, dtype=torch.int64, device=dev)
+        opacity = torch.empty(R, dtype=torch.float32, device=dev)
+        depth = torch.empty(R, dtype=torch.float32, device=dev)
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        ws = torch.empty(S, dtype=torch.float32, device=dev)
+        check(lib.ngp_composite_train_fw(ptr(sigmas), ptr(rgbs), None, None, ptr(deltas), ptr(ts), ptr(rays_a),
+                                         float(T_threshold), 0, S, R, ptr(total), ptr(opacity), ptr(depth), ptr(rgb), None,
+                                         None, ptr(ws), stream()), "composite_train_fw")
+        ctx.save_for_backward(sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, ws)
+        ctx.T_threshold = T_threshold
+        return total.sum(), opacity, depth, rgb, ws
+
+    @staticmethod
+    def backward(ctx, g_total, g_opacity, g_depth, g_rgb, g_ws):
+        from ._lib import lib, ptr, check, stream
+        sigmas, rgbs, deltas, ts, rays_a, opacity, depth, rgb, ws = ctx.saved_tensors
+        S, R = sigmas.shape[0], rays_a.shape[0]
+        d_sig = torch.empty_like(sigmas)
+        d_rgb = torch.empty_like(rgbs)
+        check(lib.ngp_composite_train_bw(ptr(g_opacity.contiguous()), ptr(g_depth.contiguous()), ptr(g_rgb.contiguous()), None,
+                                         None, ptr(g_ws.contiguous()), ptr(sigmas), ptr(rgbs), ptr(ws), ptr(deltas), ptr(ts),
+                                         ptr(rays_a), ptr(opacity), ptr(depth), ptr(rgb), float(ctx.T_threshold), 0, S, R,
+                                         ptr(d_sig), ptr(d_rgb), None, None, stream()), "composite_train_bw")
+        return d_sig, d_rgb, None, None, None, None
+
+
 class RefLoss(torch.autograd.Function):
     """Composited Ref-NeRF normal losses: forward(sigmas, normals_diff (S,3), normals_ori (S), deltas,
     ts, rays_a, T_threshold) -> loss_o (R), loss_p (R,3).  No gradient reaches sigmas

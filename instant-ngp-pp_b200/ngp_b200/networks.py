@@ -262,21 +262,23 @@ class NGPCompact(nn.Module, _OccupancyMixin):
     def _normalise(self, x):
         return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
 
+    has_normals = False     # no normal / semantic heads: the renderer takes the lite compositor path
+
     def density(self, x, return_feat=False):
-        h = self.sigma_net(self.xyz_encoder(self._normalise(x)))
-        sigmas = TruncExp.apply(h[:, 0])
+        h, sigmas = self.sigma_net.forward_density_head(self.xyz_encoder(self._normalise(x)))
         return (sigmas, h) if return_feat else sigmas
 
     def forward(self, x, d, **kwargs):
+        """-> sigmas (N), rgbs (N,3), None, None, None (no normal / semantic heads)."""
         sigmas, h = self.density(x, return_feat=True)
         rgbs = self.rgb_net.forward_segments([d, h], [1, 0])
-        zeros3 = torch.zeros(x.shape[0], 3, device=x.device)
-        return sigmas, rgbs, zeros3, zeros3, torch.zeros(x.shape[0], self.classes, device=x.device)
+        return sigmas, rgbs, None, None, None
 
     def forward_test(self, x, d, **kwargs):
         with torch.no_grad():
-            sigmas, rgbs, n_raw, n_pred, sem = self.forward(x, d, **kwargs)
-        return sigmas, rgbs, n_pred, n_raw, sem
+            sigmas, rgbs, _, _, _ = self.forward(x, d, **kwargs)
+        z3 = torch.zeros(x.shape[0], 3, device=x.device)
+        return sigmas, rgbs, z3, z3, torch.zeros(x.shape[0], kwargs.get("num_classes", self.classes), device=x.device)
 
     def forward_skybox(self, d):
         return None

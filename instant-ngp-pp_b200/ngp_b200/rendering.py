@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from . import vren
-from .custom_functions import RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer
+from .custom_functions import RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer, VolumeRendererLite
 
 MAX_SAMPLES = 1024      # models/rendering.py:9
 NEAR_DISTANCE = 0.01    # models/rendering.py:10
@@ -131,11 +131,16 @@ def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
             kw[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0, output_size=xyzs.shape[0])
     sigmas, rgbs, normals_raw, normals_pred, sems = model(xyzs, dirs, **kw)
     results["sigma"], results["xyzs"] = sigmas, xyzs
+    lite = normals_pred is None          # field without normal / semantic heads (NGPCompact)
 
-    (results["vr_samples"], results["opacity"], results["depth"], results["rgb"], results["normal_pred"],
-     results["semantic"], results["ws"]) = VolumeRenderer.apply(
-        sigmas.contiguous(), rgbs.contiguous(), normals_pred.contiguous(), sems.contiguous(), results["deltas"],
-        results["ts"], rays_a, T_thr, classes)
+    if lite:
+        results["vr_samples"], results["opacity"], results["depth"], results["rgb"], results["ws"] = \
+            VolumeRendererLite.apply(sigmas.contiguous(), rgbs.contiguous(), results["deltas"], results["ts"], rays_a, T_thr)
+    else:
+        (results["vr_samples"], results["opacity"], results["depth"], results["rgb"], results["normal_pred"],
+         results["semantic"], results["ws"]) = VolumeRenderer.apply(
+            sigmas.contiguous(), rgbs.contiguous(), normals_pred.contiguous(), sems.contiguous(), results["deltas"],
+            results["ts"], rays_a, T_thr, classes)
 
     if kwargs.get("use_skybox", False):
         rgb_bg = model.forward_skybox(rays_d)
@@ -145,6 +150,8 @@ def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
         rgb_bg = torch.zeros(3, device=rays_o.device)
     results["rgb"] = results["rgb"] + rgb_bg * (1 - results["opacity"])[:, None]
 
+    if lite:
+        return results
     # Ref-NeRF regularisers (rendering.py:243-249)
     normals_diff = (normals_raw - normals_pred) ** 2
     view = F.normalize(dirs, p=2, dim=-1, eps=1e-6)

@@ -200,17 +200,19 @@ def _seg_arrays(segs):
     return P, W, K, S
 
 
-def mlp_forward(segs, params, m: MlpConfig):
-    """segs: [(tensor (N,w) fp32 | dirs (N,3), width, kind)]; kind 0 plain, 1 SH4-of-normalised-dirs."""
+def mlp_forward(segs, params, m: MlpConfig, aux_exp=False):
+    """segs: [(tensor (N,w) fp32 | dirs (N,3), width, kind)]; kind 0 plain, 1 SH4-of-normalised-dirs.
+    aux_exp=True additionally returns exp(out[:,0]) (N) from the same epilogue."""
     n = segs[0][0].shape[0]
     out = torch.empty(n, m.n_out, dtype=torch.float32, device=params.device)
+    aux = torch.empty(n, dtype=torch.float32, device=params.device) if aux_exp else None
     P, W, K, S = _seg_arrays(segs)
     check(lib.ngp_mlp_fw(len(segs), P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n,
-                         ptr(out), out.stride(0), stream()), "mlp_fw")
-    return out
+                         ptr(out), out.stride(0), ptr(aux), stream()), "mlp_fw")
+    return (out, aux) if aux_exp else out
 
 
-def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg):
+def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None):
     n = segs[0][0].shape[0]
     dparams = torch.zeros_like(params)
     P, W, K, S = _seg_arrays(segs)
@@ -221,7 +223,8 @@ def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg):
     DS = (ctypes.c_int64 * k)(*[int(d.stride(0)) if d is not None else 0 for d in dsegs])
     dout = dout.contiguous()
     check(lib.ngp_mlp_bw(k, P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n, ptr(dout),
-                         dout.stride(0), ptr(dparams), DP, DS, stream()), "mlp_bw")
+                         dout.stride(0), ptr(dparams), DP, DS, ptr(d_aux.contiguous()) if d_aux is not None else None,
+                         stream()), "mlp_bw")
     return dparams, dsegs
 
 
@@ -248,6 +251,27 @@ class _MlpFn(torch.autograd.Function):
         return (dparams if ctx.needs_input_grad[0] else None, None, None, *dsegs)
 
 
+class _MlpDensityHeadFn(torch.autograd.Function):
+    """(h, sigma) = (MLP(x), exp(MLP(x)[:,0])) with TruncExp's backward (clamp to +-7) — the ngp_pl-shaped
+    density head in one kernel each way (no strided select / exp / select_backward passes)."""
+
+    @staticmethod
+    def forward(ctx, params, m, x):
+        _lib.require_device()
+        x = x.contiguous()
+        ctx.m = m
+        ctx.save_for_backward(params, x)
+        h, sigma = mlp_forward([(x.detach(), x.shape[1], 0)], params.detach(), m, aux_exp=True)
+        return h, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dh, dsigma):
+        params, x = ctx.saved_tensors
+        dparams, dsegs = mlp_backward([(x, x.shape[1], 0)], params, ctx.m, dh, [ctx.needs_input_grad[2]], d_aux=dsigma)
+        return (dparams if ctx.needs_input_grad[0] else None), None, dsegs[0]
+
+
 def xavier_uniform_flat(shapes, seed):
     gen = torch.Generator().manual_seed(seed)
     parts = []
@@ -270,6 +294,10 @@ class Network(nn.Module):
 
     def forward(self, x):
         return _MlpFn.apply(self.params, self.mlp, (0,), x.float())
+
+    def forward_density_head(self, x):
+        """-> (out (N,n_out), exp(out[:,0]) (N))"""
+        return _MlpDensityHeadFn.apply(self.params, self.mlp, x.float())
 
     def forward_segments(self, tensors, kinds):
         """Fused input assembly: MLP(cat(segments)) without materialising the concatenation
