@@ -7,10 +7,13 @@
 // fill of N_rays*max_samples rows of every output (8.6 GB at 2^18 rays).
 //
 // Here (training): three launches, no atomics, no fill, deterministic ray-index order
-//   1. march_count   : pass 1 per ray -> n_samples[r], jittered start t[r]; block sum of counts
+//   1. march_count   : the ONE serial march per ray -> n_samples[r], and the (t, dt) of its first
+//                      kScratch samples into a per-ray scratch row; block sum of counts
 //   2. block_scan    : one CTA scans the per-block sums -> block offsets, total (device resident)
-//   3. march_write   : block-local exclusive scan of counts + block offset = start_idx; pass 2
-//                      writes rays_a / xyzs / dirs / deltas / ts at their final packed positions.
+//   3. march_emit    : block-local exclusive scan of counts + block offset = start_idx; a group of
+//                      8 lanes per ray turns the scratch row into rays_a / xyzs (= fma(t,d,o), the same
+//                      rounding as in the loop) / dirs / deltas / ts with coalesced stores.  Only
+//                      rays with more than kScratch samples are re-marched (by one lane).
 // The per-ray float recurrence (t += dt, cell lookup, empty-cell skip) is the reference's, step by
 // step, with the FMA contractions of the reference build made explicit (common.cuh).
 #include "common.cuh"
@@ -18,6 +21,7 @@
 namespace ngp {
 
 constexpr int kMarchBlock = 256;
+constexpr int kScratch = 64;     // samples per ray recorded by pass 1 (8 B each)
 
 struct MarchParams {
   const uint8_t* __restrict__ bitfield;
@@ -101,7 +105,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
 __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
     const float* __restrict__ noise, MarchParams p, int max_samples, int64_t n_rays,
-    int32_t* __restrict__ n_samples, float* __restrict__ t_start, int32_t* __restrict__ block_sums) {
+    int32_t* __restrict__ n_samples, float* __restrict__ t_start, int32_t* __restrict__ block_sums,
+    float2* __restrict__ scratch) {
   const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
   int N = 0;
   if (r < n_rays) {
@@ -111,8 +116,12 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     if (t1 >= 0) t1 = __fmaf_rn(calc_dt(t1, p.dt), __ldg(noise + r), t1);  // raymarching.cu:195-198
     t_start[r] = t1;
     float t = t1, x, y, z, dt;
+    float2* row = scratch + r * kScratch;
     while (0 <= t && t < t2 && N < max_samples) {
-      if (march_step(q, p, t, x, y, z, dt)) { t = __fadd_rn(t, dt); N++; }
+      if (march_step(q, p, t, x, y, z, dt)) {
+        if (N < kScratch) row[N] = make_float2(t, dt);
+        t = __fadd_rn(t, dt); N++;
+      }
     }
     n_samples[r] = N;
   }
@@ -167,31 +176,62 @@ __global__ void __launch_bounds__(1024) block_scan_kernel(const int32_t* __restr
   }
 }
 
-__global__ void __launch_bounds__(kMarchBlock) march_write_kernel(
+// Pass 2.  CTA = kMarchBlock threads = kMarchBlock/8 rays x 8 lanes; the CTA covers the same ray range
+// [blockIdx.x*256, +256) as pass 1 in 8 sweeps so that the block sums / offsets line up.
+__global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
     MarchParams p, int64_t n_rays, const int32_t* __restrict__ n_samples, const float* __restrict__ t_start,
-    const int64_t* __restrict__ block_offsets, int64_t capacity, int64_t* __restrict__ rays_a,
-    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts) {
-  const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
-  const int N = r < n_rays ? n_samples[r] : 0;
-  int total;
-  const int64_t start = block_offsets[blockIdx.x] + block_exclusive_scan(N, &total);
-  if (r >= n_rays) return;
-  rays_a[3 * r] = r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = N;
-  if (N == 0) return;
-  const Ray q = load_ray(rays_o, rays_d, r);
-  const float t2 = __ldg(hits_t + 2 * r + 1);
-  float t = t_start[r], x, y, z, dt;
-  int s = 0;
-  while (t < t2 && s < N) {
-    if (march_step(q, p, t, x, y, z, dt)) {
+    const int64_t* __restrict__ block_offsets, const float2* __restrict__ scratch, int64_t capacity,
+    int64_t* __restrict__ rays_a, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+    float* __restrict__ ts) {
+  __shared__ int64_t s_start[kMarchBlock];
+  {
+    const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+    const int N = r < n_rays ? n_samples[r] : 0;
+    int total;
+    const int64_t start = block_offsets[blockIdx.x] + block_exclusive_scan(N, &total);
+    s_start[threadIdx.x] = start;
+    if (r < n_rays) { rays_a[3 * r] = r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = N; }
+  }
+  __syncthreads();
+  const int j = threadIdx.x & 7;
+  for (int sweep = 0; sweep < 8; sweep++) {
+    const int lr = sweep * (kMarchBlock / 8) + (threadIdx.x >> 3);     // ray within the CTA's 256
+    const int64_t r = (int64_t)blockIdx.x * kMarchBlock + lr;
+    if (r >= n_rays) continue;
+    const int N = n_samples[r];
+    if (N == 0) continue;
+    const int64_t start = s_start[lr];
+    const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
+    const float dx = __ldg(rays_d + 3 * r), dy = __ldg(rays_d + 3 * r + 1), dz = __ldg(rays_d + 3 * r + 2);
+    const float2* row = scratch + r * kScratch;
+    const int nrec = min(N, kScratch);
+    for (int s = j; s < nrec; s += 8) {
       const int64_t o = start + s;
-      if (o < capacity) {
-        xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
-        dirs[3 * o] = q.dx; dirs[3 * o + 1] = q.dy; dirs[3 * o + 2] = q.dz;
-        ts[o] = t; deltas[o] = dt;
+      if (o >= capacity) break;
+      const float2 td = row[s];
+      xyzs[3 * o] = __fmaf_rn(td.x, dx, ox); xyzs[3 * o + 1] = __fmaf_rn(td.x, dy, oy); xyzs[3 * o + 2] = __fmaf_rn(td.x, dz, oz);
+      dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+      ts[o] = td.x; deltas[o] = td.y;
+    }
+    if (N > kScratch && j == 0) {
+      // long ray: resume the serial march right after the last recorded sample
+      const Ray q = load_ray(rays_o, rays_d, r);
+      const float t2 = __ldg(hits_t + 2 * r + 1);
+      const float2 last = row[kScratch - 1];
+      float t = __fadd_rn(last.x, last.y), x, y, z, dt;
+      int s = kScratch;
+      while (t < t2 && s < N) {
+        if (march_step(q, p, t, x, y, z, dt)) {
+          const int64_t o = start + s;
+          if (o < capacity) {
+            xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+            dirs[3 * o] = q.dx; dirs[3 * o + 1] = q.dy; dirs[3 * o + 2] = q.dz;
+            ts[o] = t; deltas[o] = dt;
+          }
+          t = __fadd_rn(t, dt); s++;
+        }
       }
-      t = __fadd_rn(t, dt); s++;
     }
   }
 }
@@ -254,14 +294,15 @@ static MarchParams make_params(const uint8_t* bitfield, int cascades, float scal
 using namespace ngp;
 
 // Workspace layout for the training marcher (caller-provided device memory):
-//   int32 n_samples[R] | float t_start[R] | int32 block_sums[B] | int64 block_offsets[B] | int64 total
+//   int32 n_samples[R] | float t_start[R] | int32 block_sums[B] | int64 block_offsets[B] | int64 total |
+//   float2 scratch[R][kScratch]
 NGP_API int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays) {
   const int64_t B = ceil_div(n_rays, kMarchBlock);
   auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
-  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256;
+  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256 + al(n_rays * kScratch * 8);
 }
 
-struct MarchWs { int32_t* n_samples; float* t_start; int32_t* block_sums; int64_t* block_offsets; int64_t* total; };
+struct MarchWs { int32_t* n_samples; float* t_start; int32_t* block_sums; int64_t* block_offsets; int64_t* total; float2* scratch; };
 static MarchWs carve(void* ws, int64_t n_rays) {
   const int64_t B = ceil_div(n_rays, kMarchBlock);
   auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -271,7 +312,8 @@ static MarchWs carve(void* ws, int64_t n_rays) {
   w.t_start = (float*)p; p += al(n_rays * 4);
   w.block_sums = (int32_t*)p; p += al(B * 4);
   w.block_offsets = (int64_t*)p; p += al(B * 8);
-  w.total = (int64_t*)p;
+  w.total = (int64_t*)p; p += 256;
+  w.scratch = (float2*)p;
   return w;
 }
 
@@ -289,7 +331,7 @@ NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d
   const MarchParams p = make_params(density_bitfield, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
   const int B = (int)ceil_div(n_rays, kMarchBlock);
   march_count_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays,
-                                              w.n_samples, w.t_start, w.block_sums);
+                                              w.n_samples, w.t_start, w.block_sums, w.scratch);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/count");
   block_scan_kernel<<<1, 1024, 0, s>>>(w.block_sums, B, w.block_offsets, counter, n_rays, w.total);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/scan");
@@ -307,9 +349,9 @@ NGP_API int ngp_raymarching_train_write(const float* rays_o, const float* rays_d
   const MarchWs w = carve((void*)workspace, n_rays);
   const MarchParams p = make_params(density_bitfield, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
   const int B = (int)ceil_div(n_rays, kMarchBlock);
-  march_write_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, p, n_rays, w.n_samples,
-                                                                  w.t_start, w.block_offsets, capacity, rays_a,
-                                                                  xyzs, dirs, deltas, ts);
+  march_emit_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, p, n_rays, w.n_samples,
+                                                                 w.t_start, w.block_offsets, w.scratch, capacity,
+                                                                 rays_a, xyzs, dirs, deltas, ts);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_write");
   return 0;
 }

@@ -307,7 +307,9 @@ __device__ __forceinline__ void cta_teardown(CtaCtx& x, uint32_t tm_cols) {
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(x.tmem, tm_cols);
 }
-// every thread: wait until all MMAs committed so far have finished
+// every thread: wait until all MMAs committed so far have finished.
+// NOTE: mbarrier.try_wait parks the WARP; the single-thread issue blocks are therefore followed by
+// __syncwarp() so that lane 0 never has work left when its sibling lanes start waiting.
 __device__ __forceinline__ void wait_mma(CtaCtx& x) {
   mbar_wait(x.bar, x.phase);
   x.phase ^= 1;
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
 
   zero_pad_cols(c, t, Xs);
   if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, nullptr, blockIdx.x, smem, cx.full);
+  __syncwarp();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
     if (tile_is_bulk(c, tile, n)) { mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1; convert_raw(c, smem, t, Xs); }
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
     {   // the landing zone is free again: fetch the next tile while this one is computed
       const int64_t nxt = tile + gridDim.x;
       if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, nullptr, nxt, smem, cx.full);
+      __syncwarp();
     }
     for (int l = 0; l <= c.nh; l++) {
       const bool last = l == c.nh;
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
         issue_fwd(tacc, sbase + (l == 0 ? c.off_x : c.off_h[0]), sbase + c.off_w[l], (uint32_t)N, N, K);
         mma_commit(cx.bar);
       }
+      __syncwarp();
       wait_mma(cx);
       if (!last) {
         for (int c0 = 0; c0 < c.wp; c0 += 16) {
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
 
   zero_pad_cols(c, t, Xs);
   if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, dout, blockIdx.x, smem, cx.full);
+  __syncwarp();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
     const bool bulk = tile_is_bulk(c, tile, n);
@@ -432,6 +438,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
     {
       const int64_t nxt = tile + gridDim.x;
       if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, dout, nxt, smem, cx.full);
+      __syncwarp();
     }
     // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
     for (int l = 0; l < c.nh; l++) {
@@ -440,6 +447,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
         issue_fwd(tacc, sbase + (l == 0 ? c.off_x : c.off_h[l - 1]), sbase + c.off_w[l], (uint32_t)c.wp, c.wp, l == 0 ? c.k0p : c.wp);
         mma_commit(cx.bar);
       }
+      __syncwarp();
       // overlap the (coalesced) load of this tile's upstream gradient with the first MMA
       if (l == 0 && !dout_staged) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
       wait_mma(cx);
@@ -460,6 +468,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
       issue_fwd(tacc, sbase + c.off_h[c.nh - 1], sbase + c.off_w[c.nh], (uint32_t)c.nop, c.nop, c.wp);
       mma_commit(cx.bar);
     }
+    __syncwarp();
     wait_mma(cx);
     for (int p0 = 0; p0 < c.nop; p0 += 32) {
       if (p0 > 0) {     // n_out > 32: bring in the next 32 columns of dL/dy (panel 0 was loaded under the first MMA)
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
         if (need_dgrad) issue_dgrad(tacc, sbase + c.off_dz, sbase + c.off_w[l], (uint32_t)Nz, Kin, Nz);
         mma_commit(cx.bar);
       }
+      __syncwarp();
       wait_mma(cx);
       if (l > 0) {
         const uint8_t* H = smem + c.off_h[l - 1];
