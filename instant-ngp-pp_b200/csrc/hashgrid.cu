@@ -86,9 +86,12 @@ template <int F, typename TP>
 __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
                                                           GridMeta m, int64_t n, float* __restrict__ y) {
   constexpr int LC = levels_per_thread<F>();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // level chunk is the FASTEST block coordinate: the n_chunks CTAs that touch the same 128-byte rows of
+  // x / y run back to back, so the rows are served from L2 instead of being swept from HBM once per chunk
+  const int n_chunks = (m.n_levels + LC - 1) / LC;
+  const int64_t i = (int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int l0 = blockIdx.y * LC;
+  const int l0 = (blockIdx.x % n_chunks) * LC;
   const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
   float out[LC * F];
 #pragma unroll
@@ -168,9 +171,10 @@ template <int F>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable) {
   constexpr int LC = levels_per_thread<F>();
-  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kSPT;
+  const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
+  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x) * kSPT;
   if (s0 >= n) return;
-  const int l0 = blockIdx.y * LC;
+  const int l0 = (blockIdx.x % n_chunks) * LC;
   const int LF = m.n_levels * F;
   CellAcc<F> acc[LC];
 #pragma unroll
@@ -389,7 +393,7 @@ NGP_API int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)ceil_div(n_levels, LC));
+    const unsigned grid = (unsigned)(ceil_div(n, 256) * ceil_div(n_levels, LC));
     if (table_dtype == 0) hashgrid_fw_kernel<F, float><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
     else hashgrid_fw_kernel<F, __half><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
   });
@@ -407,7 +411,7 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_lev
     return set_error_msg("ngp_hashgrid_bw_params: bad grid config");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const dim3 grid((unsigned)ceil_div(ceil_div(n, kSPT), 128), (unsigned)ceil_div(n_levels, LC));
+    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 128) * ceil_div(n_levels, LC));
     hashgrid_bw_params_kernel<F><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");

@@ -21,7 +21,7 @@
 namespace ngp {
 
 constexpr int kMarchBlock = 256;
-constexpr int kScratch = 64;     // samples per ray recorded by pass 1 (8 B each)
+constexpr int kScratch = 256;    // samples per ray recorded by pass 1 (8 B each; only touched rows cost bandwidth)
 
 struct MarchParams {
   const uint8_t* __restrict__ bitfield;

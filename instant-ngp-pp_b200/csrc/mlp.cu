@@ -653,12 +653,17 @@ static int build_cfg(MlpCfg& c, int n_seg, const float* const* seg_ptr, const in
   return finalize_cfg(c, backward);
 }
 
+// Persistent grid: SMs x co-resident CTAs.  Residency is limited by shared memory (227 KB/SM, +1 KB
+// driver reservation per CTA), TMEM columns (512/SM) and 16 warps' worth of registers; it is computed
+// here directly (the kernels' per-tile latency chain is hidden ONLY by co-resident CTAs, so a
+// too-small answer is a 3x slowdown, not a detail).
 static int launch_grid(const void* fn, const MlpCfg& c, int64_t n) {
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kTile, c.smem_bytes);
-  if (occ < 1) occ = 1;
+  (void)fn;
+  int occ = (int)((227 * 1024) / (c.smem_bytes + 1024));
   const int by_tmem = 512 / (int)c.tm_cols;
   if (occ > by_tmem) occ = by_tmem;
+  if (occ > 8) occ = 8;
+  if (occ < 1) occ = 1;
   int64_t g = (int64_t)kSMs * occ;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (g > tiles) g = tiles;

@@ -64,8 +64,12 @@ def test_hashgrid_forward_and_first_order(cfg):
     gx, gp = torch.autograd.grad(y, (x, enc.params), dy)
     gxo, gpo = torch.autograd.grad(yo, (xo, po), dy.double())
     assert rel(gp, gpo) < 1e-3, rel(gp, gpo)
-    # dy/dx is discontinuous at cell faces: compare away from the hand-placed lattice points
-    assert rel(gx[8:], gxo[8:]) < 3e-3, rel(gx[8:], gxo[8:])
+    # dy/dx is piecewise constant and DISCONTINUOUS at cell faces: a sample whose fp32 position rounds
+    # into the neighbouring cell of a fine level (P ~ eps*scale per axis per level) gets that cell's
+    # slope.  Robust statistics: median per-sample error, and the fraction of such outliers.
+    e = (gx.double() - gxo).norm(dim=1) / (gxo.norm(dim=1) + 1e-12)
+    assert float(e[8:].median()) < 2e-3, float(e[8:].median())
+    assert float((e[8:] > 2e-2).float().mean()) < 1e-2, float((e[8:] > 2e-2).float().mean())
 
 
 def test_hashgrid_double_backward():

@@ -1,0 +1,49 @@
+"""Launches the individual hot kernels on a realistic sample set (for ncu captures).
+usage: python tools/run_kernel.py [n_rays_log2=17]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "instant-ngp-pp_b200"))
+import torch
+from ngp_b200 import vren, tcnn
+from ngp_b200.networks import NGPCompact
+from ngp_b200.synthetic import BoxScene, scene_density_grid
+from ngp_b200.custom_functions import RayMarcher
+
+dev = torch.device("cuda", 0)
+scene = BoxScene("lego", device=dev)
+poses = scene.poses(100)
+model = NGPCompact(scale=0.5).to(dev)
+model.density_grid.copy_(scene_density_grid(scene))
+vren.packbits(model.density_grid, 0.5, model.density_bitfield)
+R = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 17)
+ro, rd = scene.sample_rays(R, poses)
+with torch.no_grad():
+    _, hits_t, _ = vren.ray_aabb_intersect(ro, rd, model.center, model.half_size, 1)
+    for _ in range(2):
+        ra, xyzs, dirs, deltas, ts, tot = RayMarcher.apply(ro, rd, hits_t[:, 0].contiguous(), model.density_bitfield, 1, 0.5, 0.0, 128, 1024)
+    S = xyzs.shape[0]
+    g = model.xyz_encoder.grid
+    xn = ((xyzs - model.xyz_min) / (model.xyz_max - model.xyz_min)).contiguous()
+    table = model.xyz_encoder.params.detach()
+    for _ in range(2):
+        y = tcnn.grid_forward(xn, table, g)
+    dy = torch.randn_like(y); dtab = torch.zeros_like(table)
+    for _ in range(2):
+        tcnn.grid_backward_params(xn, dy, g, out=dtab)
+    m1, m2 = model.sigma_net.mlp, model.rgb_net.mlp
+    for _ in range(2):
+        h, sig = tcnn.mlp_forward([(y, 32, 0)], model.sigma_net.params.detach(), m1, aux_exp=True)
+    dh = torch.randn_like(h); ds = torch.randn_like(sig)
+    for _ in range(2):
+        tcnn.mlp_backward([(y, 32, 0)], model.sigma_net.params.detach(), m1, dh, [True], d_aux=ds)
+    segs = [(dirs, 16, 1), (h, 16, 0)]
+    for _ in range(2):
+        rgb = tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)
+    drgb = torch.randn_like(rgb)
+    for _ in range(2):
+        tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True])
+    sigmas = torch.rand(S, device=dev) * 20
+    for _ in range(2):
+        out = vren.composite_train_fw(sigmas, rgb, rgb, torch.zeros(S, 0, device=dev), deltas, ts, ra, 1e-4, 0)
+torch.cuda.synchronize()
+print("rays", R, "samples", S)
