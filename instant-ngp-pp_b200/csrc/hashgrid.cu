@@ -106,9 +106,20 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
       const bool dense = m.dense[l];
       float v[8][F];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
-        Vec<F, TP>::ld(base + (size_t)idx * F, v[k]);
+      for (int p = 0; p < 4; p++) {
+        const uint32_t i0 = grid_index(c.px, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+        const uint32_t i1 = grid_index(c.px + 1, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+        if constexpr (F == 2 && sizeof(TP) == 4) {
+          // the two x-neighbours are adjacent entries whenever the lower index is even (always for hashed
+          // levels with even x): one 16-byte gather instead of two 8-byte ones
+          if (i1 == i0 + 1 && (i0 & 1u) == 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(base + (size_t)i0 * 2));
+            v[2 * p][0] = q.x; v[2 * p][1] = q.y; v[2 * p + 1][0] = q.z; v[2 * p + 1][1] = q.w;
+            continue;
+          }
+        }
+        Vec<F, TP>::ld(base + (size_t)i0 * F, v[2 * p]);
+        Vec<F, TP>::ld(base + (size_t)i1 * F, v[2 * p + 1]);
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
 //    (always for hashed levels with even x: h(x+1) = h(x)^1), so for F=2 the pair goes out as ONE
 //    16-byte red.global.add.v4.f32 instead of two 8-byte ones;
 //  * exactly-zero upstream rows (samples past early termination) are skipped.
-constexpr int kSPT = 4;
+constexpr int kSPT = 8;
 
 template <int F> struct CellAcc {
   uint32_t px, py, pz;

@@ -11,10 +11,11 @@
 // Parameter layout (flat fp32, row-major (out,in) per layer, layers concatenated):
 //   W_0 [width x k0] | W_1.. [width x width] (n_hidden-1 of them) | W_out [n_out_pad16 x width]
 //
-// Kernel shape: CTA = 128 threads = 4 warps; thread t owns tile row (sample) t for staging and for
-// the TMEM->register epilogues (warp w can read TMEM lanes 32w..32w+31).  Thread 0 issues every
-// tcgen05.mma and commits to one mbarrier; the CTA loops over tiles with stride gridDim.x, and
-// 2-5 co-resident CTAs per SM overlap each other's load / MMA / epilogue phases.
+// Kernel shape: CTA = 256 threads = 8 warps; thread t works on tile row (sample) t%128 and on column
+// half t/128 in the TMEM->register epilogues (warp w can read TMEM lanes 32*(w%4)..+31).  Thread 0
+// issues every tcgen05.mma and commits to one mbarrier; the next tile's inputs arrive by bulk copy
+// (UBLKCP) while the current one is computed; the CTA loops over tiles with stride gridDim.x, and the
+// 2-3 co-resident CTAs per SM overlap each other's MMA / epilogue phases.
 //   forward : X -> [MMA -> act -> bf16 smem]* -> MMA -> act_out -> global
 //   backward: recompute the forward chain (hidden activations stay in smem), then per layer, top
 //             down:  wgrad (accumulated in TMEM for the CTA's whole lifetime, flushed once with
@@ -28,7 +29,8 @@
 namespace ngp {
 using namespace tc05;
 
-constexpr int kTile = 128;
+constexpr int kTile = 128;          // samples (rows) per tile = TMEM lanes
+constexpr int kThreads = 256;       // 8 warps: warp w reads TMEM lanes 32*(w%4).., warps 0-3 / 4-7 split the columns
 constexpr int kMaxSeg = 3;
 constexpr int kMaxHidden = 6;
 
@@ -129,6 +131,7 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
   for (int s = 0; s < c.n_seg; s++) {
     const int w = c.seg_w[s];
     if (c.seg_kind[s] == kSegSH4) {
+      if (t >= kTile) { col += w; continue; }            // one thread per row evaluates the harmonics
       const int64_t row = row0 + t;
       float o[16];
       if (row < n) {
@@ -148,7 +151,7 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
       const bool vec = ((col & 3) == 0) && ((w & 3) == 0) && ((stride & 3) == 0) && ((((uintptr_t)base) & 15) == 0);
       if (vec) {
         const int upr = w >> 2;                       // float4 units per row
-        for (int u = t; u < kTile * upr; u += kTile) {
+        for (int u = t; u < kTile * upr; u += kThreads) {
           const int r = u / upr, c4 = u - r * upr;
           const int64_t row = row0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,7 +159,7 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
           st_quad(Xs, kTile, r, col + c4 * 4, v);
         }
       } else {
-        for (int u = t; u < kTile * w; u += kTile) {
+        for (int u = t; u < kTile * w; u += kThreads) {
           const int r = u / w, cc = u - r * w;
           const int64_t row = row0 + r;
           st_elem(Xs, kTile, r, col + cc, row < n ? __ldg(base + row * stride + cc) : 0.f);
@@ -167,7 +170,7 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
   }
   if (col < c.k0p) {
     const int padw = c.k0p - col;
-    for (int u = t; u < kTile * padw; u += kTile) st_elem(Xs, kTile, u / padw, col + u % padw, 0.f);
+    for (int u = t; u < kTile * padw; u += kThreads) st_elem(Xs, kTile, u / padw, col + u % padw, 0.f);
   }
 }
 
@@ -175,7 +178,7 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
 constexpr int kStgPitch = 33;
 __device__ __forceinline__ void panel_store(const float* stg, int ncols_valid, int64_t row0, int64_t n, float* dst,
                                             int64_t dst_stride, int dst_col0, uint32_t t) {
-  for (int u = t; u < kTile * ncols_valid; u += kTile) {
+  for (int u = t; u < kTile * ncols_valid; u += kThreads) {
     const int r = u / ncols_valid, cc = u - r * ncols_valid;
     const int64_t row = row0 + r;
     if (row < n) dst[row * dst_stride + dst_col0 + cc] = stg[r * kStgPitch + cc];
@@ -184,7 +187,7 @@ __device__ __forceinline__ void panel_store(const float* stg, int ncols_valid, i
 // Coalesced load of a [128 x ncols] fp32 panel into the staging buffer (zeros past n).
 __device__ __forceinline__ void panel_load(float* stg, int ncols_valid, int64_t row0, int64_t n, const float* src,
                                            int64_t src_stride, int src_col0, uint32_t t) {
-  for (int u = t; u < kTile * ncols_valid; u += kTile) {
+  for (int u = t; u < kTile * ncols_valid; u += kThreads) {
     const int r = u / ncols_valid, cc = u - r * ncols_valid;
     const int64_t row = row0 + r;
     stg[r * kStgPitch + cc] = row < n ? __ldg(src + row * src_stride + src_col0 + cc) : 0.f;
@@ -213,6 +216,7 @@ __device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem
     const int w = c.seg_w[s];
     const float* raw = reinterpret_cast<const float*>(smem + c.off_raw[s]);
     if (c.seg_kind[s] == kSegSH4) {
+      if (t >= kTile) { col += w; continue; }
       const float dx = raw[3 * t], dy = raw[3 * t + 1], dz = raw[3 * t + 2];
       const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
       float o[16];
@@ -222,12 +226,12 @@ __device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem
     } else if (((col | w) & 3) == 0) {
       const int upr = w >> 2, total = kTile * upr;
 #pragma unroll 4
-      for (int u = t; u < total; u += kTile) {
+      for (int u = t; u < total; u += kThreads) {
         const int r = u / upr, c4 = u - r * upr;
         st_quad(Xs, kTile, r, col + c4 * 4, reinterpret_cast<const float4*>(raw)[u]);
       }
     } else {
-      for (int u = t; u < kTile * w; u += kTile) st_elem(Xs, kTile, u / w, col + u % w, raw[u]);
+      for (int u = t; u < kTile * w; u += kThreads) st_elem(Xs, kTile, u / w, col + u % w, raw[u]);
     }
     col += w;
   }
@@ -236,7 +240,7 @@ __device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem
 __device__ __forceinline__ void zero_pad_cols(const MlpCfg& c, uint32_t t, uint8_t* Xs) {
   if (c.k0 < c.k0p) {
     const int padw = c.k0p - c.k0;
-    for (int u = t; u < kTile * padw; u += kTile) st_elem(Xs, kTile, u / padw, c.k0 + u % padw, 0.f);
+    for (int u = t; u < kTile * padw; u += kThreads) st_elem(Xs, kTile, u / padw, c.k0 + u % padw, 0.f);
   }
 }
 
@@ -323,19 +327,42 @@ __device__ __forceinline__ void publish() {
 }
 
 // =============================================================================== forward kernel
+// Thread geometry shared by both kernels.
+struct Lane {
+  uint32_t t, row, half, trow;      // thread id, tile row, column half (0/1), TMEM address of this warp's lanes
+};
+__device__ __forceinline__ Lane make_lane(uint32_t tmem) {
+  Lane L;
+  L.t = threadIdx.x; L.row = L.t & (kTile - 1); L.half = L.t >> 7;
+  L.trow = tmem + ((((L.t >> 5) & 3u) * 32u) << 16);
+  return L;
+}
+// hidden-layer epilogue: this thread's half of the wp accumulator columns -> act -> bf16 tile row
+__device__ __forceinline__ void epilogue_hidden(const MlpCfg& c, const Lane& L, uint8_t* H) {
+  const int cb = (int)L.half * (c.wp >> 1), ce = cb + (c.wp >> 1);
+  for (int c0 = cb; c0 < ce; c0 += 32) {
+    float v[32];
+    tmem_ld32(L.trow + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = act_apply(c.act_h, v[i]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 8 * q, v + 8 * q);
+  }
+}
+
 // aux_exp (optional): aux_exp[row] = exp(z_out[row][0]) — the density head of the ngp_pl-shaped field
 // (sigma = TruncExp(h[:,0])) produced by the same epilogue instead of a strided select + exp pass.
-__global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
-                                                       float* __restrict__ out, int64_t out_stride,
-                                                       float* __restrict__ aux_exp) {
+__global__ void __launch_bounds__(kThreads) mlp_fw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
+                                                          float* __restrict__ out, int64_t out_stride,
+                                                          float* __restrict__ aux_exp) {
   extern __shared__ __align__(128) uint8_t smem[];
   CtaCtx cx;
   cta_setup(cx, smem, c.tm_cols);
   stage_weights(c, params, smem);
-  const uint32_t t = threadIdx.x, warp = t >> 5;
+  const Lane L = make_lane(cx.tmem);
+  const uint32_t t = L.t;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tacc = cx.tmem;                               // accumulator columns [0, max(wp,nop))
-  const uint32_t trow = cx.tmem + ((warp * 32u) << 16);        // this warp's lanes
   uint8_t* Xs = smem + c.off_x;
   uint8_t* Hs = smem + c.off_h[0];
   float* stg = reinterpret_cast<float*>(smem + c.off_stg);
@@ -366,24 +393,18 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
       __syncwarp();
       wait_mma(cx);
       if (!last) {
-        for (int c0 = 0; c0 < c.wp; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + c0, v);
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_h, v[i]);
-          st_chunk(Hs, kTile, t, c0, v);
-          st_chunk(Hs, kTile, t, c0 + 8, v + 8);
-        }
+        epilogue_hidden(c, L, Hs);
         publish();
       } else {
         // output: TMEM -> registers -> activation -> fp32 staging panel -> coalesced global stores
         for (int p0 = 0; p0 < c.no; p0 += 32) {
-          for (int c0 = p0; c0 < p0 + 32 && c0 < c.nop; c0 += 16) {
+          const int c0 = p0 + 16 * (int)L.half;                 // each half owns 16 of the panel's 32 columns
+          if (c0 < c.nop) {
             float v[16];
-            tmem_ld16(trow + c0, v);
-            if (aux_exp && c0 == 0 && row0 + t < n) aux_exp[row0 + t] = __expf(v[0]);
+            tmem_ld16(L.trow + c0, v);
+            if (aux_exp && c0 == 0 && row0 + L.row < n) aux_exp[row0 + L.row] = __expf(v[0]);
 #pragma unroll
-            for (int i = 0; i < 16; i++) stg[t * kStgPitch + (c0 - p0) + i] = act_apply(c.act_o, v[i]);
+            for (int i = 0; i < 16; i++) stg[L.row * kStgPitch + (c0 - p0) + i] = act_apply(c.act_o, v[i]);
           }
           fence_before_sync();
           __syncthreads();
@@ -397,18 +418,18 @@ __global__ void __launch_bounds__(kTile) mlp_fw_kernel(MlpCfg c, SegPtrs in, con
 }
 
 // =============================================================================== backward kernel
-__global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
-                                                       const float* __restrict__ dout, int64_t dout_stride,
-                                                       float* __restrict__ dparams, SegGrads dseg,
-                                                       const float* __restrict__ d_aux_exp) {
+__global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
+                                                          const float* __restrict__ dout, int64_t dout_stride,
+                                                          float* __restrict__ dparams, SegGrads dseg,
+                                                          const float* __restrict__ d_aux_exp) {
   extern __shared__ __align__(128) uint8_t smem[];
   CtaCtx cx;
   cta_setup(cx, smem, c.tm_cols);
   stage_weights(c, params, smem);
-  const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const Lane L = make_lane(cx.tmem);
+  const uint32_t t = L.t;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t tacc = cx.tmem;
-  const uint32_t trow = cx.tmem + ((warp * 32u) << 16);
   uint8_t* Xs = smem + c.off_x;
   uint8_t* dZ = smem + c.off_dz;
   float* stg = reinterpret_cast<float*>(smem + c.off_stg);
@@ -428,7 +449,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
       convert_raw(c, smem, t, Xs);
       if (c.bulk_dout) {                                    // dL/dy rows -> staging panel (pitch 33)
         const float* rd = reinterpret_cast<const float*>(smem + c.off_raw_dout);
-        for (int u = t; u < kTile * c.no; u += kTile) stg[(u / c.no) * kStgPitch + u % c.no] = rd[u];
+        for (int u = t; u < kTile * c.no; u += kThreads) stg[(u / c.no) * kStgPitch + u % c.no] = rd[u];
       }
     } else {
       stage_input(c, in, row0, n, t, Xs);
@@ -451,15 +472,7 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
       // overlap the (coalesced) load of this tile's upstream gradient with the first MMA
       if (l == 0 && !dout_staged) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
       wait_mma(cx);
-      uint8_t* H = smem + c.off_h[l];
-      for (int c0 = 0; c0 < c.wp; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_h, v[i]);
-        st_chunk(H, kTile, t, c0, v);
-        st_chunk(H, kTile, t, c0 + 8, v + 8);
-      }
+      epilogue_hidden(c, L, smem + c.off_h[l]);
       publish();
     }
     // ---- output layer pre-activation -> dZ_out = dL/dy * act_o'(z)
@@ -471,27 +484,29 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
     __syncwarp();
     wait_mma(cx);
     for (int p0 = 0; p0 < c.nop; p0 += 32) {
-      if (p0 > 0) {     // n_out > 32: bring in the next 32 columns of dL/dy (panel 0 was loaded under the first MMA)
+      if (p0 > 0) {     // n_out > 32: bring in the next 32 columns of dL/dy (panel 0 is already staged)
         __syncthreads();
         panel_load(stg, min(32, c.no - p0), row0, n, dout, dout_stride, p0, t);
         __syncthreads();
       }
-      for (int c0 = p0; c0 < p0 + 32 && c0 < c.nop; c0 += 16) {
+      const int c0 = p0 + 16 * (int)L.half;
+      if (c0 < c.nop) {
         float v[16];
-        tmem_ld16(trow + c0, v);
+        tmem_ld16(L.trow + c0, v);
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           float g = 0.f;
           if (c0 + i < c.no) {
             const float y = act_apply(c.act_o, v[i]);
-            g = stg[t * kStgPitch + (c0 - p0) + i] * act_grad_from_out(c.act_o, y);
+            g = stg[L.row * kStgPitch + (c0 - p0) + i] * act_grad_from_out(c.act_o, y);
             // TruncExp backward of the density head: g * exp(clamp(z, -7, 7))  (custom_functions.py:211)
-            if (d_aux_exp && c0 + i == 0 && row0 + t < n) g = fmaf(__ldg(d_aux_exp + row0 + t), __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
+            if (d_aux_exp && c0 + i == 0 && row0 + L.row < n)
+              g = fmaf(__ldg(d_aux_exp + row0 + L.row), __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
           }
           v[i] = g;
         }
-        st_chunk(dZ, kTile, t, c0, v);
-        st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+        st_chunk(dZ, kTile, L.row, c0, v);
+        st_chunk(dZ, kTile, L.row, c0 + 8, v + 8);
       }
     }
     publish();
@@ -513,26 +528,28 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
       wait_mma(cx);
       if (l > 0) {
         const uint8_t* H = smem + c.off_h[l - 1];
-        for (int c0 = 0; c0 < c.wp; c0 += 16) {
-          float v[16], h[16];
-          tmem_ld16(trow + c0, v);
-          ld_chunk(H, kTile, t, c0, h);
-          ld_chunk(H, kTile, t, c0 + 8, h + 8);
+        const int cb = (int)L.half * (c.wp >> 1), ce = cb + (c.wp >> 1);
+        for (int c0 = cb; c0 < ce; c0 += 32) {
+          float v[32], h[32];
+          tmem_ld32(L.trow + c0, v);
 #pragma unroll
-          for (int i = 0; i < 16; i++) v[i] *= act_grad_from_out(c.act_h, h[i]);
-          st_chunk(dZ, kTile, t, c0, v);
-          st_chunk(dZ, kTile, t, c0 + 8, v + 8);
+          for (int q = 0; q < 4; q++) ld_chunk(H, kTile, L.row, c0 + 8 * q, h + 8 * q);
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] *= act_grad_from_out(c.act_h, h[i]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) st_chunk(dZ, kTile, L.row, c0 + 8 * q, v + 8 * q);
         }
         publish();
       } else {
         if (want_dx) {
           // input gradient: 32-column panels through the staging buffer, coalesced per segment
           for (int p0 = 0; p0 < c.k0; p0 += 32) {
-            for (int c0 = p0; c0 < p0 + 32 && c0 < c.k0p; c0 += 16) {
+            const int c0 = p0 + 16 * (int)L.half;
+            if (c0 < c.k0p) {
               float v[16];
-              tmem_ld16(trow + c0, v);
+              tmem_ld16(L.trow + c0, v);
 #pragma unroll
-              for (int i = 0; i < 16; i++) stg[t * kStgPitch + (c0 - p0) + i] = v[i];
+              for (int i = 0; i < 16; i++) stg[L.row * kStgPitch + (c0 - p0) + i] = v[i];
             }
             fence_before_sync();
             __syncthreads();
@@ -558,14 +575,15 @@ __global__ void __launch_bounds__(kTile) mlp_bw_kernel(MlpCfg c, SegPtrs in, con
     fence_after_sync();
     // accumulator row m of an M=128 tile sits in TMEM lane m; of an M=64 tile in lane (m%16)+32*(m/16)
     const bool m128 = c.wp == 128;
-    const int m = m128 ? (int)t : (lane < 16 ? (int)(warp * 16 + lane) : -1);
+    const uint32_t lane = t & 31, quad = (t >> 5) & 3;
+    const int m = m128 ? (int)L.row : (lane < 16 ? (int)(quad * 16 + lane) : -1);
     for (int l = 0; l <= c.nh; l++) {
       const bool is_out = l == c.nh;
       const int ncols = is_out ? c.nop : (l == 0 ? c.k0p : c.wp);
       const int in_true = l == 0 ? c.k0 : c.w;
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
+      for (int c0 = 16 * (int)L.half; c0 < ncols; c0 += 32) {       // 16-column groups alternate between the halves
         float v[16];
-        tmem_ld16(trow + c.tm_wg[l] + c0, v);
+        tmem_ld16(L.trow + c.tm_wg[l] + c0, v);
         if (m >= 0 && m < c.w) {
 #pragma unroll
           for (int i = 0; i < 16; i++) {
@@ -658,10 +676,15 @@ static int build_cfg(MlpCfg& c, int n_seg, const float* const* seg_ptr, const in
 // here directly (the kernels' per-tile latency chain is hidden ONLY by co-resident CTAs, so a
 // too-small answer is a 3x slowdown, not a detail).
 static int launch_grid(const void* fn, const MlpCfg& c, int64_t n) {
-  (void)fn;
   int occ = (int)((227 * 1024) / (c.smem_bytes + 1024));
   const int by_tmem = 512 / (int)c.tm_cols;
   if (occ > by_tmem) occ = by_tmem;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) {
+    const int regs = (fa.numRegs + 7) / 8 * 8;
+    const int by_regs = 65536 / (regs * kThreads);
+    if (occ > by_regs) occ = by_regs;
+  }
   if (occ > 8) occ = 8;
   if (occ < 1) occ = 1;
   int64_t g = (int64_t)kSMs * occ;
@@ -697,7 +720,7 @@ NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   cudaError_t e = cudaFuncSetAttribute(mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
   if (e != cudaSuccess) return set_error(e, "ngp_mlp_fw/attr");
   const int grid = launch_grid((const void*)mlp_fw_kernel, c, n);
-  mlp_fw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, out, out_stride, aux_exp_out);
+  mlp_fw_kernel<<<grid, kThreads, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, out, out_stride, aux_exp_out);
   NGP_LAUNCH_CHECK("ngp_mlp_fw");
   return 0;
 }
@@ -723,7 +746,7 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   cudaError_t e = cudaFuncSetAttribute(mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
   if (e != cudaSuccess) return set_error(e, "ngp_mlp_bw/attr");
   const int grid = launch_grid((const void*)mlp_bw_kernel, c, n);
-  mlp_bw_kernel<<<grid, kTile, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp);
+  mlp_bw_kernel<<<grid, kThreads, c.smem_bytes, (cudaStream_t)stream>>>(c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp);
   NGP_LAUNCH_CHECK("ngp_mlp_bw");
   return 0;
 }
