@@ -30,7 +30,8 @@ namespace ngp {
 using namespace tc05;
 
 constexpr int kTile = 128;          // samples (rows) per tile = TMEM lanes
-constexpr int kThreads = 256;       // 8 warps: warp w reads TMEM lanes 32*(w%4).., warps 0-3 / 4-7 split the columns
+constexpr int kThreads = 128;       // 4 warps: warp w reads TMEM lanes 32*w..  (256 = two column halves; measured slower)
+constexpr int kHalves = kThreads / kTile;
 constexpr int kMaxSeg = 3;
 constexpr int kMaxHidden = 6;
 
@@ -49,10 +50,10 @@ struct MlpCfg {
   int act_h, act_o;
   // shared-memory byte offsets
   uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]
-  uint32_t off_x, off_h[kMaxHidden], off_dz, off_stg;
+  uint32_t off_x, off_h[kMaxHidden], off_dz;
   // raw fp32 landing zone of the next tile (bulk copies): per segment, then dL/dy (backward)
-  uint32_t off_raw[kMaxSeg], off_raw_dout, raw_bytes[kMaxSeg], raw_dout_bytes;
-  int bulk, bulk_dout;             // set by the host when every segment (resp. dL/dy) is contiguous + 16-B aligned
+  uint32_t off_raw[kMaxSeg], raw_bytes[kMaxSeg];
+  int bulk;                        // set by the host when every segment is contiguous + 16-byte aligned
   uint32_t smem_bytes;
   // TMEM column offsets
   uint32_t tm_cols;                  // allocation (power of two)
@@ -174,49 +175,30 @@ __device__ __forceinline__ void stage_input(const MlpCfg& c, const SegPtrs& in, 
   }
 }
 
-// Coalesced copy-out of a [128 x ncols] fp32 panel held in the staging buffer (row pitch kStgPitch).
-constexpr int kStgPitch = 33;
-__device__ __forceinline__ void panel_store(const float* stg, int ncols_valid, int64_t row0, int64_t n, float* dst,
-                                            int64_t dst_stride, int dst_col0, uint32_t t) {
-  for (int u = t; u < kTile * ncols_valid; u += kThreads) {
-    const int r = u / ncols_valid, cc = u - r * ncols_valid;
-    const int64_t row = row0 + r;
-    if (row < n) dst[row * dst_stride + dst_col0 + cc] = stg[r * kStgPitch + cc];
-  }
-}
-// Coalesced load of a [128 x ncols] fp32 panel into the staging buffer (zeros past n).
-__device__ __forceinline__ void panel_load(float* stg, int ncols_valid, int64_t row0, int64_t n, const float* src,
-                                           int64_t src_stride, int src_col0, uint32_t t) {
-  for (int u = t; u < kTile * ncols_valid; u += kThreads) {
-    const int r = u / ncols_valid, cc = u - r * ncols_valid;
-    const int64_t row = row0 + r;
-    stg[r * kStgPitch + cc] = row < n ? __ldg(src + row * src_stride + src_col0 + cc) : 0.f;
-  }
-}
-
 // ---- next-tile prefetch: one thread arms `full` and fires one bulk copy per segment (+ dL/dy) ------
 __device__ __forceinline__ bool tile_is_bulk(const MlpCfg& c, int64_t tile, int64_t n) {
   return c.bulk && (tile + 1) * kTile <= n;
 }
-__device__ __forceinline__ void issue_prefetch(const MlpCfg& c, const SegPtrs& in, const float* dout, int64_t tile,
-                                               uint8_t* smem, uint64_t* full) {
+__device__ __forceinline__ void issue_prefetch(const MlpCfg& c, const SegPtrs& in, int64_t tile, uint8_t* smem,
+                                               uint64_t* full) {
   const int64_t row0 = tile * kTile;
   uint32_t total = 0;
   for (int s = 0; s < c.n_seg; s++) total += c.raw_bytes[s];
-  if (c.bulk_dout && dout) total += c.raw_dout_bytes;
   mbar_expect_tx(full, total);
   for (int s = 0; s < c.n_seg; s++)
     bulk_g2s(smem + c.off_raw[s], in.p[s] + row0 * c.seg_stride[s], c.raw_bytes[s], full);
-  if (c.bulk_dout && dout) bulk_g2s(smem + c.off_raw_dout, dout + row0 * c.no, c.raw_dout_bytes, full);
 }
-// All threads: raw fp32 landing zone -> bf16 operand tile (flat, conflict-free 16-byte smem reads).
+// Raw fp32 landing zone -> bf16 operand tile.  Thread r converts row r; in step i it reads float4
+// #((i + r) mod upr) of its row, so the 32 lanes of a warp hit distinct bank groups even though rows
+// are w*4 bytes apart (a straight per-row walk would be a 32-way conflict), and no index division is
+// needed.
 __device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem, uint32_t t, uint8_t* Xs) {
+  if (t >= kTile) return;
   int col = 0;
   for (int s = 0; s < c.n_seg; s++) {
     const int w = c.seg_w[s];
     const float* raw = reinterpret_cast<const float*>(smem + c.off_raw[s]);
     if (c.seg_kind[s] == kSegSH4) {
-      if (t >= kTile) { col += w; continue; }
       const float dx = raw[3 * t], dy = raw[3 * t + 1], dz = raw[3 * t + 2];
       const float inv = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
       float o[16];
@@ -224,14 +206,16 @@ __device__ __forceinline__ void convert_raw(const MlpCfg& c, const uint8_t* smem
       if ((col & 7) == 0) { st_chunk(Xs, kTile, t, col, o); st_chunk(Xs, kTile, t, col + 8, o + 8); }
       else { for (int i = 0; i < 16; i++) st_elem(Xs, kTile, t, col + i, o[i]); }
     } else if (((col | w) & 3) == 0) {
-      const int upr = w >> 2, total = kTile * upr;
+      const int upr = w >> 2;
+      const float4* rowp = reinterpret_cast<const float4*>(raw) + (size_t)t * upr;
+      int c4 = (int)(t % (uint32_t)upr);
 #pragma unroll 4
-      for (int u = t; u < total; u += kThreads) {
-        const int r = u / upr, c4 = u - r * upr;
-        st_quad(Xs, kTile, r, col + c4 * 4, reinterpret_cast<const float4*>(raw)[u]);
+      for (int i = 0; i < upr; i++) {
+        st_quad(Xs, kTile, t, col + c4 * 4, rowp[c4]);
+        c4 = (c4 + 1 == upr) ? 0 : c4 + 1;
       }
     } else {
-      for (int u = t; u < kTile * w; u += kThreads) st_elem(Xs, kTile, u / w, col + u % w, raw[u]);
+      for (int cc = 0; cc < w; cc++) st_elem(Xs, kTile, t, col + cc, raw[t * w + cc]);
     }
     col += w;
   }
@@ -337,16 +321,28 @@ __device__ __forceinline__ Lane make_lane(uint32_t tmem) {
   L.trow = tmem + ((((L.t >> 5) & 3u) * 32u) << 16);
   return L;
 }
-// hidden-layer epilogue: this thread's half of the wp accumulator columns -> act -> bf16 tile row
+// hidden-layer epilogue: this thread's share of the wp accumulator columns -> act -> bf16 tile row
 __device__ __forceinline__ void epilogue_hidden(const MlpCfg& c, const Lane& L, uint8_t* H) {
-  const int cb = (int)L.half * (c.wp >> 1), ce = cb + (c.wp >> 1);
-  for (int c0 = cb; c0 < ce; c0 += 32) {
+  const int cw = c.wp / kHalves, cb = (int)L.half * cw;
+  for (int c0 = cb; c0 < cb + cw; c0 += 32) {
     float v[32];
     tmem_ld32(L.trow + c0, v);
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = act_apply(c.act_h, v[i]);
 #pragma unroll
     for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 8 * q, v + 8 * q);
+  }
+}
+// 16 consecutive columns [c0, c0+16) of one row -> global, clipped to [0, ncols); 16-byte stores when the
+// destination allows it (each thread owns a contiguous 64-byte run of its row)
+__device__ __forceinline__ void store_row16(float* dst_row, int c0, int ncols, bool vec, const float* v) {
+  if (vec && c0 + 16 <= ncols) {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      *reinterpret_cast<float4*>(dst_row + c0 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (c0 + i < ncols) dst_row[c0 + i] = v[i];
   }
 }
 
@@ -365,20 +361,21 @@ __global__ void __launch_bounds__(kThreads) mlp_fw_kernel(MlpCfg c, SegPtrs in, 
   const uint32_t tacc = cx.tmem;                               // accumulator columns [0, max(wp,nop))
   uint8_t* Xs = smem + c.off_x;
   uint8_t* Hs = smem + c.off_h[0];
-  float* stg = reinterpret_cast<float*>(smem + c.off_stg);
   const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const bool out_vec = ((out_stride & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
 
   zero_pad_cols(c, t, Xs);
-  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, nullptr, blockIdx.x, smem, cx.full);
+  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, blockIdx.x, smem, cx.full);
   __syncwarp();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
+    const int64_t row = row0 + L.row;
     if (tile_is_bulk(c, tile, n)) { mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1; convert_raw(c, smem, t, Xs); }
     else stage_input(c, in, row0, n, t, Xs);
     publish();
     {   // the landing zone is free again: fetch the next tile while this one is computed
       const int64_t nxt = tile + gridDim.x;
-      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, nullptr, nxt, smem, cx.full);
+      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, nxt, smem, cx.full);
       __syncwarp();
     }
     for (int l = 0; l <= c.nh; l++) {
@@ -396,21 +393,18 @@ __global__ void __launch_bounds__(kThreads) mlp_fw_kernel(MlpCfg c, SegPtrs in, 
         epilogue_hidden(c, L, Hs);
         publish();
       } else {
-        // output: TMEM -> registers -> activation -> fp32 staging panel -> coalesced global stores
-        for (int p0 = 0; p0 < c.no; p0 += 32) {
-          const int c0 = p0 + 16 * (int)L.half;                 // each half owns 16 of the panel's 32 columns
-          if (c0 < c.nop) {
-            float v[16];
-            tmem_ld16(L.trow + c0, v);
-            if (aux_exp && c0 == 0 && row0 + L.row < n) aux_exp[row0 + L.row] = __expf(v[0]);
+        for (int c0 = 16 * (int)L.half; c0 < c.nop; c0 += 16 * kHalves) {
+          float v[16];
+          tmem_ld16(L.trow + c0, v);
+          if (row < n) {
+            if (aux_exp && c0 == 0) aux_exp[row] = __expf(v[0]);
 #pragma unroll
-            for (int i = 0; i < 16; i++) stg[L.row * kStgPitch + (c0 - p0) + i] = act_apply(c.act_o, v[i]);
+            for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_o, v[i]);
+            store_row16(out + row * out_stride, c0, c.no, out_vec, v);
           }
-          fence_before_sync();
-          __syncthreads();
-          panel_store(stg, min(32, c.no - p0), row0, n, out, out_stride, p0, t);
-          __syncthreads();
         }
+        fence_before_sync();
+        __syncthreads();                 // all TMEM reads of this tile are done before the next tile's first MMA
       }
     }
   }
@@ -432,35 +426,45 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
   const uint32_t tacc = cx.tmem;
   uint8_t* Xs = smem + c.off_x;
   uint8_t* dZ = smem + c.off_dz;
-  float* stg = reinterpret_cast<float*>(smem + c.off_stg);
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   bool have_wgrad = false;
   bool want_dx = false;
   for (int s = 0; s < c.n_seg; s++) want_dx |= dseg.p[s] != nullptr;
+  const bool dout_vec = ((dout_stride & 3) == 0) && ((((uintptr_t)dout) & 15) == 0);
 
   zero_pad_cols(c, t, Xs);
-  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, dout, blockIdx.x, smem, cx.full);
+  if (t == 0 && (int64_t)blockIdx.x < n_tiles && tile_is_bulk(c, blockIdx.x, n)) issue_prefetch(c, in, blockIdx.x, smem, cx.full);
   __syncwarp();
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
-    const bool bulk = tile_is_bulk(c, tile, n);
-    if (bulk) {
-      mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1;
-      convert_raw(c, smem, t, Xs);
-      if (c.bulk_dout) {                                    // dL/dy rows -> staging panel (pitch 33)
-        const float* rd = reinterpret_cast<const float*>(smem + c.off_raw_dout);
-        for (int u = t; u < kTile * c.no; u += kThreads) stg[(u / c.no) * kStgPitch + u % c.no] = rd[u];
-      }
-    } else {
-      stage_input(c, in, row0, n, t, Xs);
-    }
-    const bool dout_staged = bulk && c.bulk_dout;
+    const int64_t row = row0 + L.row;
+    const bool valid = row < n;
+    if (tile_is_bulk(c, tile, n)) { mbar_wait(cx.full, cx.fphase); cx.fphase ^= 1; convert_raw(c, smem, t, Xs); }
+    else stage_input(c, in, row0, n, t, Xs);
     publish();
     {
       const int64_t nxt = tile + gridDim.x;
-      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, dout, nxt, smem, cx.full);
+      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, nxt, n)) issue_prefetch(c, in, nxt, smem, cx.full);
       __syncwarp();
     }
+    // this thread's first 16 columns of dL/dy are requested NOW and consumed after the forward recompute,
+    // so their HBM latency hides behind the MMA phases
+    float dreg[16];
+    const int d0 = 16 * (int)L.half;
+    {
+      const float* drow = dout + row * dout_stride;
+      if (valid && dout_vec && d0 + 16 <= c.no) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(drow + d0) + q);
+          dreg[4 * q] = g4.x; dreg[4 * q + 1] = g4.y; dreg[4 * q + 2] = g4.z; dreg[4 * q + 3] = g4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) dreg[i] = (valid && d0 + i < c.no) ? __ldg(drow + d0 + i) : 0.f;
+      }
+    }
+    const float daux = (d_aux_exp && valid && L.half == 0) ? __ldg(d_aux_exp + row) : 0.f;
     // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
     for (int l = 0; l < c.nh; l++) {
       if (t == 0) {
@@ -469,8 +473,6 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
         mma_commit(cx.bar);
       }
       __syncwarp();
-      // overlap the (coalesced) load of this tile's upstream gradient with the first MMA
-      if (l == 0 && !dout_staged) panel_load(stg, min(32, c.no), row0, n, dout, dout_stride, 0, t);
       wait_mma(cx);
       epilogue_hidden(c, L, smem + c.off_h[l]);
       publish();
@@ -483,31 +485,23 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
     }
     __syncwarp();
     wait_mma(cx);
-    for (int p0 = 0; p0 < c.nop; p0 += 32) {
-      if (p0 > 0) {     // n_out > 32: bring in the next 32 columns of dL/dy (panel 0 is already staged)
-        __syncthreads();
-        panel_load(stg, min(32, c.no - p0), row0, n, dout, dout_stride, p0, t);
-        __syncthreads();
-      }
-      const int c0 = p0 + 16 * (int)L.half;
-      if (c0 < c.nop) {
-        float v[16];
-        tmem_ld16(L.trow + c0, v);
+    for (int c0 = d0; c0 < c.nop; c0 += 16 * kHalves) {
+      float v[16];
+      tmem_ld16(L.trow + c0, v);
+      if (c0 != d0) {                      // n_out > 16*kHalves: later column groups are read at use
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          float g = 0.f;
-          if (c0 + i < c.no) {
-            const float y = act_apply(c.act_o, v[i]);
-            g = stg[L.row * kStgPitch + (c0 - p0) + i] * act_grad_from_out(c.act_o, y);
-            // TruncExp backward of the density head: g * exp(clamp(z, -7, 7))  (custom_functions.py:211)
-            if (d_aux_exp && c0 + i == 0 && row0 + L.row < n)
-              g = fmaf(__ldg(d_aux_exp + row0 + L.row), __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
-          }
-          v[i] = g;
-        }
-        st_chunk(dZ, kTile, L.row, c0, v);
-        st_chunk(dZ, kTile, L.row, c0 + 8, v + 8);
+        for (int i = 0; i < 16; i++) dreg[i] = (valid && c0 + i < c.no) ? __ldg(dout + row * dout_stride + c0 + i) : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float y = act_apply(c.act_o, v[i]);
+        float g = dreg[i] * act_grad_from_out(c.act_o, y);
+        // TruncExp backward of the density head: g * exp(clamp(z, -7, 7))  (custom_functions.py:211)
+        if (i == 0 && c0 == 0 && d_aux_exp) g = fmaf(daux, __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
+        v[i] = (c0 + i < c.no) ? g : 0.f;
+      }
+      st_chunk(dZ, kTile, L.row, c0, v);
+      st_chunk(dZ, kTile, L.row, c0 + 8, v + 8);
     }
     publish();
     // ---- top-down: wgrad + dgrad per layer
@@ -528,8 +522,8 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
       wait_mma(cx);
       if (l > 0) {
         const uint8_t* H = smem + c.off_h[l - 1];
-        const int cb = (int)L.half * (c.wp >> 1), ce = cb + (c.wp >> 1);
-        for (int c0 = cb; c0 < ce; c0 += 32) {
+        const int cw = c.wp / kHalves, cb = (int)L.half * cw;
+        for (int c0 = cb; c0 < cb + cw; c0 += 32) {
           float v[32], h[32];
           tmem_ld32(L.trow + c0, v);
 #pragma unroll
@@ -542,26 +536,32 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
         publish();
       } else {
         if (want_dx) {
-          // input gradient: 32-column panels through the staging buffer, coalesced per segment
-          for (int p0 = 0; p0 < c.k0; p0 += 32) {
-            const int c0 = p0 + 16 * (int)L.half;
-            if (c0 < c.k0p) {
-              float v[16];
-              tmem_ld16(L.trow + c0, v);
+          // input gradient straight from TMEM to global: each thread owns 64-byte runs of its row
+          for (int c0 = 16 * (int)L.half; c0 < c.k0; c0 += 16 * kHalves) {
+            float v[16];
+            tmem_ld16(L.trow + c0, v);
+            if (valid) {
+              int col = 0;
+              for (int s = 0; s < c.n_seg; s++) {
+                const int w = c.seg_w[s];
+                float* dst = dseg.p[s];
+                if (dst && col < c0 + 16 && col + w > c0) {
+                  float* drow = dst + row * dseg.stride[s];
+                  const bool vec = ((dseg.stride[s] & 3) == 0) && ((col & 3) == 0) && ((w & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
 #pragma unroll
-              for (int i = 0; i < 16; i++) stg[L.row * kStgPitch + (c0 - p0) + i] = v[i];
+                  for (int q = 0; q < 4; q++) {
+                    const int cc = c0 + 4 * q;
+                    if (vec && cc >= col && cc + 4 <= col + w) {
+                      *reinterpret_cast<float4*>(drow + (cc - col)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 4; i++) if (cc + i >= col && cc + i < col + w) drow[cc + i - col] = v[4 * q + i];
+                    }
+                  }
+                }
+                col += w;
+              }
             }
-            fence_before_sync();
-            __syncthreads();
-            int col = 0;
-            for (int s = 0; s < c.n_seg; s++) {
-              const int w = c.seg_w[s];
-              const int lo = max(col, p0), hi = min(col + w, p0 + 32);     // overlap of this segment with the panel
-              if (dseg.p[s] && lo < hi)
-                panel_store(stg + (lo - p0), hi - lo, row0, n, dseg.p[s], dseg.stride[s], lo - col, t);
-              col += w;
-            }
-            __syncthreads();
           }
         }
         publish();
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
       const bool is_out = l == c.nh;
       const int ncols = is_out ? c.nop : (l == 0 ? c.k0p : c.wp);
       const int in_true = l == 0 ? c.k0 : c.w;
-      for (int c0 = 16 * (int)L.half; c0 < ncols; c0 += 32) {       // 16-column groups alternate between the halves
+      for (int c0 = 16 * (int)L.half; c0 < ncols; c0 += 16 * kHalves) {
         float v[16];
         tmem_ld16(L.trow + c.tm_wg[l] + c0, v);
         if (m >= 0 && m < c.w) {
@@ -628,7 +628,6 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   for (int l = n_h; l < kMaxHidden; l++) c.off_h[l] = c.off_h[0];
   c.off_dz = off;
   if (backward) off += al(tile_bytes(kTile, c.wp > c.nop ? c.wp : c.nop));
-  c.off_stg = off; off += al(kTile * kStgPitch * 4);
   // raw landing zone (optional: dropped when it does not fit)
   if (c.bulk) {
     uint32_t o2 = off;
@@ -636,9 +635,8 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
       c.raw_bytes[s] = (uint32_t)(kTile * (c.seg_kind[s] == kSegSH4 ? 3 : c.seg_w[s]) * 4);
       c.off_raw[s] = o2; o2 += al(c.raw_bytes[s]);
     }
-    if (backward && c.bulk_dout) { c.raw_dout_bytes = (uint32_t)(kTile * c.no * 4); c.off_raw_dout = o2; o2 += al(c.raw_dout_bytes); }
-    if (o2 <= 227 * 1024) off = o2; else { c.bulk = 0; c.bulk_dout = 0; }
-  } else c.bulk_dout = 0;
+    if (o2 <= 227 * 1024) off = o2; else c.bulk = 0;
+  }
   c.smem_bytes = off;
   uint32_t cols = (uint32_t)c.wp;
   if ((uint32_t)c.nop > cols) cols = c.nop;
@@ -667,7 +665,7 @@ static int build_cfg(MlpCfg& c, int n_seg, const float* const* seg_ptr, const in
     const int raw_w = seg_kind[s] == kSegSH4 ? 3 : seg_w[s];
     if (seg_stride[s] != raw_w || (((uintptr_t)seg_ptr[s]) & 15) != 0) c.bulk = 0;
   }
-  c.bulk_dout = (dout != nullptr && dout_stride == n_out && n_out <= 32 && (((uintptr_t)dout) & 15) == 0) ? 1 : 0;
+  (void)dout; (void)dout_stride;
   return finalize_cfg(c, backward);
 }
 
