@@ -83,6 +83,35 @@ __device__ __forceinline__ float act_grad_from_out(int a, float y) {
   }
 }
 
+// Array forms: ONE dispatch on the (launch-constant) activation id, then straight-line code — the scalar
+// forms above inside an unrolled loop compile to a jump table per element (BRX + range checks were 15 %
+// of all issued instructions in the first ncu capture of mlp_bw_kernel).
+template <int N> __device__ __forceinline__ void act_apply_arr(int a, float* v) {
+  if (a == kActReLU) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = fmaxf(v[i], 0.f);
+  } else if (a == kActSigmoid) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+  } else if (a == kActExp) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = __expf(v[i]);
+  }
+}
+// v[i] *= act'(.) given the activation OUTPUT y[i]
+template <int N> __device__ __forceinline__ void act_grad_mul_arr(int a, float* v, const float* y) {
+  if (a == kActReLU) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = y[i] > 0.f ? v[i] : 0.f;
+  } else if (a == kActSigmoid) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] *= y[i] * (1.f - y[i]);
+  } else if (a == kActExp) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] *= y[i];
+  }
+}
+
 __device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
   const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
   o[0] = 0.28209479177387814f;
@@ -327,8 +356,7 @@ __device__ __forceinline__ void epilogue_hidden(const MlpCfg& c, const Lane& L, 
   for (int c0 = cb; c0 < cb + cw; c0 += 32) {
     float v[32];
     tmem_ld32(L.trow + c0, v);
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = act_apply(c.act_h, v[i]);
+    act_apply_arr<32>(c.act_h, v);
 #pragma unroll
     for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 8 * q, v + 8 * q);
   }
@@ -398,8 +426,7 @@ __global__ void __launch_bounds__(kThreads) mlp_fw_kernel(MlpCfg c, SegPtrs in, 
           tmem_ld16(L.trow + c0, v);
           if (row < n) {
             if (aux_exp && c0 == 0) aux_exp[row] = __expf(v[0]);
-#pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = act_apply(c.act_o, v[i]);
+            act_apply_arr<16>(c.act_o, v);
             store_row16(out + row * out_stride, c0, c.no, out_vec, v);
           }
         }
@@ -492,46 +519,50 @@ __global__ void __launch_bounds__(kThreads) mlp_bw_kernel(MlpCfg c, SegPtrs in, 
 #pragma unroll
         for (int i = 0; i < 16; i++) dreg[i] = (valid && c0 + i < c.no) ? __ldg(dout + row * dout_stride + c0 + i) : 0.f;
       }
+      const float z0 = v[0];
+      float g[16];
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const float y = act_apply(c.act_o, v[i]);
-        float g = dreg[i] * act_grad_from_out(c.act_o, y);
-        // TruncExp backward of the density head: g * exp(clamp(z, -7, 7))  (custom_functions.py:211)
-        if (i == 0 && c0 == 0 && d_aux_exp) g = fmaf(daux, __expf(fminf(fmaxf(v[0], -7.f), 7.f)), g);
-        v[i] = (c0 + i < c.no) ? g : 0.f;
-      }
+      for (int i = 0; i < 16; i++) g[i] = dreg[i];
+      act_apply_arr<16>(c.act_o, v);                 // v = y
+      act_grad_mul_arr<16>(c.act_o, g, v);           // g = dL/dy * act'(z)
+      // TruncExp backward of the density head: + dL/dsigma * exp(clamp(z0, -7, 7))  (custom_functions.py:211)
+      if (c0 == 0 && d_aux_exp) g[0] = fmaf(daux, __expf(fminf(fmaxf(z0, -7.f), 7.f)), g[0]);
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = (c0 + i < c.no) ? g[i] : 0.f;
       st_chunk(dZ, kTile, L.row, c0, v);
       st_chunk(dZ, kTile, L.row, c0 + 8, v + 8);
     }
     publish();
-    // ---- top-down: wgrad + dgrad per layer
+    // ---- top-down: wgrad + dgrad per layer.  dZ_out lives in its own (narrow) tile; every hidden dZ_l is
+    // written IN PLACE over H_{l} (the thread that reads a 16-byte chunk for the activation mask is the one
+    // that overwrites it), so no wp-wide gradient tile is needed.
     for (int l = c.nh; l >= 0; l--) {
       const bool is_out = l == c.nh;
       const int Nz = is_out ? c.nop : c.wp;                       // width of dZ_l
       const int Kin = l == 0 ? c.k0p : c.wp;                      // width of the layer's input
       const uint32_t ain = sbase + (l == 0 ? c.off_x : c.off_h[l - 1]);
+      const uint32_t dza = sbase + (is_out ? c.off_dz : c.off_h[l]);
       const bool need_dgrad = l > 0 || want_dx;
       if (t == 0) {
         fence_after_sync();
-        if (is_out) issue_wgrad(cx.tmem + c.tm_wg[l], ain, sbase + c.off_dz, c.wp, c.nop, have_wgrad);   // D^T[in x out]
-        else issue_wgrad(cx.tmem + c.tm_wg[l], sbase + c.off_dz, ain, c.wp, Kin, have_wgrad);            // D[out x in]
-        if (need_dgrad) issue_dgrad(tacc, sbase + c.off_dz, sbase + c.off_w[l], (uint32_t)Nz, Kin, Nz);
+        if (is_out) issue_wgrad(cx.tmem + c.tm_wg[l], ain, dza, c.wp, c.nop, have_wgrad);   // D^T[in x out]
+        else issue_wgrad(cx.tmem + c.tm_wg[l], dza, ain, c.wp, Kin, have_wgrad);            // D[out x in]
+        if (need_dgrad) issue_dgrad(tacc, dza, sbase + c.off_w[l], (uint32_t)Nz, Kin, Nz);
         mma_commit(cx.bar);
       }
       __syncwarp();
       wait_mma(cx);
       if (l > 0) {
-        const uint8_t* H = smem + c.off_h[l - 1];
+        uint8_t* H = smem + c.off_h[l - 1];
         const int cw = c.wp / kHalves, cb = (int)L.half * cw;
         for (int c0 = cb; c0 < cb + cw; c0 += 32) {
           float v[32], h[32];
           tmem_ld32(L.trow + c0, v);
 #pragma unroll
           for (int q = 0; q < 4; q++) ld_chunk(H, kTile, L.row, c0 + 8 * q, h + 8 * q);
+          act_grad_mul_arr<32>(c.act_h, v, h);
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] *= act_grad_from_out(c.act_h, h[i]);
-#pragma unroll
-          for (int q = 0; q < 4; q++) st_chunk(dZ, kTile, L.row, c0 + 8 * q, v + 8 * q);
+          for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 8 * q, v + 8 * q);
         }
         publish();
       } else {
@@ -627,7 +658,7 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   for (int l = 0; l < n_h; l++) { c.off_h[l] = off; off += al(tile_bytes(kTile, c.wp)); }
   for (int l = n_h; l < kMaxHidden; l++) c.off_h[l] = c.off_h[0];
   c.off_dz = off;
-  if (backward) off += al(tile_bytes(kTile, c.wp > c.nop ? c.wp : c.nop));
+  if (backward) off += al(tile_bytes(kTile, c.nop));      // dZ_out only; hidden dZ_l overwrite H_l in place
   // raw landing zone (optional: dropped when it does not fit)
   if (c.bulk) {
     uint32_t o2 = off;
