@@ -1,0 +1,137 @@
+"""End-to-end GPU checks of the composed path: the reference-literal NGP
+field (two hash grids, torch density MLP, normals via double backward, semantic / normal heads,
+appearance embedding) and the ngp_pl-shaped NGPCompact, through render() in train and test mode."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tcnn_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_ngp(**kw):
+    from ngp_b200.networks import NGP
+    torch.manual_seed(0)
+    m = NGP(scale=0.5, grid_levels=8, grid_features=8, log2_T_xyz=15, log2_T_rgb=16, **kw).cuda()
+    with torch.no_grad():
+        m.xyz_encoder.params.mul_(3000.0)          # tcnn's U(-1e-4,1e-4) init gives ~zero features; make them O(0.3)
+        m.rgb_encoder.params.mul_(3000.0)
+    return m
+
+
+def _oracle_field(m, x, d, embed=None):
+    """The same field evaluated with plain torch ops (tcnn_oracle) from the module's own parameters."""
+    g1, g2 = m.xyz_encoder.grid, m.rgb_encoder.grid
+    x = x.clone().requires_grad_(True)
+    xn = (x - m.xyz_min) / (m.xyz_max - m.xyz_min)
+    enc = tcnn_oracle.grid_encode(xn, m.xyz_encoder.params, g1.n_levels, g1.n_features, g1.log2_T, g1.base_res, g1.per_level_scale)
+    sig = F.softplus(m.xyz_net(enc)[:, 0])
+    (grads,) = torch.autograd.grad(sig, x, torch.ones_like(sig), create_graph=True)
+    feat = tcnn_oracle.grid_encode(xn, m.rgb_encoder.params, g2.n_levels, g2.n_features, g2.log2_T, g2.base_res, g2.per_level_scale)
+    n_raw = -F.normalize(grads, dim=-1, eps=1e-6)
+    n_pred = -F.normalize(tcnn_oracle.mlp_forward(feat, m.norm_pred_header.params, feat.shape[1], 32, 1, 3), dim=-1, eps=1e-6)
+    sem = torch.softmax(tcnn_oracle.mlp_forward(feat, m.semantic_header.params, feat.shape[1], 32, 1, m.classes), -1)
+    dn = F.normalize(d, dim=-1, eps=1e-6)
+    inp = [tcnn_oracle.sh_encode((dn + 1) / 2, 4), feat] + ([embed] if embed is not None else [])
+    inp = torch.cat(inp, 1)
+    rgb = tcnn_oracle.mlp_forward(inp, m.rgb_net.params, inp.shape[1], 128, 1, 3, "ReLU", "Sigmoid")
+    return sig, rgb, n_raw, n_pred, sem
+
+
+@pytest.mark.parametrize("embed_a", [False, True])
+def test_ngp_field_matches_torch_restatement(embed_a):
+    m = _small_ngp(embed_a=embed_a, embed_a_len=8, classes=7)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 3000
+    x = (torch.rand(n, 3, device="cuda", generator=g) - 0.5) * 0.98
+    d = torch.randn(n, 3, device="cuda", generator=g)
+    kw = {}
+    emb = None
+    if embed_a:
+        emb = torch.randn(n, 8, device="cuda", generator=g) * 0.3
+        kw["embedding_a"] = emb
+    sig, rgb, n_raw, n_pred, sem = m(x, d, **kw)
+    o_sig, o_rgb, o_nraw, o_npred, o_sem = _oracle_field(m, x, d, emb)
+    assert torch.allclose(sig, o_sig, rtol=1e-3, atol=1e-4)
+    cos = (n_raw * o_nraw).sum(-1)
+    assert float(cos.median()) > 0.9999 and float((cos < 0.99).float().mean()) < 0.02     # cell-face flips only
+    assert float((rgb - o_rgb).abs().max()) < 3e-2 and float((rgb - o_rgb).abs().mean()) < 4e-3   # bf16 heads
+    assert float((sem - o_sem).abs().max()) < 3e-2
+    assert float(((n_pred * o_npred).sum(-1)).median()) > 0.999
+    # gradients of a scalar of every output w.r.t. the parameters that feed it, incl. the double backward
+    w = torch.randn(n, device="cuda", generator=g)
+    loss = (sig * w).sum() + (rgb.sum(-1) * w).sum() + (n_raw[:, 0] * w).sum() + (sem[:, 1] * w).sum()
+    o_loss = (o_sig * w).sum() + (o_rgb.sum(-1) * w).sum() + (o_nraw[:, 0] * w).sum() + (o_sem[:, 1] * w).sum()
+    ps = [m.xyz_encoder.params, m.rgb_encoder.params, m.xyz_net[0].weight, m.rgb_net.params]
+    g1 = torch.autograd.grad(loss, ps)
+    g2 = torch.autograd.grad(o_loss, ps)
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    assert rel(g1[2], g2[2]) < 2e-2, rel(g1[2], g2[2])      # torch density MLP weights (through normals too)
+    assert rel(g1[0], g2[0]) < 5e-2, rel(g1[0], g2[0])      # xyz table: first + second order scatter
+    assert rel(g1[1], g2[1]) < 5e-2, rel(g1[1], g2[1])      # rgb table through three bf16 heads
+    assert rel(g1[3], g2[3]) < 5e-2, rel(g1[3], g2[3])
+
+
+def _scene_and_model(model_kind):
+    from ngp_b200 import vren
+    from ngp_b200.networks import NGPCompact
+    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    scene = BoxScene("lego", device="cuda")
+    if model_kind == "compact":
+        torch.manual_seed(0)
+        m = NGPCompact(scale=0.5).cuda()
+    else:
+        m = _small_ngp(classes=7)
+    m.density_grid.copy_(scene_density_grid(scene))
+    vren.packbits(m.density_grid, 0.5, m.density_bitfield)
+    return scene, m
+
+
+@pytest.mark.parametrize("kind", ["compact", "ngp"])
+def test_training_converges_and_test_render_agrees(kind):
+    from ngp_b200.rendering import render
+    from ngp_b200.trainer import Trainer, psnr
+    scene, m = _scene_and_model(kind)
+    classes = 0 if kind == "compact" else 7
+    kw = dict(exp_step_factor=0.0, num_classes=classes)
+    if kind == "ngp":
+        kw["normal_ref"] = True
+    tr = Trainer(m, lr=1e-2, render_kwargs=kw, max_grad_norm=50.0)
+    poses = scene.poses(20)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    losses = []
+    for it in range(60):
+        ro, rd = scene.sample_rays(8192, poses, gen)
+        rgb, *_ = scene.shade(ro, rd)
+        loss, res = tr.train_step(ro, rd, rgb, update_grid=False)
+        losses.append(float(loss))
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-5:]) < 0.5 * np.mean(losses[:3]), (losses[:3], losses[-5:])
+    # the adaptive test-time renderer and the training renderer see the same field
+    ro, rd = scene.sample_rays(4096, poses, gen)
+    gt, *_ = scene.shade(ro, rd)
+    with torch.no_grad():
+        a = render(m, ro, rd, exp_step_factor=0.0, num_classes=classes)
+        b = render(m, ro, rd, exp_step_factor=0.0, num_classes=classes, test_time=True, T_threshold=1e-4)
+    assert float(psnr(a["rgb"], gt)) > 15
+    assert float(psnr(b["rgb"], a["rgb"])) > 30, float(psnr(b["rgb"], a["rgb"]))
+    assert torch.allclose(a["opacity"], b["opacity"], atol=5e-2)
+    assert b["depth"].shape == (4096,) and b["semantic"].shape == (4096, 1)
+    if kind == "ngp":
+        assert torch.isfinite(b["normal_raw"]).all() and b["normal_pred"].shape == (4096, 3)
+
+
+def test_occupancy_update_runs_and_keeps_bitfield_consistent():
+    from ngp_b200 import vren
+    scene, m = _scene_and_model("compact")
+    before = int(torch.count_nonzero(m.density_bitfield))
+    for warm in (True, False):
+        m.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=warm)
+    thr_grid = m.density_grid.clone()
+    pos = thr_grid > 0
+    mean = float((thr_grid * pos).sum() / pos.sum().clamp(min=1))
+    ref = torch.zeros_like(m.density_bitfield)
+    vren.packbits(thr_grid, min(mean, 0.01 * 1024 / 3 ** 0.5), ref)
+    assert torch.equal(ref, m.density_bitfield) and before > 0
