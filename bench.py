@@ -275,7 +275,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--pretrain", type=int, default=300)
+    ap.add_argument("--pretrain", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":
