@@ -141,6 +141,33 @@ def kernel_breakdown(model, xyzs, dirs):
     return out
 
 
+def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20):
+    """Test-time rendering (BASELINE.json configs[4]): full frames through raymarching_test +
+    composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules."""
+    from ngp_b200.rendering import render
+    out = {}
+    with torch.no_grad():
+        for sched in ("geometric", "reference"):
+            def frame(i):
+                ro, rd = scene.image_rays(poses[i % poses.shape[0]], wh=wh)
+                tot = 0
+                for a in range(0, ro.shape[0], chunk):
+                    r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=0.0, num_classes=0, test_time=True,
+                               T_threshold=1e-2, sample_schedule=sched)
+                    tot += int(r["total_samples"])
+                return tot, ro.shape[0]
+            frame(0); torch.cuda.synchronize()
+            n = frames if sched == "geometric" else 1
+            t0 = time.perf_counter()
+            for i in range(n):
+                tot, nr = frame(i + 1)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n
+            out[sched] = {"Mrays_per_s": nr / dt / 1e6, "ms_per_frame": dt * 1e3, "samples_per_ray": tot / nr}
+    return {"metric": "render Mrays/s", "frame": f"{wh[0]}x{wh[1]}", "value": out["geometric"]["Mrays_per_s"], "unit": "Mrays/s",
+            "timing": "wall clock incl. the per-round host read-backs, rays generated on device", **{k: v for k, v in out.items()}}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def gpu_arm(args):
     import torch.distributed as dist
@@ -251,6 +278,7 @@ def gpu_arm(args):
             "peak_source": pk_src, "traffic": None, "samples_per_launch": int(xyzs.shape[0])}
     roof["frac"] = roof["achieved"] / roof["peak"]
 
+    rend = render_bench(model, scene, poses) if not args.no_render else None
     cpu, _ = cpu_arm(steps=4, warmup=1)
     value = world * R * args.steps / t_res
     line = {
@@ -263,7 +291,7 @@ def gpu_arm(args):
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
         "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / args.steps * 1e3},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "render": rend,
     }
     print(json.dumps(line))
     if world > 1:
@@ -277,6 +305,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pretrain", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-render", action="store_true", help="skip the test-time render sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:

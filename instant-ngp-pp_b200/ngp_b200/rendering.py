@@ -36,7 +36,17 @@ def render(model, rays_o, rays_d, **kwargs):
 def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pred, normal_raw, sem, **kwargs):
     """Adaptive test-time march/compose loop (rendering.py:46-133): while rays are alive, march each
     alive ray to its next N_samples occupied samples, evaluate the field there, composite in place,
-    drop converged rays.  N_samples grows as rays die: max(min(N_rays//N_alive, 64), min_samples)."""
+    drop converged rays.
+
+    kwargs['sample_schedule']:
+      'reference' — the reference's chunk sizes: max(min(N_rays//N_alive, 64), min_samples) per round,
+                    i.e. ONE sample per ray per round while most rays are alive (dozens to hundreds of
+                    rounds, each with several host syncs);
+      'geometric' (default) — 4, 8, 16, ... samples per round: <= 9 rounds to reach MAX_SAMPLES and one
+                    host read-back per round.  The marcher resumes every ray exactly where it stopped
+                    and the compositor is a per-ray sequential recurrence, so the composited result
+                    does not depend on the chunking (up to the association of per-round partial sums).
+    """
     N_rays = len(rays_o)
     device = rays_o.device
     esf = kwargs.get("exp_step_factor", 0.)
@@ -44,15 +54,21 @@ def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pre
     T_thr = kwargs.get("T_threshold", 1e-4)
     max_samples = kwargs.get("max_samples", MAX_SAMPLES)
     min_samples = 1 if esf == 0 else 4
+    schedule = kwargs.get("sample_schedule", "geometric")
     alive = torch.arange(N_rays, device=device)
     samples = 0
+    rnd = 0
     total_samples = torch.zeros((), dtype=torch.int64, device=device)
 
     while samples < max_samples:
         N_alive = len(alive)
         if N_alive == 0:
             break
-        N_samples = max(min(N_rays // N_alive, 64), min_samples)
+        if schedule == "reference":
+            N_samples = max(min(N_rays // N_alive, 64), min_samples)
+        else:
+            N_samples = min(4 << rnd, 128, max_samples - samples)
+        rnd += 1
         samples += N_samples
         xyzs, dirs, deltas, ts, N_eff = vren.raymarching_test(
             rays_o, rays_d, hits_t, alive, model.density_bitfield, model.cascades, model.scale, esf,

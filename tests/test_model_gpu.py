@@ -135,3 +135,23 @@ def test_occupancy_update_runs_and_keeps_bitfield_consistent():
     ref = torch.zeros_like(m.density_bitfield)
     vren.packbits(thr_grid, min(mean, 0.01 * 1024 / 3 ** 0.5), ref)
     assert torch.equal(ref, m.density_bitfield) and before > 0
+
+
+def test_geometric_schedule_renders_the_same_image_as_the_reference_schedule():
+    from ngp_b200.rendering import render
+    from ngp_b200.trainer import Trainer
+    scene, m = _scene_and_model("compact")
+    tr = Trainer(m, lr=1e-2, render_kwargs=dict(exp_step_factor=0.0, num_classes=0))
+    poses = scene.poses(20)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(40):
+        ro, rd = scene.sample_rays(8192, poses, gen)
+        rgb, *_ = scene.shade(ro, rd)
+        tr.train_step(ro, rd, rgb, update_grid=False)
+    ro, rd = scene.image_rays(poses[0], wh=(100, 100))
+    with torch.no_grad():
+        a = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="reference")
+        b = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric")
+    assert torch.allclose(a["rgb"], b["rgb"], atol=2e-5) and torch.allclose(a["depth"], b["depth"], atol=2e-4)
+    assert torch.allclose(a["opacity"], b["opacity"], atol=2e-5)
+    assert int(b["total_samples"]) >= int(a["total_samples"])          # coarser chunks march a little further
