@@ -30,7 +30,7 @@ namespace ngp {
 using namespace tc05;
 
 constexpr int kTile = 128;          // samples (rows) per tile = TMEM lanes
-constexpr int kThreads = 128;       // 4 warps: warp w reads TMEM lanes 32*w..  (256 = two column halves; measured slower)
+constexpr int kThreads = 128;       // 4 warps: warp w reads TMEM lanes 32*w..  (256 = two column halves: measured no faster, r01 call 16)
 constexpr int kHalves = kThreads / kTile;
 constexpr int kMaxSeg = 3;
 constexpr int kMaxHidden = 6;

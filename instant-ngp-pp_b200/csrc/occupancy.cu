@@ -56,31 +56,52 @@ template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 
-// One warp packs 32 consecutive cells per step: every lane reads one cell (coalesced 128 B),
-// `__ballot_sync` yields the 32 occupancy bits = 4 output bytes in exactly the reference's
-// bit order (bit i of byte n <-> cell 8n+i, raymarching.cu:133-140, strict '>').
-// Comparison is done in the grid's own dtype promoted to the type the reference compares in
-// (scalar_t > float  ==> float for half/float, double for double).
+// One thread packs 32 consecutive cells into one 32-bit word: eight 16-byte loads in flight per
+// thread (128 B), one 4-byte store, consecutive threads on consecutive 128-byte lines.  Bit order is the
+// reference's (bit i of byte n <-> cell 8n+i, raymarching.cu:133-140, strict '>'); the comparison is
+// done in the type the reference compares in (scalar_t > float ==> float for half/float, double for
+// double).  A scalar tail handles byte counts that are not a multiple of 4.
+template <typename T> __device__ __forceinline__ bool above(T v, float thr) {
+  if constexpr (sizeof(T) == 8) return v > (double)thr;
+  else return to_f<T>(v) > thr;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) packbits_kernel(const T* __restrict__ grid, int64_t n_bytes, float thr,
                                                        uint8_t* __restrict__ bitfield) {
-  const int lane = threadIdx.x & 31;
-  const int64_t n_cells = n_bytes * 8;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_words = (n_cells + 31) >> 5;
-  for (int64_t w = warp0; w < n_words; w += n_warps) {
-    const int64_t cell = (w << 5) + lane;
-    bool occ = false;
-    if (cell < n_cells) {
-      if constexpr (sizeof(T) == 8) occ = grid[cell] > (double)thr;
-      else occ = to_f<T>(grid[cell]) > thr;
+  const int64_t n_words = n_bytes >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool aligned = (((uintptr_t)grid) & 15) == 0 && (((uintptr_t)bitfield) & 3) == 0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+    const T* src = grid + (w << 5);
+    uint32_t bits = 0;
+    if constexpr (sizeof(T) == 4) {
+      if (aligned) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldg(reinterpret_cast<const float4*>(src) + k);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          bits |= (v[k].x > thr ? 1u : 0u) << (4 * k);
+          bits |= (v[k].y > thr ? 1u : 0u) << (4 * k + 1);
+          bits |= (v[k].z > thr ? 1u : 0u) << (4 * k + 2);
+          bits |= (v[k].w > thr ? 1u : 0u) << (4 * k + 3);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+        continue;
+      }
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, occ);
-    if (lane < 4) {
-      const int64_t byte = (w << 2) + lane;
-      if (byte < n_bytes) bitfield[byte] = (uint8_t)(bits >> (8 * lane));
-    }
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) bits |= (above<T>(src[k], thr) ? 1u : 0u) << k;
+    if (aligned) reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+    else { for (int b = 0; b < 4; b++) bitfield[(w << 2) + b] = (uint8_t)(bits >> (8 * b)); }
+  }
+  // tail bytes
+  const int64_t tb = (n_words << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tb < n_bytes) {
+    uint8_t b8 = 0;
+    for (int k = 0; k < 8; k++) b8 |= above<T>(grid[8 * tb + k], thr) ? (uint8_t)(1u << k) : 0;
+    bitfield[tb] = b8;
   }
 }
 
@@ -117,7 +138,7 @@ NGP_API int ngp_morton3D_invert(const int32_t* indices, int64_t n, int32_t* coor
 NGP_API int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold,
                          uint8_t* density_bitfield, void* stream) {
   if (n_bytes <= 0) return 0;
-  const int grid = stream_grid(n_bytes * 8, 256 * 4);
+  const int grid = stream_grid((n_bytes + 3) / 4, 256);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case 0: packbits_kernel<float><<<grid, 256, 0, s>>>((const float*)density_grid, n_bytes, density_threshold, density_bitfield); break;
