@@ -62,7 +62,7 @@ def last_error() -> str:
     return lib.ngp_last_error().decode()
 
 
-_KERNELS_PER_CALL = {"raymarching_train/count": 2}     # count + block scan; every other entry point = 1 launch
+_KERNELS_PER_CALL = {"raymarching_train/count": 3}     # count + block sums + block scan; every other entry point = 1 launch
 _launches = 0
 
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_tcnn_gpu.py -q -m gpu -k mlp --timeout=300 > gpurun_out/test_mlp.log 2>&1; echo "mlp tests rc=$?"; tail -3 gpurun_out/test_mlp.log
+timeout 900 python -m pytest tests/test_vren_gpu.py -q -m gpu --timeout=300 > gpurun_out/test_vren.log 2>&1; echo "vren tests rc=$?"; tail -3 gpurun_out/test_vren.log
 timeout 600 python bench.py --steps 10 --warmup 3 --pretrain 100 --no-render > gpurun_out/bench_quick.log 2>&1; echo "rc=$?"
 python - <<'PY'
 import json
@@ -11,3 +11,4 @@ for l in open('gpurun_out/bench_quick.log'):
         print('ms/step', round(d['ms_per_step'],3), 'Mrays/s', round(d['value']/1e6,2), 'e2e', round(d['e2e']['value']/1e6,2), 'spr', round(d['config']['samples_per_ray'],1))
         for k,v in d['kernels'].items(): print(' ', k, round(v['ms'],3))
 PY
+timeout 300 python tools/step_profile.py 40 > gpurun_out/step_profile.txt 2>&1; grep -E "ngp::|Self CUDA time total" gpurun_out/step_profile.txt | cut -c1-75,150-230 | head -24
