@@ -17,6 +17,7 @@
 // The per-ray float recurrence (t += dt, cell lookup, empty-cell skip) is the reference's, step by
 // step, with the FMA contractions of the reference build made explicit (common.cuh).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ngp {
 
@@ -118,22 +119,23 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     const float* __restrict__ noise, MarchParams p, int max_samples, int64_t n_rays,
     int32_t* __restrict__ n_samples, float2* __restrict__ scratch, int* __restrict__ next_ray) {
   const unsigned lane = threadIdx.x & 31u;
-  bool have = false;
+  bool have = false, exhausted = false;     // exhausted: the counter has run past n_rays, stop asking
   int64_t r = 0;
   Ray q;
   float t = 0.f, t2 = 0.f, x, y, z, dt;
   int N = 0;
   float2* row = nullptr;
   while (true) {
-    const unsigned need = __ballot_sync(0xffffffffu, !have);
+    const unsigned need = __ballot_sync(0xffffffffu, !have && !exhausted);
     if (need) {
       int base = 0;
       const int leader = __ffs(need) - 1;
       if ((int)lane == leader) base = atomicAdd(next_ray, __popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (!have) {
+      if (!have && !exhausted) {
         r = (int64_t)base + __popc(need & ((1u << lane) - 1u));
-        if (r < n_rays) {
+        if (r >= n_rays) exhausted = true;
+        else {
           have = true;
           q = load_ray(rays_o, rays_d, r);
           float t1 = __ldg(hits_t + 2 * r);
@@ -142,8 +144,8 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
           t = t1; N = 0; row = scratch + r * kScratch;
         }
       }
-      if (!__any_sync(0xffffffffu, have)) break;
     }
+    if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
       if (0 <= t && t < t2 && N < max_samples) {
         if (march_step<kSimple>(q, p, t, x, y, z, dt)) {
@@ -373,7 +375,9 @@ NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d
   int* next_ray = reinterpret_cast<int*>(w.t_start);          // first word of the (otherwise unused) t_start area
   cudaMemsetAsync(next_ray, 0, sizeof(int), s);
   const bool simple = cascades == 1 && exp_step_factor == 0.0f;
-  const int G = (int)(ceil_div(n_rays, kMarchBlock) < (int64_t)kSMs * 6 ? ceil_div(n_rays, kMarchBlock) : (int64_t)kSMs * 6);
+  static const int ctas_per_sm = getenv("NGP_MARCH_CTAS_PER_SM") ? atoi(getenv("NGP_MARCH_CTAS_PER_SM")) : 4;   // swept 1..6 on B200 (r01 call 19): 4 is the minimum
+  const int64_t gmax = (int64_t)kSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+  const int G = (int)(ceil_div(n_rays, kMarchBlock) < gmax ? ceil_div(n_rays, kMarchBlock) : gmax);
   if (simple) march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, next_ray);
   else march_count_kernel<false><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, next_ray);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/count");

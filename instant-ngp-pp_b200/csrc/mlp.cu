@@ -350,15 +350,29 @@ __device__ __forceinline__ Lane make_lane(uint32_t tmem) {
   L.trow = tmem + ((((L.t >> 5) & 3u) * 32u) << 16);
   return L;
 }
-// hidden-layer epilogue: this thread's share of the wp accumulator columns -> act -> bf16 tile row
+// hidden-layer epilogue: this thread's share of the wp accumulator columns -> act -> bf16 tile row.
+// Columns are fetched 64 at a time (two x32 TMEM loads in flight, ONE wait).
 __device__ __forceinline__ void epilogue_hidden(const MlpCfg& c, const Lane& L, uint8_t* H) {
   const int cw = c.wp / kHalves, cb = (int)L.half * cw;
-  for (int c0 = cb; c0 < cb + cw; c0 += 32) {
+  for (int c0 = cb; c0 < cb + cw; c0 += 64) {
+    uint32_t r0[32], r1[32];
+    const bool two = c0 + 32 < cb + cw;
+    tmem_ld32_nowait(L.trow + c0, r0);
+    if (two) tmem_ld32_nowait(L.trow + c0 + 32, r1);
+    tmem_wait_ld();
     float v[32];
-    tmem_ld32(L.trow + c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r0[i]);
     act_apply_arr<32>(c.act_h, v);
 #pragma unroll
     for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 8 * q, v + 8 * q);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r1[i]);
+      act_apply_arr<32>(c.act_h, v);
+#pragma unroll
+      for (int q = 0; q < 4; q++) st_chunk(H, kTile, L.row, c0 + 32 + 8 * q, v + 8 * q);
+    }
   }
 }
 // 16 consecutive columns [c0, c0+16) of one row -> global, clipped to [0, ncols); 16-byte stores when the
