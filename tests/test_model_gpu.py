@@ -155,3 +155,48 @@ def test_geometric_schedule_renders_the_same_image_as_the_reference_schedule():
     assert torch.allclose(a["rgb"], b["rgb"], atol=2e-5) and torch.allclose(a["depth"], b["depth"], atol=2e-4)
     assert torch.allclose(a["opacity"], b["opacity"], atol=2e-5)
     assert int(b["total_samples"]) > 0 and int(a["total_samples"]) > 0
+
+
+def test_street_shaped_scene_cascades_semantics_normals_embedding():
+    """BASELINE.json configs[2]/[3] in miniature: unbounded-style scene (scale 8 -> 5 cascades, exponential
+    stepping 1/256), appearance embedding, 10 semantic classes, normal_ref + semantic + distortion losses,
+    global-norm clip 50 — the KITTI-360 / Playground recipe (configs/kitti360_1538.txt, configs/Playground.txt)."""
+    from ngp_b200 import vren
+    from ngp_b200.networks import NGP
+    from ngp_b200.rendering import render
+    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    from ngp_b200.trainer import Trainer
+    scene = BoxScene("street", device="cuda")
+    torch.manual_seed(0)
+    m = NGP(scale=8.0, grid_levels=8, grid_features=8, log2_T_xyz=15, log2_T_rgb=16, embed_a=True, embed_a_len=8, classes=10).cuda()
+    assert m.cascades == 5 and m.density_bitfield.numel() == 5 * 128 ** 3 // 8
+    with torch.no_grad():
+        m.xyz_encoder.params.mul_(3000.0); m.rgb_encoder.params.mul_(3000.0)
+    m.density_grid.copy_(scene_density_grid(scene))
+    vren.packbits(m.density_grid, 0.5, m.density_bitfield)
+    emb = torch.nn.Embedding(16, 8).cuda()
+    kw = dict(exp_step_factor=1.0 / 256, num_classes=10, normal_ref=True, semantic=True, random_bg=True)
+    tr = Trainer(torch.nn.ModuleList([m, emb]), lr=2e-3, render_kwargs=kw, max_grad_norm=50.0)
+    tr.model = m                                              # the trainer renders with the field; the optimiser also owns emb
+    poses = scene.poses(16)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    losses = []
+    for it in range(30):
+        img = torch.randint(16, (4096,), device="cuda", generator=gen)
+        u = torch.randint(scene.img_wh[0], (4096,), device="cuda", generator=gen).float()
+        v = torch.randint(scene.img_wh[1], (4096,), device="cuda", generator=gen).float()
+        ro, rd = scene.rays_from_pixels(poses, img, u, v)
+        rgb, _, _, label = scene.shade(ro, rd)
+        res = render(m, ro, rd, embedding_a=emb(img), **kw)
+        d = tr.loss_fn(res, {"rgb": rgb, "label": label}, **kw)
+        loss = sum(x.mean() for x in d.values())
+        tr.opt.zero_grad(set_to_none=True); loss.backward(); tr.opt.step()
+        losses.append(float(loss))
+        assert res["semantic"].shape == (4096, 10) and res["normal_pred"].shape == (4096, 3)
+        assert res["Ro"].shape == (4096,) and res["Rp"].shape == (4096, 3)
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:3])
+    assert emb.weight.grad is not None and float(emb.weight.grad.abs().sum()) > 0
+    with torch.no_grad():
+        out = render(m, ro[:2048], rd[:2048], embedding_a=emb(img[:1]), exp_step_factor=1.0 / 256, num_classes=10,
+                     test_time=True, T_threshold=1e-2)
+    assert torch.isfinite(out["rgb"]).all() and out["semantic"].max() < 10
