@@ -68,6 +68,20 @@ int ngp_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t
                          int grid_size, int max_samples, int n_samples, int64_t n_alive, float* xyzs, float* dirs,
                          float* deltas, float* ts, int32_t* n_eff_samples, void* stream);
 
+/* ------------------------------------------------------------------ f3: test-time wavefront renderer
+ * models/rendering.py:46-133 (volume_render loop) = per round raymarching_test + composite_test_fw + Python
+ * compaction.  One advance launch per round composites the previous round and marches the next one. */
+int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                       int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
+                       const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
+                       int cascades, float scale, float exp_step_factor, int grid_size, int max_samples, int n_next,
+                       float* opacity, float* depth, float* rgb, int64_t* alive_out, int32_t* counters, void* workspace,
+                       void* stream);
+int ngp_render_emit(const float* rays_o, const float* rays_d, const float* hits_t, const int64_t* alive_out,
+                    int64_t n_slots, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                    int grid_size, int max_samples, const void* workspace, int64_t capacity, int64_t* rays_a,
+                    float* xyzs, float* dirs, float* deltas, float* ts, int32_t* counters, void* stream);
+
 /* ------------------------------------------------------------------ a4: training compositor
  * vren.composite_train_fw  binding.cpp:121-145 -> volumerendering.cu:118-164
  * vren.composite_train_bw  binding.cpp:148-188 -> volumerendering.cu:249-311

@@ -222,7 +222,9 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     MarchParams p, int64_t n_rays, const int32_t* __restrict__ n_samples,
     const int64_t* __restrict__ block_offsets, const float2* __restrict__ scratch, int64_t capacity,
     int64_t* __restrict__ rays_a, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-    float* __restrict__ ts) {
+    float* __restrict__ ts, const int64_t* __restrict__ slot_to_ray) {
+  // slot_to_ray (optional): position i of n_samples / scratch / rays_a belongs to ray slot_to_ray[i]
+  // (test-time wavefront: slots are the currently alive rays); NULL = identity (training).
   __shared__ int64_t s_start[kMarchBlock];
   {
     const int64_t r = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     int total;
     const int64_t start = block_offsets[blockIdx.x] + block_exclusive_scan(N, &total);
     s_start[threadIdx.x] = start;
-    if (r < n_rays) { rays_a[3 * r] = r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = N; }
+    if (r < n_rays) { rays_a[3 * r] = slot_to_ray ? (N > 0 ? slot_to_ray[r] : 0) : r; rays_a[3 * r + 1] = start; rays_a[3 * r + 2] = N; }
   }
   __syncthreads();
   const int j = threadIdx.x & 7;
@@ -241,8 +243,9 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     const int N = n_samples[r];
     if (N == 0) continue;
     const int64_t start = s_start[lr];
-    const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
-    const float dx = __ldg(rays_d + 3 * r), dy = __ldg(rays_d + 3 * r + 1), dz = __ldg(rays_d + 3 * r + 2);
+    const int64_t ray = slot_to_ray ? slot_to_ray[r] : r;
+    const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
+    const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
     const float2* row = scratch + r * kScratch;
     const int nrec = min(N, kScratch);
     for (int s = j; s < nrec; s += 8) {
@@ -255,8 +258,8 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     }
     if (N > kScratch && j == 0) {
       // long ray: resume the serial march right after the last recorded sample
-      const Ray q = load_ray(rays_o, rays_d, r);
-      const float t2 = __ldg(hits_t + 2 * r + 1);
+      const Ray q = load_ray(rays_o, rays_d, ray);
+      const float t2 = __ldg(hits_t + 2 * ray + 1);
       const float2 last = row[kScratch - 1];
       float t = __fadd_rn(last.x, last.y), x, y, z, dt;
       int s = kScratch;
@@ -311,6 +314,75 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
     dirs[3 * o] = 0.f; dirs[3 * o + 1] = 0.f; dirs[3 * o + 2] = 0.f;
     ts[o] = 0.f; deltas[o] = 0.f;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Test-time wavefront renderer (replaces the Python loop of models/rendering.py:46-133 + the per-round
+// raymarching_test / composite_test_fw pair).  One launch per round, one thread per currently alive ray:
+//   1. composite the samples this ray got in the PREVIOUS round (volumerendering.cu:335-373 semantics:
+//      resume T = 1 - opacity, stop at T <= T_threshold),
+//   2. if the ray is still alive and a next round exists, append it to the next alive list and march its
+//      next <= n_next occupied samples (raymarching.cu:335-404 incl. the calc_dt(cascades) argument),
+//      recording (t, dt) in the slot's scratch row; march_emit then packs them.
+// Rays never wait for each other across rounds, the host reads back two counters per round, and the
+// field is only evaluated on samples that exist.
+__global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t,
+    const int64_t* __restrict__ alive_in, int64_t n_alive_in, const int64_t* __restrict__ prev_rays_a,
+    const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+    const float* __restrict__ ts, float T_thr, MarchParams p, int n_next, float* __restrict__ opacity,
+    float* __restrict__ depth, float* __restrict__ rgb, int64_t* __restrict__ alive_out, int32_t* __restrict__ counters,
+    int32_t* __restrict__ n_samples, float2* __restrict__ scratch) {
+  const int64_t i = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  bool alive = i < n_alive_in;
+  int64_t r = 0;
+  if (alive) {
+    r = alive_in ? alive_in[i] : i;
+    if (prev_rays_a) {
+      const int64_t start = prev_rays_a[3 * i + 1];
+      const int N = (int)prev_rays_a[3 * i + 2];
+      if (N == 0) alive = false;                       // marched to the end of the box without a sample
+      else {
+        float T = 1.0f - opacity[r];
+        float aO = 0.f, aD = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
+        for (int s = 0; s < N; s++) {
+          const int64_t o = start + s;
+          const float a = 1.0f - __expf(-__ldg(sigmas + o) * __ldg(deltas + o));
+          const float w = a * T;
+          aR = fmaf(w, __ldg(rgbs + 3 * o), aR); aG = fmaf(w, __ldg(rgbs + 3 * o + 1), aG); aB = fmaf(w, __ldg(rgbs + 3 * o + 2), aB);
+          aD = fmaf(w, __ldg(ts + o), aD);
+          aO += w;
+          T *= 1.0f - a;
+          if (T <= T_thr) { alive = false; break; }
+        }
+        opacity[r] += aO; depth[r] += aD;
+        rgb[3 * r] += aR; rgb[3 * r + 1] += aG; rgb[3 * r + 2] += aB;
+      }
+    }
+  }
+  if (n_next <= 0) return;
+  // compact the survivors (warp-aggregated append; order is irrelevant, every ray owns its slot)
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  int base = 0;
+  const unsigned lane = threadIdx.x & 31u;
+  if (m && (int)lane == __ffs(m) - 1) base = atomicAdd(counters, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, m ? __ffs(m) - 1 : 0);
+  if (!alive) return;
+  const int64_t j = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+  alive_out[j] = r;
+  const Ray q = load_ray(rays_o, rays_d, r);
+  float t = hits_t[2 * r], x, y, z, dt, t_mark = t;
+  const float t2 = hits_t[2 * r + 1];
+  float2* row = scratch + j * kScratch;
+  int s = 0;
+  while (t < t2 && s < n_next) {
+    if (march_step(q, p, t, x, y, z, dt)) {
+      row[s] = make_float2(t, dt);
+      t = __fadd_rn(t, dt); t_mark = t; s++;
+    }
+  }
+  if (s > 0) hits_t[2 * r] = t_mark;
+  n_samples[j] = s;
 }
 
 static MarchParams make_params(const uint8_t* bitfield, int cascades, float scale, float dt_scale, float esf,
@@ -401,7 +473,7 @@ NGP_API int ngp_raymarching_train_write(const float* rays_o, const float* rays_d
   const int B = (int)ceil_div(n_rays, kMarchBlock);
   march_emit_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, p, n_rays, w.n_samples,
                                                                  w.block_offsets, w.scratch, capacity,
-                                                                 rays_a, xyzs, dirs, deltas, ts);
+                                                                 rays_a, xyzs, dirs, deltas, ts, nullptr);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_write");
   return 0;
 }
@@ -418,5 +490,56 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
   march_test_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples,
                                                                  n_alive, xyzs, dirs, deltas, ts, n_eff_samples);
   NGP_LAUNCH_CHECK("ngp_raymarching_test");
+  return 0;
+}
+
+// ---- test-time wavefront renderer ------------------------------------------------------------------
+// Round k of the renderer that replaces models/rendering.py:46-133 (volume_render).  Composites the previous
+// round's packed samples of every alive ray (prev_rays_a (n_alive_in,3) = [ray, start, N] per slot, NULL in
+// round 0), appends survivors to alive_out (counters[0] = their number) and marches their next <= n_next
+// samples into the workspace; ngp_render_emit then packs them.  n_next = 0 -> composite only (last round).
+// n_next must be <= 256.  workspace: ngp_raymarching_train_workspace_bytes(n_alive_in).
+NGP_API int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                               int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
+                               const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
+                               int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
+                               int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
+                               int32_t* counters, void* workspace, void* stream) {
+  if (n_alive_in <= 0) return 0;
+  if (n_next > kScratch) return set_error_msg("ngp_render_advance: n_next must be <= 256");
+  cudaStream_t s = (cudaStream_t)stream;
+  const MarchWs w = carve(workspace, n_alive_in);
+  const MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), s);
+  if (n_next > 0) cudaMemsetAsync(w.n_samples, 0, n_alive_in * sizeof(int32_t), s);
+  const int B = (int)ceil_div(n_alive_in, kMarchBlock);
+  render_advance_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_in, n_alive_in, prev_rays_a, sigmas, rgbs,
+                                                 deltas, ts, T_threshold, p, n_next, opacity, depth, rgb, alive_out, counters,
+                                                 w.n_samples, w.scratch);
+  NGP_LAUNCH_CHECK("ngp_render_advance");
+  return 0;
+}
+
+// Packs the samples recorded by ngp_render_advance: rays_a (n_slots,3) = [ray, start, N] per slot of alive_out,
+// xyzs/dirs (S,3), deltas/ts (S); counters[1] = S.  n_slots = an upper bound of counters[0] (n_alive_in is fine:
+// unused slots hold N = 0).  capacity >= n_slots * n_next is always enough.
+NGP_API int ngp_render_emit(const float* rays_o, const float* rays_d, const float* hits_t, const int64_t* alive_out,
+                            int64_t n_slots, const uint8_t* density_bitfield, int cascades, float scale,
+                            float exp_step_factor, int grid_size, int max_samples, const void* workspace,
+                            int64_t capacity, int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                            int32_t* counters, void* stream) {
+  if (n_slots <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const MarchWs w = carve((void*)workspace, n_slots);
+  const MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  const int B = (int)ceil_div(n_slots, kMarchBlock);
+  block_sums_kernel<<<B, kMarchBlock, 0, s>>>(w.n_samples, n_slots, w.block_sums);
+  NGP_LAUNCH_CHECK("ngp_render_emit/sums");
+  block_scan_kernel<<<1, 1024, 0, s>>>(w.block_sums, B, w.block_offsets, nullptr, n_slots, w.total);
+  NGP_LAUNCH_CHECK("ngp_render_emit/scan");
+  march_emit_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, p, n_slots, w.n_samples, w.block_offsets, w.scratch,
+                                             capacity, rays_a, xyzs, dirs, deltas, ts, alive_out);
+  NGP_LAUNCH_CHECK("ngp_render_emit/emit");
+  cudaMemcpyAsync(counters + 1, w.total, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);   // low word of the int64 total
   return 0;
 }

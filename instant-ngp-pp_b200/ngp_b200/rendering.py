@@ -105,11 +105,70 @@ def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pre
 
 
 @torch.no_grad()
+def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs):
+    """Test-time renderer for fields without normal / semantic heads: the reference's march -> evaluate ->
+    composite -> compact loop (rendering.py:46-133) as ONE fused advance kernel per round (composite the
+    previous round, compact the survivors, march the next round), a packing pass, and the field evaluation on
+    exactly the samples that exist.  Rounds take 4, 8, 16, ... samples; the host reads two counters per round.
+    Same samples and the same per-ray compositing recurrence as the reference loop."""
+    from . import _lib
+    from ._lib import lib, ptr, check, stream
+    _lib.require_device()
+    N_rays, dev = len(rays_o), rays_o.device
+    esf = float(kwargs.get("exp_step_factor", 0.))
+    T_thr = float(kwargs.get("T_threshold", 1e-4))
+    max_samples = int(kwargs.get("max_samples", MAX_SAMPLES))
+    geo = (model.cascades, float(model.scale), esf, model.grid_size, MAX_SAMPLES)
+    alive_in, n_alive = None, N_rays
+    prev = None                        # (rays_a, sigmas, rgbs, deltas, ts) of the previous round
+    counters = torch.zeros(2, dtype=torch.int32, device=dev)
+    total = 0
+    samples, rnd = 0, 0
+    while n_alive > 0:
+        n_next = min(4 << rnd, 128, max_samples - samples) if samples < max_samples else 0
+        rnd += 1; samples += n_next
+        ws = torch.empty(int(lib.ngp_raymarching_train_workspace_bytes(n_alive)), dtype=torch.uint8, device=dev)
+        alive_out = torch.empty(n_alive, dtype=torch.int64, device=dev)
+        pr = prev if prev is not None else (None,) * 5
+        check(lib.ngp_render_advance(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(pr[0]), ptr(pr[1]),
+                                     ptr(pr[2]), ptr(pr[3]), ptr(pr[4]), T_thr, ptr(model.density_bitfield), *geo, n_next,
+                                     ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_out), ptr(counters), ptr(ws), stream()),
+              "render_advance")
+        if n_next == 0:
+            break
+        cap = n_alive * n_next
+        rays_a = torch.empty(n_alive, 3, dtype=torch.int64, device=dev)
+        xyzs = torch.empty(cap, 3, device=dev); dirs = torch.empty(cap, 3, device=dev)
+        deltas = torch.empty(cap, device=dev); ts = torch.empty(cap, device=dev)
+        check(lib.ngp_render_emit(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_out), n_alive, ptr(model.density_bitfield),
+                                  *geo, ptr(ws), cap, ptr(rays_a), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), ptr(counters),
+                                  stream()), "render_emit")
+        n_alive_out, n_pts = (int(v) for v in counters.tolist())          # the round's one host read-back
+        total += n_pts
+        if n_alive_out == 0 or n_pts == 0:
+            break
+        sig, col, _, _, _ = model.forward_test(xyzs[:n_pts], dirs[:n_pts], **kwargs)
+        prev = (rays_a[:n_alive_out].contiguous(), sig.contiguous(), col.contiguous(), deltas, ts)
+        alive_in, n_alive = alive_out, n_alive_out
+    return total
+
+
+@torch.no_grad()
 def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     """rendering.py:135-190."""
     hits_t = hits_t[:, 0, :].contiguous()
     classes = kwargs.get("num_classes", 7)
     N_rays, device = len(rays_o), rays_o.device
+    if not getattr(model, "has_normals", True) and kwargs.get("renderer", "wavefront") == "wavefront" \
+            and not kwargs.get("use_skybox", False):
+        opacity = torch.zeros(N_rays, device=device); depth = torch.zeros(N_rays, device=device)
+        rgb = torch.zeros(N_rays, 3, device=device)
+        total = render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
+        z3 = torch.zeros(N_rays, 3, device=device)
+        return {"opacity": opacity, "depth": depth, "rgb": rgb, "normal_pred": z3, "normal_raw": z3,
+                "semantic": torch.zeros(N_rays, 1, dtype=torch.long, device=device),
+                "total_samples": torch.tensor(total, device=device), "points": rays_o + rays_d * depth.unsqueeze(-1),
+                "mask": torch.zeros(N_rays, device=device)}
     opacity = torch.zeros(N_rays, device=device)
     depth = torch.zeros(N_rays, device=device)
     rgb = torch.zeros(N_rays, 3, device=device)

@@ -150,10 +150,13 @@ def test_geometric_schedule_renders_the_same_image_as_the_reference_schedule():
         tr.train_step(ro, rd, rgb, update_grid=False)
     ro, rd = scene.image_rays(poses[0], wh=(100, 100))
     with torch.no_grad():
-        a = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="reference")
-        b = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric")
+        a = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="reference", renderer="loop")
+        b = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric", renderer="loop")
+        c = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2)       # wavefront kernels
     assert torch.allclose(a["rgb"], b["rgb"], atol=2e-5) and torch.allclose(a["depth"], b["depth"], atol=2e-4)
     assert torch.allclose(a["opacity"], b["opacity"], atol=2e-5)
+    assert torch.allclose(a["rgb"], c["rgb"], atol=2e-5) and torch.allclose(a["depth"], c["depth"], atol=2e-4)
+    assert torch.allclose(a["opacity"], c["opacity"], atol=2e-5) and int(c["total_samples"]) > 0
     assert int(b["total_samples"]) > 0 and int(a["total_samples"]) > 0
 
 
