@@ -12,6 +12,7 @@ Prints ONE JSON line (see README / DESIGN.md §measurement for every key).
 import argparse
 import json
 import os
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")   # per-step sample counts vary: no cudaMalloc/cudaFree churn
 import subprocess
 import sys
 import threading
@@ -206,8 +207,12 @@ def gpu_arm(args):
     host = [(o.cpu().pin_memory(), d.cpu().pin_memory(), c.cpu().pin_memory()) for o, d, c in zip(pool_o, pool_d, pool_c)]
     h2d_bytes = sum(t.numel() * 4 for t in host[0])
 
+    sample_log = []
+
     def step_resident(i):
-        return tr.train_step(pool_o[i % n_batches], pool_d[i % n_batches], pool_c[i % n_batches])
+        out = tr.train_step(pool_o[i % n_batches], pool_d[i % n_batches], pool_c[i % n_batches])
+        sample_log.append(tr.last_samples)
+        return out
 
     def step_e2e(i):
         o, d, c = (t.to(dev, non_blocking=True) for t in host[i % n_batches])
@@ -243,7 +248,9 @@ def gpu_arm(args):
         calls = (_lib.lib_calls() if hasattr(_lib, "lib_calls") else 0) - calls0
         return float(ms) * 1e-3, (sampler.stop() if rank == 0 else None), calls
 
+    del sample_log[:]
     t_res, clocks, launches = timed(step_resident, args.steps)
+    spr_timed = [float(x) / R for x in sample_log]
     t_e2e, _, _ = timed(step_e2e, args.steps)
 
     # steady-state quality + sample statistics (outside the timed regions)
@@ -298,7 +305,7 @@ def gpu_arm(args):
         "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32 (bf16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr,
+        "config": {"workload": WORKLOAD, "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr, "samples_per_ray_timed_steps": {"min": min(spr_timed), "max": max(spr_timed), "mean": sum(spr_timed) / len(spr_timed)},
                    "pretrain_steps": args.pretrain, "psnr_after_pretrain": q, "l2": "inputs_exceed_l2 (>250 MB of samples per step)",
                    "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of table+MLP gradients" if world > 1 else "single GPU",
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
