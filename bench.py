@@ -183,6 +183,14 @@ def gpu_arm(args):
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    for attempt in range(6):            # a freshly leased box can refuse the very first driver init for a few seconds
+        try:
+            torch.cuda.init()
+            break
+        except RuntimeError:
+            if attempt == 5:
+                raise
+            time.sleep(3)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
