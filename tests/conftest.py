@@ -13,9 +13,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
-def pytest_collection_modifyitems(config, items):
+def _cuda_ready():
+    """torch.cuda.is_available(), retried for a few seconds when a GPU device node exists: a freshly
+    leased box can refuse the very first driver initialisation."""
+    import time
     import torch
     if torch.cuda.is_available():
+        return True
+    if not os.path.exists("/dev/nvidia0"):
+        return False
+    for _ in range(6):
+        time.sleep(3)
+        try:
+            torch.cuda.init()
+            return True
+        except Exception:
+            pass
+    return torch.cuda.is_available()
+
+
+def pytest_collection_modifyitems(config, items):
+    if _cuda_ready():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
