@@ -296,7 +296,8 @@ def gpu_arm(args):
             "peak_source": pk_src, "traffic": None, "samples_per_launch": int(xyzs.shape[0])}
     roof["frac"] = roof["achieved"] / roof["peak"]
     try:    # measured DRAM bytes per launch of that kernel: per-sample figure of the committed ncu capture x this launch's samples
-        tr_ = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        import glob
+        tr_ = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))   # newest capture
         if tr_["kernel"] == dom:
             roof["traffic"] = tr_["dram_bytes_per_sample"] * int(xyzs.shape[0])
             roof["traffic_source"] = tr_["source"]
@@ -304,7 +305,7 @@ def gpu_arm(args):
         pass
     roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the 43.6 MB fp32 "
                     "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 — the kernel is bound by L2 "
-                    "atomic throughput (ncu lts__throughput 78 %), see profiles/r01_ncu_hashgrid_bw_v2.txt")
+                    "atomic throughput (ncu lts__throughput 77 %, 50 red sectors/sample), see profiles/r01b_ncu_hashgrid_bw_params_kernel.txt")
 
     rend = render_bench(model, scene, poses) if not args.no_render else None
     cpu, _ = cpu_arm(steps=4, warmup=1)

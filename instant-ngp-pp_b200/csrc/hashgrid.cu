@@ -17,6 +17,7 @@
 // 43 MB fp32 table of the L16/F2/T2^19 shape fits the 126 MB L2 outright).  Gradients are
 // scattered with vector reductions (red.global.add.v2/v4.f32).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ngp {
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
 //    (always for hashed levels with even x: h(x+1) = h(x)^1), so for F=2 the pair goes out as ONE
 //    16-byte red.global.add.v4.f32 instead of two 8-byte ones;
 //  * exactly-zero upstream rows (samples past early termination) are skipped.
-constexpr int kSPT = 8;
+constexpr int kSPT = 16;   // 8 -> 16: one forced flush per run, -8 % (tools/hash_sweep.py)
 
 template <int F> struct CellAcc {
   uint32_t px, py, pz;
@@ -180,10 +181,10 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, float* __restric
 
 template <int F>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                 GridMeta m, int64_t n, float* __restrict__ dtable) {
+                                                                 GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
   constexpr int LC = levels_per_thread<F>();
   const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
-  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x) * kSPT;
+  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x) * spt;
   if (s0 >= n) return;
   const int l0 = (blockIdx.x % n_chunks) * LC;
   const int LF = m.n_levels * F;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
   for (int li = 0; li < LC; li++) acc[li].has = false;
 
 #pragma unroll 1
-  for (int j = 0; j < kSPT; j++) {
+  for (int j = 0; j < spt; j++) {
     const int64_t i = s0 + j;
     if (i >= n) break;
     const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
@@ -422,8 +423,10 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_lev
     return set_error_msg("ngp_hashgrid_bw_params: bad grid config");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 128) * ceil_div(n_levels, LC));
-    hashgrid_bw_params_kernel<F><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable);
+    const char* e = getenv("NGP_HASH_SPT");
+    const int spt = e ? atoi(e) : kSPT;
+    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC));
+    hashgrid_bw_params_kernel<F><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
   return 0;
