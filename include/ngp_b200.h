@@ -42,6 +42,9 @@ int ngp_morton3D(const int32_t* coords, int64_t n, int32_t* indices, void* strea
 int ngp_morton3D_invert(const int32_t* indices, int64_t n, int32_t* coords, void* stream);
 int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold,
                  uint8_t* density_bitfield, void* stream);
+/* threshold in device memory (networks.py:404-408, thr = min(mean, density_threshold), without the .item() sync) */
+int ngp_packbits_dthr(const float* density_grid, int64_t n_bytes, const float* density_threshold_dev,
+                      uint8_t* density_bitfield, void* stream);
 
 /* ------------------------------------------------------------------ a2: training ray marcher
  * vren.raymarching_train  binding.cpp:60-81 -> raymarching.cu:283-332, split so the caller can
@@ -132,19 +135,22 @@ int ngp_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan
 /* ------------------------------------------------------------------ a10: hash-grid encoding
  * tcnn.Encoding(3, {"otype":"Grid"|"HashGrid", ...})  models/networks.py:40-52, 67-76
  * (tiny-cuda-nn is an un-vendored dependency of the reference; semantics per SURVEY.md App. B).
- * table_dtype: 0 = f32, 1 = f16.  Gradients are always fp32. */
+ * table_dtype: 0 = f32, 1 = f16.  Gradients are always fp32.
+ * aabb: HOST pointer to {lo[3], range[3]} or NULL.  When given, x is world-space and every kernel applies
+ * (x - lo) / range itself — the (x - xyz_min) / (xyz_max - xyz_min) pass of models/networks.py:174,188 fused
+ * (IEEE sub + div: bit-identical to the tensor ops).  dL_dx is always w.r.t. the unit-cube coordinate. */
 int64_t ngp_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
                             float per_level_scale, uint32_t* offsets /*L+1*/, uint32_t* sizes, uint32_t* resolutions,
                             float* scales, uint8_t* dense);
-int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, int n_levels, int n_features,
+int ngp_hashgrid_fw(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels, int n_features,
                     int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n, float* y,
                     void* stream);
-int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_levels, int n_features, int log2_hashmap_size,
+int ngp_hashgrid_bw_params(const float* x, const float* aabb, const float* dL_dy, int n_levels, int n_features, int log2_hashmap_size,
                            int base_resolution, float per_level_scale, int64_t n, float* dtable, void* stream);
-int ngp_hashgrid_bw_input(const float* x, const float* dL_dy, const void* table, int table_dtype, int n_levels,
+int ngp_hashgrid_bw_input(const float* x, const float* aabb, const float* dL_dy, const void* table, int table_dtype, int n_levels,
                           int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
                           float* dL_dx, void* stream);
-int ngp_hashgrid_bwbw_input(const float* x, const float* g2, const float* dL_dy, const void* table, int table_dtype,
+int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const float* g2, const float* dL_dy, const void* table, int table_dtype,
                             int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
                             float per_level_scale, int64_t n, float* dtable, float* d_dL_dy, void* stream);
 

@@ -31,7 +31,18 @@ struct GridMeta {
   uint32_t res[kMaxLevels];
   float scale[kMaxLevels];
   uint8_t dense[kMaxLevels];
+  // optional world -> unit-cube map fused into every kernel: x01 = (x - lo) / range with IEEE sub and div, i.e.
+  // bit-identical to the (x - xyz_min) / (xyz_max - xyz_min) tensor pass of models/networks.py:174,188
+  int affine;
+  float lo[3], range[3];
 };
+__device__ __forceinline__ void to_unit(const GridMeta& m, float& x, float& y, float& z) {
+  if (m.affine) {
+    x = __fdiv_rn(__fsub_rn(x, m.lo[0]), m.range[0]);
+    y = __fdiv_rn(__fsub_rn(y, m.lo[1]), m.range[1]);
+    z = __fdiv_rn(__fsub_rn(z, m.lo[2]), m.range[2]);
+  }
+}
 
 __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size,
                                                bool dense) {
@@ -93,7 +104,8 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
   const int64_t i = (int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l0 = (blockIdx.x % n_chunks) * LC;
-  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  to_unit(m, xx, xy, xz);
   float out[LC * F];
 #pragma unroll
   for (int k = 0; k < LC * F; k++) out[k] = 0.f;
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
 //    (always for hashed levels with even x: h(x+1) = h(x)^1), so for F=2 the pair goes out as ONE
 //    16-byte red.global.add.v4.f32 instead of two 8-byte ones;
 //  * exactly-zero upstream rows (samples past early termination) are skipped.
-constexpr int kSPT = 16;   // 8 -> 16: one forced flush per run, -8 % (tools/hash_sweep.py)
+constexpr int kSPT = 24;   // 8 -> 16: one forced flush per run, -8 % (tools/hash_sweep.py)
 
 template <int F> struct CellAcc {
   uint32_t px, py, pz;
@@ -179,10 +191,9 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, float* __restric
   }
 }
 
-template <int F>
+template <int F, int LC>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
-  constexpr int LC = levels_per_thread<F>();
   const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
   const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x) * spt;
   if (s0 >= n) return;
@@ -196,7 +207,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
   for (int j = 0; j < spt; j++) {
     const int64_t i = s0 + j;
     if (i >= n) break;
-    const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+    float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+    to_unit(m, xx, xy, xz);
     const float* src = dy + i * LF + (int64_t)l0 * F;
     float g[LC * F];
     if (l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0) {
@@ -251,7 +263,8 @@ __global__ void __launch_bounds__(256) hashgrid_bw_input_kernel(const float* __r
                                                                 float* __restrict__ dx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  to_unit(m, xx, xy, xz);
   const int LF = m.n_levels * F;
   float gx = 0.f, gy = 0.f, gz = 0.f;
   for (int l = 0; l < m.n_levels; l++) {
@@ -297,7 +310,8 @@ __global__ void __launch_bounds__(256) hashgrid_bwbw_kernel(const float* __restr
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l = blockIdx.y;
-  const float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  to_unit(m, xx, xy, xz);
   const float hx = __ldg(g2 + 3 * i), hy = __ldg(g2 + 3 * i + 1), hz = __ldg(g2 + 3 * i + 2);
   const int LF = m.n_levels * F;
   const Cell c = locate(xx, xy, xz, m.scale[l]);
@@ -337,10 +351,12 @@ __global__ void __launch_bounds__(256) hashgrid_bwbw_kernel(const float* __restr
   }
 }
 
-static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res, float per_level_scale) {
+static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res, float per_level_scale, const float* aabb = nullptr) {
   if (n_levels < 1 || n_levels > kMaxLevels) return -1;
   if (!(F == 1 || F == 2 || F == 4 || F == 8)) return -1;
   m.n_levels = n_levels; m.n_features = F;
+  m.affine = aabb != nullptr;
+  for (int d = 0; d < 3; d++) { m.lo[d] = aabb ? aabb[d] : 0.f; m.range[d] = aabb ? aabb[3 + d] : 1.f; }
   const float log2_pls = log2f(per_level_scale);
   uint32_t off = 0;
   for (int l = 0; l < n_levels; l++) {
@@ -394,13 +410,15 @@ NGP_API int64_t ngp_hashgrid_layout(int n_levels, int n_features, int log2_hashm
   }
 
 // y (N, L*F) f32 = encode(x (N,3) f32 in [0,1]).  table_dtype: 0 = f32, 1 = f16.
+// aabb (all four entry points; HOST pointer, may be NULL): {lo_x, lo_y, lo_z, range_x, range_y, range_z} — the kernels
+// then take world-space x and map it with (x - lo) / range themselves (networks.py:174 fused; bit-identical).
 // Replaces tcnn.Encoding.forward for the Grid encoding (called from models/networks.py:177,182).
-NGP_API int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, int n_levels, int n_features,
+NGP_API int ngp_hashgrid_fw(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels, int n_features,
                             int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n, float* y,
                             void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
-  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_fw: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
@@ -414,31 +432,38 @@ NGP_API int ngp_hashgrid_fw(const float* x, const void* table, int table_dtype, 
 }
 
 // dtable (n_params) f32 += scatter(dL/dy).  The caller zeroes dtable (or accumulates on purpose).
-NGP_API int ngp_hashgrid_bw_params(const float* x, const float* dL_dy, int n_levels, int n_features,
+NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const float* dL_dy, int n_levels, int n_features,
                                    int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
                                    float* dtable, void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
-  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_bw_params: bad grid config");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
     const char* e = getenv("NGP_HASH_SPT");
     const int spt = e ? atoi(e) : kSPT;
-    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC));
-    hashgrid_bw_params_kernel<F><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    const char* e2 = getenv("NGP_HASH_LC");
+    if (e2 && atoi(e2) == 2 && LC >= 2) {
+      constexpr int LC2 = LC >= 2 ? LC / 2 : 1;
+      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC2));
+      hashgrid_bw_params_kernel<F, LC2><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    } else {
+      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC));
+      hashgrid_bw_params_kernel<F, LC><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    }
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
   return 0;
 }
 
 // dx (N,3) f32 = (dy/dx)^T dL/dy
-NGP_API int ngp_hashgrid_bw_input(const float* x, const float* dL_dy, const void* table, int table_dtype, int n_levels,
+NGP_API int ngp_hashgrid_bw_input(const float* x, const float* aabb, const float* dL_dy, const void* table, int table_dtype, int n_levels,
                                   int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
                                   int64_t n, float* dL_dx, void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
-  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_bw_input: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
@@ -453,13 +478,13 @@ NGP_API int ngp_hashgrid_bw_input(const float* x, const float* dL_dy, const void
 // Double backward of ngp_hashgrid_bw_input: g2 = dL/d(dL_dx) (N,3).
 //   dtable += d(g2 . dL_dx)/dtable   (skipped when dtable == NULL)
 //   d_dL_dy = d(g2 . dL_dx)/d(dL_dy) (skipped when d_dL_dy == NULL; dL_dy may then be NULL too)
-NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* g2, const float* dL_dy, const void* table,
+NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const float* g2, const float* dL_dy, const void* table,
                                     int table_dtype, int n_levels, int n_features, int log2_hashmap_size,
                                     int base_resolution, float per_level_scale, int64_t n, float* dtable,
                                     float* d_dL_dy, void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
-  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale))
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_bwbw_input: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {

@@ -68,7 +68,8 @@ template <typename T> __device__ __forceinline__ bool above(T v, float thr) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) packbits_kernel(const T* __restrict__ grid, int64_t n_bytes, float thr,
-                                                       uint8_t* __restrict__ bitfield) {
+                                                       const float* __restrict__ thr_dev, uint8_t* __restrict__ bitfield) {
+  if (thr_dev) thr = __ldg(thr_dev);          // threshold produced on the device (occupancy update): no host read-back
   const int64_t n_words = n_bytes >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool aligned = (((uintptr_t)grid) & 15) == 0 && (((uintptr_t)bitfield) & 3) == 0;
@@ -141,11 +142,22 @@ NGP_API int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, f
   const int grid = stream_grid((n_bytes + 3) / 4, 256);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case 0: packbits_kernel<float><<<grid, 256, 0, s>>>((const float*)density_grid, n_bytes, density_threshold, density_bitfield); break;
-    case 1: packbits_kernel<__half><<<grid, 256, 0, s>>>((const __half*)density_grid, n_bytes, density_threshold, density_bitfield); break;
-    case 2: packbits_kernel<double><<<grid, 256, 0, s>>>((const double*)density_grid, n_bytes, density_threshold, density_bitfield); break;
+    case 0: packbits_kernel<float><<<grid, 256, 0, s>>>((const float*)density_grid, n_bytes, density_threshold, nullptr, density_bitfield); break;
+    case 1: packbits_kernel<__half><<<grid, 256, 0, s>>>((const __half*)density_grid, n_bytes, density_threshold, nullptr, density_bitfield); break;
+    case 2: packbits_kernel<double><<<grid, 256, 0, s>>>((const double*)density_grid, n_bytes, density_threshold, nullptr, density_bitfield); break;
     default: return set_error_msg("ngp_packbits: dtype must be 0 (f32), 1 (f16) or 2 (f64)");
   }
   NGP_LAUNCH_CHECK("ngp_packbits");
+  return 0;
+}
+
+// Same as ngp_packbits with the threshold read from DEVICE memory (one float): the occupancy update
+// (models/networks.py:404-408: thr = min(mean density, density_threshold)) stays on the stream, no .item().
+NGP_API int ngp_packbits_dthr(const float* density_grid, int64_t n_bytes, const float* density_threshold_dev,
+                              uint8_t* density_bitfield, void* stream) {
+  if (n_bytes <= 0) return 0;
+  const int grid = stream_grid((n_bytes + 3) / 4, 256);
+  packbits_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(density_grid, n_bytes, 0.f, density_threshold_dev, density_bitfield);
+  NGP_LAUNCH_CHECK("ngp_packbits_dthr");
   return 0;
 }

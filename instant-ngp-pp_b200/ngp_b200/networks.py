@@ -55,6 +55,16 @@ class _OccupancyMixin:
         ax = torch.arange(G, dtype=torch.int32)
         self.register_buffer("grid_coords", torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3))
 
+    def aabb(self):
+        """(lo xyz, range xyz) as python floats for the fused normalisation of the grid kernels; read from the
+        xyz_min / xyz_max buffers once (they are fixed by `scale`, networks.py:23-27)."""
+        cached = getattr(self, "_aabb_host", None)
+        if cached is None:
+            lo = self.xyz_min.detach().float().cpu().reshape(3)
+            rng = (self.xyz_max - self.xyz_min).detach().float().cpu().reshape(3)
+            cached = self._aabb_host = tuple(float(v) for v in lo) + tuple(float(v) for v in rng)
+        return cached
+
     @torch.no_grad()
     def get_all_cells(self):
         """[(indices, coords)] * cascades — every cell of the 128^3 lattice (networks.py:294-305)."""
@@ -69,9 +79,15 @@ class _OccupancyMixin:
         for c in range(self.cascades):
             coords1 = torch.randint(G, (M, 3), dtype=torch.int32, device=dev)
             indices1 = vren.morton3D(coords1).long()
-            indices2 = torch.nonzero(self.density_grid[c] > density_threshold)[:, 0]
-            if len(indices2) > 0:
-                indices2 = indices2[torch.randint(len(indices2), (M,), device=dev)]
+            # M draws (with replacement) among the cells above the threshold — the reference's
+            # nonzero()[randint(len)] without the host round trip: rank r of the draw -> r-th occupied cell through
+            # a running count.  No occupied cell -> the reference keeps an empty list; here the M draws all land on
+            # the last cell, which just gets one more (legitimate) density sample.
+            occ = self.density_grid[c] > density_threshold
+            count = torch.cumsum(occ, 0, dtype=torch.int32)
+            total = count[-1]
+            r = (torch.rand(M, device=dev) * total).to(torch.int32).clamp_(max=(total - 1).clamp(min=0))
+            indices2 = torch.searchsorted(count, r + 1).clamp_(max=G ** 3 - 1)
             coords2 = vren.morton3D_invert(indices2.int())
             cells.append((torch.cat([indices1, indices2]), torch.cat([coords1, coords2])))
         return cells
@@ -121,8 +137,8 @@ class _OccupancyMixin:
                                         torch.maximum(self.density_grid * decay, tmp))
         pos = self.density_grid > 0
         mean_density = (self.density_grid * pos).sum() / pos.sum().clamp(min=1)
-        thr = torch.clamp(mean_density, max=density_threshold)     # min(mean, thr), still on the device
-        vren.packbits(self.density_grid, float(thr), self.density_bitfield)
+        thr = torch.clamp(mean_density, max=density_threshold).float()     # min(mean, thr): stays on the device
+        vren.packbits_dthr(self.density_grid, thr, self.density_bitfield)
 
 
 class NGP(nn.Module, _OccupancyMixin):
@@ -168,29 +184,29 @@ class NGP(nn.Module, _OccupancyMixin):
 
     def density(self, x, return_feat=False, grad=True, grad_feat=True):
         """sigmas (N) [, feat_rgb (N, L*F)] for x (N,3) in [-scale, scale]  (networks.py:165-184)."""
-        xn = self._normalise(x)
+        x, ab = x.contiguous(), self.aabb()              # (x - xyz_min) / (xyz_max - xyz_min) happens inside the grid kernels
         with torch.set_grad_enabled(grad and torch.is_grad_enabled()):
-            sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(xn))[:, 0])
+            sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(x, ab))[:, 0])
         if not return_feat:
             return sigmas
         with torch.set_grad_enabled(grad_feat and torch.is_grad_enabled()):
-            feat_rgb = self.rgb_encoder(xn)
+            feat_rgb = self.rgb_encoder(x, ab)
         return sigmas, feat_rgb
 
     @torch.enable_grad()
     def grad(self, x):
         """sigmas, feat_rgb, d sigma / d x (N,3), differentiable w.r.t. the parameters
         (networks.py:186-196)."""
-        xn = self._normalise(x.detach())
-        enc = self.xyz_encoder(xn)
+        x, ab = x.detach().contiguous(), self.aabb()
+        enc = self.xyz_encoder(x, ab)
         sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
         (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)
         # input gradient of the grid as a differentiable op of (g_enc, table): its backward is the
         # double-backward kernel
-        g_xn, _ = _GridBwFn.apply(g_enc.contiguous(), xn.contiguous(), self.xyz_encoder.params, self.xyz_encoder.grid,
-                                  True, False)
+        g_xn, _ = _GridBwFn.apply(g_enc.contiguous(), x, self.xyz_encoder.params, self.xyz_encoder.grid,
+                                  True, False, ab)
         grads = g_xn / (self.xyz_max - self.xyz_min)
-        feat_rgb = self.rgb_encoder(xn)
+        feat_rgb = self.rgb_encoder(x, ab)
         return sigmas, feat_rgb, grads
 
     # ------------------------------------------------------------------ heads
@@ -265,7 +281,7 @@ class NGPCompact(nn.Module, _OccupancyMixin):
     has_normals = False     # no normal / semantic heads: the renderer takes the lite compositor path
 
     def density(self, x, return_feat=False):
-        h, sigmas = self.sigma_net.forward_density_head(self.xyz_encoder(self._normalise(x)))
+        h, sigmas = self.sigma_net.forward_density_head(self.xyz_encoder(x.contiguous(), self.aabb()))
         return (sigmas, h) if return_feat else sigmas
 
     def forward(self, x, d, **kwargs):

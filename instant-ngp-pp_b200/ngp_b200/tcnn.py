@@ -63,43 +63,50 @@ class GridConfig:
         return (self.n_levels, self.n_features, self.log2_T, self.base_res, self.per_level_scale)
 
 
-def grid_forward(x, table, g: GridConfig):
+def _aabb_arg(aabb):
+    """aabb = None | 6 python floats (lo xyz, range xyz) -> HOST float[6] for the C ABI (kernels then take world x)."""
+    return None if aabb is None else (ctypes.c_float * 6)(*[float(v) for v in aabb])
+
+
+def grid_forward(x, table, g: GridConfig, aabb=None):
     n = x.shape[0]
     y = torch.empty(n, g.n_levels * g.n_features, dtype=torch.float32, device=x.device)
-    check(lib.ngp_hashgrid_fw(ptr(x), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(), n, ptr(y),
+    check(lib.ngp_hashgrid_fw(ptr(x), _aabb_arg(aabb), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(), n, ptr(y),
                               stream()), "hashgrid_fw")
     return y
 
 
-def grid_backward_params(x, dy, g: GridConfig, out=None):
+def grid_backward_params(x, dy, g: GridConfig, out=None, aabb=None):
     dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device) if out is None else out
-    check(lib.ngp_hashgrid_bw_params(ptr(x), ptr(dy), *g.args(), x.shape[0], ptr(dtable), stream()),
+    check(lib.ngp_hashgrid_bw_params(ptr(x), _aabb_arg(aabb), ptr(dy), *g.args(), x.shape[0], ptr(dtable), stream()),
           "hashgrid_bw_params")
     return dtable
 
 
-def grid_backward_input(x, dy, table, g: GridConfig):
+def grid_backward_input(x, dy, table, g: GridConfig, aabb=None):
     dx = torch.empty_like(x)
-    check(lib.ngp_hashgrid_bw_input(ptr(x), ptr(dy), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(),
+    check(lib.ngp_hashgrid_bw_input(ptr(x), _aabb_arg(aabb), ptr(dy), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(),
                                     x.shape[0], ptr(dx), stream()), "hashgrid_bw_input")
     return dx
 
 
 class _GridFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, table, g):
+    def forward(ctx, x, table, g, aabb=None):
         _lib.require_device()
         x = x.contiguous()
-        ctx.g = g
+        ctx.g, ctx.aabb = g, aabb
         ctx.save_for_backward(x, table)
-        return grid_forward(x.detach(), table.detach(), g)
+        return grid_forward(x.detach(), table.detach(), g, aabb)
 
     @staticmethod
     def backward(ctx, dy):
         x, table = ctx.saved_tensors
         need_dx, need_dt = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dx, dt = _GridBwFn.apply(dy.contiguous(), x, table, ctx.g, need_dx, need_dt)
-        return (dx if need_dx else None), (dt if need_dt else None), None
+        dx, dt = _GridBwFn.apply(dy.contiguous(), x, table, ctx.g, need_dx, need_dt, ctx.aabb)
+        if need_dx and ctx.aabb is not None:        # chain rule of the fused (x - lo) / range
+            dx = dx / dx.new_tensor(ctx.aabb[3:])
+        return (dx if need_dx else None), (dt if need_dt else None), None, None
 
 
 class _GridBwFn(torch.autograd.Function):
@@ -107,11 +114,12 @@ class _GridBwFn(torch.autograd.Function):
     through the encoding (models/networks.py:189-195) has a double backward."""
 
     @staticmethod
-    def forward(ctx, dy, x, table, g, need_dx, need_dt):
-        ctx.g = g
+    def forward(ctx, dy, x, table, g, need_dx, need_dt, aabb=None):
+        """dx is w.r.t. the UNIT-CUBE coordinate (also when aabb maps world x inside the kernels)."""
+        ctx.g, ctx.aabb = g, aabb
         ctx.save_for_backward(dy, x, table)
-        dx = grid_backward_input(x.detach(), dy.detach(), table.detach(), g) if need_dx else torch.zeros_like(x)
-        dt = grid_backward_params(x.detach(), dy.detach(), g) if need_dt else torch.zeros(0, device=x.device)
+        dx = grid_backward_input(x.detach(), dy.detach(), table.detach(), g, aabb) if need_dx else torch.zeros_like(x)
+        dt = grid_backward_params(x.detach(), dy.detach(), g, aabb=aabb) if need_dt else torch.zeros(0, device=x.device)
         return dx, dt
 
     @staticmethod
@@ -126,10 +134,10 @@ class _GridBwFn(torch.autograd.Function):
         d_dy = torch.empty_like(dy) if need_ddy else None
         dt2 = torch.zeros(g.n_params, dtype=torch.float32, device=x.device) if need_dt else None
         if need_ddy or need_dt:
-            check(lib.ngp_hashgrid_bwbw_input(ptr(x), ptr(g_dx.contiguous()), ptr(dy), ptr(table),
+            check(lib.ngp_hashgrid_bwbw_input(ptr(x), _aabb_arg(ctx.aabb), ptr(g_dx.contiguous()), ptr(dy), ptr(table),
                                               0 if table.dtype == torch.float32 else 1, *g.args(), n, ptr(dt2),
                                               ptr(d_dy), stream()), "hashgrid_bwbw_input")
-        return d_dy, None, dt2, None, None, None
+        return d_dy, None, dt2, None, None, None, None
 
 
 # --------------------------------------------------------------------------------------- SH
@@ -167,9 +175,11 @@ class Encoding(nn.Module):
         else:
             raise NotImplementedError(f"ngp_b200.tcnn.Encoding: otype {otype!r} is not on the hot path")
 
-    def forward(self, x):
+    def forward(self, x, aabb=None):
+        """aabb (extension, grid only): 6 floats (lo xyz, range xyz); x is then world-space and the kernels apply
+        (x - lo) / range themselves — same bits as normalising with tensor ops first, two passes over x fewer."""
         if self.kind == "grid":
-            return _GridFn.apply(x.float(), self.params, self.grid)
+            return _GridFn.apply(x.float(), self.params, self.grid, aabb)
         return sh_forward(x.float().detach(), self.degree)
 
 

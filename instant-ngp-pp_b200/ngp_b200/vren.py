@@ -88,6 +88,15 @@ def packbits(density_grid, density_threshold, density_bitfield):
                            float(density_threshold), ptr(density_bitfield), stream()), "packbits")
 
 
+def packbits_dthr(density_grid, density_threshold, density_bitfield):
+    """packbits with the threshold as a 0-dim float32 CUDA tensor (no host read-back)."""
+    _lib.require_device()
+    if density_grid.dtype != torch.float32 or density_threshold.dtype != torch.float32 or density_bitfield.dtype != torch.uint8:
+        raise RuntimeError("ngp_b200.vren.packbits_dthr: float32 grid / float32 threshold / uint8 bitfield")
+    check(lib.ngp_packbits_dthr(ptr(density_grid), density_bitfield.shape[0], ptr(density_threshold), ptr(density_bitfield),
+                                stream()), "packbits_dthr")
+
+
 class MarchPlan:
     """Result of the count+scan phase of the training marcher (device resident)."""
     __slots__ = ("workspace", "counter", "n_rays")

@@ -214,3 +214,30 @@ def test_mlp_density_head_fused_exp():
     dh_eff = dh.clone(); dh_eff[:, 0] += ds * torch.exp(ho[:, 0].detach().clamp(-7, 7))
     gxo, gpo = torch.autograd.grad(ho, (xo, po), dh_eff)
     assert rel(gx, gxo) < 1.5e-2 and rel(gp, gpo) < 1.5e-2, (rel(gx, gxo), rel(gp, gpo))
+
+
+def test_hashgrid_fused_aabb_is_bit_identical_to_normalising_first():
+    """The (x - xyz_min) / (xyz_max - xyz_min) pass of models/networks.py:174 fused into the grid kernels: IEEE sub + div
+    in the kernel give the same bits as the two tensor ops, for the forward, both first-order gradients and the
+    double backward."""
+    from ngp_b200 import tcnn
+    enc, _ = _grid(16, 2, 19, 16, 8.0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 20011
+    lo = torch.tensor([-8.0, -8.0, -8.0], device="cuda"); rng = torch.tensor([16.0, 16.0, 16.0], device="cuda")
+    xw = (torch.rand(n, 3, device="cuda", generator=g) * 2 - 1) * 8.0
+    xn = ((xw - lo) / rng).contiguous()
+    aabb = tuple(lo.tolist()) + tuple(rng.tolist())
+    table = enc.params.detach()
+    y0 = tcnn.grid_forward(xn, table, enc.grid); y1 = tcnn.grid_forward(xw, table, enc.grid, aabb)
+    assert torch.equal(y0, y1)
+    dy = torch.randn(n, 32, device="cuda", generator=g)
+    assert torch.equal(tcnn.grid_backward_input(xn, dy, table, enc.grid), tcnn.grid_backward_input(xw, dy, table, enc.grid, aabb))
+    t0 = tcnn.grid_backward_params(xn, dy, enc.grid); t1 = tcnn.grid_backward_params(xw, dy, enc.grid, aabb=aabb)
+    assert rel(t1, t0) < 1e-6          # same terms, atomic order differs run to run
+    # through autograd: d/dx of the world-space input carries the 1 / range chain-rule factor
+    xa = xw.clone().requires_grad_(True); xb = xn.clone().requires_grad_(True)
+    tcnn._GridFn.apply(xa, enc.params, enc.grid, aabb).square().sum().backward()
+    ga, pa = xa.grad.clone(), enc.params.grad.clone(); enc.params.grad = None
+    tcnn._GridFn.apply(xb, enc.params, enc.grid).square().sum().backward()
+    assert torch.allclose(ga, xb.grad / rng, rtol=1e-6, atol=0) and rel(pa, enc.params.grad) < 1e-6

@@ -78,6 +78,17 @@ def test_packbits(vren, dtype):
 
 
 # ------------------------------------------------------------------------------------ a1
+def test_packbits_device_threshold_matches_host_threshold(vren):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    grid = torch.randn(3 * 128 ** 3, device="cuda", generator=g)
+    grid[::9] = -1.0
+    thr = torch.tensor(0.3125, device="cuda")
+    grid[5::13] = 0.3125                      # exact-threshold cells stay unset (strict >, raymarching.cu:152)
+    a = torch.zeros(grid.numel() // 8, dtype=torch.uint8, device="cuda"); b = torch.zeros_like(a)
+    vren.packbits(grid, 0.3125, a); vren.packbits_dthr(grid, thr, b)
+    assert torch.equal(a, b) and int(a.sum()) > 0
+
+
 @pytest.mark.parametrize("scale", [0.5, 8.0])
 def test_aabb_bit_exact(vren, vref, scale):
     o, d = cases.rays(20000, scale, seed=4)

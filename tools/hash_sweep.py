@@ -26,10 +26,11 @@ def tm(fn, it=5):
     for _ in range(it): fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / it
-for spt in (8, 12, 16, 24, 32, 48):
-    os.environ["NGP_HASH_SPT"] = str(spt)
+import itertools
+for lc, spt in itertools.product((4, 2), (8, 16, 24)):
+    os.environ["NGP_HASH_SPT"] = str(spt); os.environ["NGP_HASH_LC"] = str(lc)
     dt = torch.zeros(g.n_params, device=dev)
     t = tm(lambda: tcnn.grid_backward_params(xn, dy, g, out=dt))
     dt.zero_(); tcnn.grid_backward_params(xn, dy, g, out=dt)
     if ref is None: ref = dt.clone()
-    print(f"SPT {spt}: {t:.3f} ms  samples {xn.shape[0]}  rel diff vs SPT8 {float((dt-ref).norm()/ref.norm()):.2e}", flush=True)
+    print(f"LC {lc} SPT {spt}: {t:.3f} ms  samples {xn.shape[0]}  rel diff vs SPT8 {float((dt-ref).norm()/ref.norm()):.2e}", flush=True)
