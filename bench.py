@@ -142,34 +142,52 @@ def kernel_breakdown(model, xyzs, dirs):
     return out
 
 
-def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20):
+def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1):
     """Test-time rendering (BASELINE.json configs[4]): full frames through raymarching_test +
-    composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules."""
+    composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules.
+    With world > 1 every frame's rays are split into `world` contiguous tiles, one per rank, no collective on
+    the data path; the frame time is the max over ranks."""
+    import torch.distributed as dist
     from ngp_b200.rendering import render
     out = {}
+    scheds = ("wavefront", "geometric", "reference") if world == 1 else ("wavefront",)
     with torch.no_grad():
-        for sched in ("wavefront", "geometric", "reference"):
+        for sched in scheds:
             def frame(i):
-                ro, rd = scene.image_rays(poses[i % poses.shape[0]], wh=wh)
+                W, H = wh
+                n = W * H
+                a0, a1 = n * rank // world, n * (rank + 1) // world           # this rank's tile of the frame
+                px = torch.arange(a0, a1, device="cuda")
+                sc = scene.img_wh[0] / W
+                u, v = (px % W).float() * sc + (sc - 1) / 2, (px // W).float() * sc + (sc - 1) / 2     # = BoxScene.image_rays on the tile
+                ro, rd = scene.rays_from_pixels(poses[i % poses.shape[0]][None], torch.zeros(a1 - a0, dtype=torch.long, device="cuda"), u, v)
                 tot = 0
                 for a in range(0, ro.shape[0], chunk):
                     r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=0.0, num_classes=0, test_time=True,
                                T_threshold=1e-2, sample_schedule=sched if sched != "wavefront" else "geometric",
                                renderer="wavefront" if sched == "wavefront" else "loop")
                     tot += int(r["total_samples"])
-                return tot, ro.shape[0]
+                return tot, n
             frame(0); torch.cuda.synchronize()
-            n = frames if sched == "wavefront" else 1
+            nf = frames if sched == "wavefront" else 1
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for i in range(n):
+            for i in range(nf):
                 tot, nr = frame(i + 1)
             torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n
+            dt = torch.tensor([(time.perf_counter() - t0) / nf], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([float(tot)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            dt, tot = float(dt), float(tt)
             out[sched] = {"Mrays_per_s": nr / dt / 1e6, "ms_per_frame": dt * 1e3, "samples_per_ray": tot / nr}
     return {"metric": "render Mrays/s", "frame": f"{wh[0]}x{wh[1]}", "value": out["wavefront"]["Mrays_per_s"], "unit": "Mrays/s",
+            "n_gpus": world, "sharding": "contiguous ray tiles per rank, no collective" if world > 1 else "single GPU",
             "legend": "wavefront = fused advance kernel per round; geometric / reference = reference-style loop over "
                       "raymarching_test + composite_test_fw with 4,8,16.. / the reference's own round sizes",
-            "timing": "wall clock incl. the per-round host read-backs, rays generated on device", **{k: v for k, v in out.items()}}
+            "timing": "wall clock incl. the per-round host read-backs, rays generated on device, max over ranks", **{k: v for k, v in out.items()}}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -269,6 +287,11 @@ def gpu_arm(args):
         q = float(psnr(out["rgb"], gt))
         spr = float(out["total_samples"]) / ro.shape[0]
         rays_a, xyzs, dirs = out["rays_a"], out["xyzs"], None
+    rend = None
+    if not args.no_render:
+        rend = render_bench(model, scene, poses, rank=rank, world=world)
+        if args.render_4k:
+            rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,7 +330,6 @@ def gpu_arm(args):
                     "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 — the kernel is bound by L2 "
                     "atomic throughput (ncu lts__throughput 77 %, 50 red sectors/sample), see profiles/r01b_ncu_hashgrid_bw_params_kernel.txt")
 
-    rend = render_bench(model, scene, poses) if not args.no_render else None
     cpu, _ = cpu_arm(steps=4, warmup=1)
     value = world * R * args.steps / t_res
     line = {
@@ -335,6 +357,7 @@ def main():
     ap.add_argument("--pretrain", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-render", action="store_true", help="skip the test-time render sweep")
+    ap.add_argument("--render-4k", action="store_true", help="also render 3840x2160 frames (BASELINE.json configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:

@@ -153,6 +153,17 @@ int ngp_hashgrid_bw_input(const float* x, const float* aabb, const float* dL_dy,
 int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const float* g2, const float* dL_dy, const void* table, int table_dtype,
                             int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
                             float per_level_scale, int64_t n, float* dtable, float* d_dL_dy, void* stream);
+/* Fused density path of the ngp_pl-shaped field (private layouts, no reference counterpart): the encoder writes bf16
+ * features directly as 128-sample tcgen05 operand tiles (ngp_feature_tile_bytes each) which ngp_mlp_fw/bw load with one
+ * bulk copy (segment kind 2), and ngp_mlp_bw returns dL/dy as fp32 "gradient tiles" (ceil(N/128)*128*k0p floats,
+ * level-chunk major) which the scatter consumes — the fp32 (N, L*F) feature / gradient matrices never exist. */
+int64_t ngp_feature_tile_bytes(int n_levels, int n_features);
+int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels,
+                          int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
+                          void* y_tiles, void* stream);
+int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, const float* dy_tiles, int n_levels, int n_features,
+                                 int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
+                                 float* dtable, void* stream);
 
 /* ------------------------------------------------------------------ a11: SH direction encoding
  * tcnn.Encoding(3, {"otype":"SphericalHarmonics","degree":4|3})  models/networks.py:78-85,128-135 */
@@ -160,7 +171,8 @@ int ngp_sh_fw(const float* v, int degree, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------ a12: fused MLP (tcgen05/TMEM)
  * tcnn.Network(n_in, n_out, {"otype":"CutlassMLP", ...})  models/networks.py:89-162
- * Input = concatenation of up to 3 segments (kind 0: fp32 rows; kind 1: SH4 of normalised dirs).
+ * Input = concatenation of up to 3 segments (kind 0: fp32 rows; kind 1: SH4 of normalised dirs; kind 2: bf16 feature
+ * tiles from ngp_hashgrid_fw_tiles, single segment only, gradient returned as gradient tiles).
  * Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.  aux_exp_out / dL_daux_exp (optional): the density head
  * sigma = TruncExp(out[:,0]) of the ngp_pl-shaped field (custom_functions.py:200-211) fused into the epilogues. */
 int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_out);

@@ -35,6 +35,7 @@ struct GridMeta {
   // bit-identical to the (x - xyz_min) / (xyz_max - xyz_min) tensor pass of models/networks.py:174,188
   int affine;
   float lo[3], range[3];
+  int k0p;                 // L*F rounded up to 16: operand-tile width of the feature-tile / gradient-tile layouts
 };
 __device__ __forceinline__ void to_unit(const GridMeta& m, float& x, float& y, float& z) {
   if (m.affine) {
@@ -94,16 +95,33 @@ __device__ __forceinline__ Cell locate(float x, float y, float z, float scale) {
 template <int F> constexpr int levels_per_thread() { return F >= 8 ? 1 : 8 / F; }
 
 // ----------------------------------------------------------------------------------- forward
-template <int F, typename TP>
+// Feature tiles (private layout of the fused density path, see mlp.cu "kSegTiles"): per 128-sample tile the
+// encoder writes bf16 features directly in the tcgen05 operand layout of the MLP's input tile
+//     byte(tile, r, c) = tile*kFeatTileBytes(k0p) + (c/8)*(128*16 + 64) + r*16 + (c%8)*2
+// — one 16-byte row chunk per thread (LC*F == 8 columns), consecutive samples contiguous — so the MLP loads a
+// tile with ONE bulk copy and no conversion pass, and the fp32 (N, L*F) feature matrix never exists.
+__host__ __device__ __forceinline__ uint32_t feat_chunk_stride() { return 128u * 16u + 64u; }
+__host__ __device__ __forceinline__ uint32_t feat_tile_bytes(int k0p) { return (uint32_t)(k0p / 8) * feat_chunk_stride(); }
+
+template <int F, typename TP, bool TILES>
 __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
                                                           GridMeta m, int64_t n, float* __restrict__ y) {
   constexpr int LC = levels_per_thread<F>();
   // level chunk is the FASTEST block coordinate: the n_chunks CTAs that touch the same 128-byte rows of
   // x / y run back to back, so the rows are served from L2 instead of being swept from HBM once per chunk
-  const int n_chunks = (m.n_levels + LC - 1) / LC;
+  const int n_chunks = TILES ? m.k0p / 8 : (m.n_levels + LC - 1) / LC;
   const int64_t i = (int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const int l0 = (blockIdx.x % n_chunks) * LC;
+  if (TILES) {
+    // n_chunks covers the PADDED width (k0p/8 chunks); rows past n of the last tile and chunks past the last
+    // level are written as zeros: the MLP multiplies whole 128-row tiles
+    if (i >= ((n + 127) >> 7 << 7)) return;
+    if (i >= n || l0 >= m.n_levels) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(y) + (i >> 7) * (int64_t)feat_tile_bytes(m.k0p) + (uint32_t)(l0 / LC) * feat_chunk_stride() + (uint32_t)(i & 127) * 16u;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+  } else if (i >= n) return;
   float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
   to_unit(m, xx, xy, xz);
   float out[LC * F];
@@ -141,6 +159,17 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
         for (int f = 0; f < F; f++) out[li * F + f] = fmaf(w, v[k][f], out[li * F + f]);
       }
     }
+  }
+  if (TILES) {
+    static_assert(LC * F == 8, "one 16-byte bf16 row chunk per thread");
+    uint8_t* dstt = reinterpret_cast<uint8_t*>(y) + (i >> 7) * (int64_t)feat_tile_bytes(m.k0p) + (uint32_t)(l0 / LC) * feat_chunk_stride() + (uint32_t)(i & 127) * 16u;
+    uint4 q;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(out[0], out[1]), h1 = __floats2bfloat162_rn(out[2], out[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(out[4], out[5]), h3 = __floats2bfloat162_rn(out[6], out[7]);
+    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dstt) = q;
+    return;
   }
   const int LF = m.n_levels * F;
   float* dst = y + i * LF + (int64_t)l0 * F;
@@ -191,7 +220,11 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, float* __restric
   }
 }
 
-template <int F, int LC>
+// DYT: dL/dy arrives in "gradient tiles" (written by the MLP backward, mlp.cu): fp32, per 128-sample tile
+//     float(tile, r, c) at tile*(128*k0p) + (c/8)*(128*8) + r*8 + (c%8)
+// i.e. the 8 columns of a level chunk are one 32-byte sector per sample and consecutive samples are contiguous —
+// exactly what a (run of samples, level chunk) thread reads, and what a row-per-thread MLP epilogue writes coalesced.
+template <int F, int LC, bool DYT>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
   const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
@@ -209,7 +242,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
     if (i >= n) break;
     float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
     to_unit(m, xx, xy, xz);
-    const float* src = dy + i * LF + (int64_t)l0 * F;
+    const float* src = DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
+                           : dy + i * LF + (int64_t)l0 * F;
     float g[LC * F];
     if (l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0) {
 #pragma unroll
@@ -355,6 +389,7 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
   if (n_levels < 1 || n_levels > kMaxLevels) return -1;
   if (!(F == 1 || F == 2 || F == 4 || F == 8)) return -1;
   m.n_levels = n_levels; m.n_features = F;
+  m.k0p = (n_levels * F + 15) / 16 * 16;
   m.affine = aabb != nullptr;
   for (int d = 0; d < 3; d++) { m.lo[d] = aabb ? aabb[d] : 0.f; m.range[d] = aabb ? aabb[3 + d] : 1.f; }
   const float log2_pls = log2f(per_level_scale);
@@ -424,8 +459,8 @@ NGP_API int ngp_hashgrid_fw(const float* x, const float* aabb, const void* table
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
     const unsigned grid = (unsigned)(ceil_div(n, 256) * ceil_div(n_levels, LC));
-    if (table_dtype == 0) hashgrid_fw_kernel<F, float><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
-    else hashgrid_fw_kernel<F, __half><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
+    if (table_dtype == 0) hashgrid_fw_kernel<F, float, false><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
+    else hashgrid_fw_kernel<F, __half, false><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_fw");
   return 0;
@@ -447,10 +482,10 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     if (e2 && atoi(e2) == 2 && LC >= 2) {
       constexpr int LC2 = LC >= 2 ? LC / 2 : 1;
       const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC2));
-      hashgrid_bw_params_kernel<F, LC2><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+      hashgrid_bw_params_kernel<F, LC2, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     } else {
       const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC));
-      hashgrid_bw_params_kernel<F, LC><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+      hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     }
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
@@ -493,5 +528,44 @@ NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const flo
     else hashgrid_bwbw_kernel<F, __half><<<grid, 256, 0, st>>>(x, g2, dL_dy, (const __half*)table, m, n, dtable, d_dL_dy);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bwbw_input");
+  return 0;
+}
+
+// ---- feature-tile / gradient-tile variants (the fused density path of the ngp_pl-shaped field) ---------------------
+// Bytes of one 128-sample bf16 feature tile for a grid of n_levels*n_features columns (padded to 16).
+NGP_API int64_t ngp_feature_tile_bytes(int n_levels, int n_features) {
+  return (int64_t)feat_tile_bytes((n_levels * n_features + 15) / 16 * 16);
+}
+// y_tiles (ceil(N/128) * ngp_feature_tile_bytes) = bf16(encode(x)) in the MLP's operand-tile layout (see the kernel).
+NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels,
+                                  int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                                  int64_t n, void* y_tiles, void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
+    return set_error_msg("ngp_hashgrid_fw_tiles: bad grid config");
+  cudaStream_t st = (cudaStream_t)stream;
+  NGP_F_DISPATCH(n_features, {
+    const unsigned grid = (unsigned)(ceil_div(n, 256) * (m.k0p / 8));      // one thread per (sample, 16-byte chunk), padded width
+    if (table_dtype == 0) hashgrid_fw_kernel<F, float, true><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, (float*)y_tiles);
+    else hashgrid_fw_kernel<F, __half, true><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, (float*)y_tiles);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_fw_tiles");
+  return 0;
+}
+// dtable += scatter(dL/dy) with dL/dy in gradient tiles (ceil(N/128) * 128 * k0p floats, see the kernel).
+NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, const float* dy_tiles, int n_levels,
+                                         int n_features, int log2_hashmap_size, int base_resolution,
+                                         float per_level_scale, int64_t n, float* dtable, void* stream) {
+  if (n <= 0) return 0;
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
+    return set_error_msg("ngp_hashgrid_bw_params_tiles: bad grid config");
+  NGP_F_DISPATCH(n_features, {
+    constexpr int LC = levels_per_thread<F>();
+    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 128) * ceil_div(n_levels, LC));
+    hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
+  });
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");
   return 0;
 }

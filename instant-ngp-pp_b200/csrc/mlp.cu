@@ -41,7 +41,7 @@ constexpr int kMaxSeg = 3;
 constexpr int kMaxHidden = 6;
 
 enum Act { kActNone = 0, kActReLU = 1, kActSigmoid = 2, kActExp = 3 };
-enum SegKind { kSegPlain = 0, kSegSH4 = 1 };
+enum SegKind { kSegPlain = 0, kSegSH4 = 1, kSegTiles = 2 };   // 2: bf16 feature tiles already in operand layout (hashgrid.cu)
 
 struct MlpCfg {
   int n_seg;
@@ -61,6 +61,8 @@ struct MlpCfg {
   // raw fp32 landing zone of the slot's NEXT tile (one bulk copy per segment), relative to the slot's region
   uint32_t off_raw[kMaxSeg], raw_bytes[kMaxSeg], raw_total;
   int bulk;                        // every segment contiguous + 16-byte aligned, and the zone fits
+  int x_tiles;                     // the single input segment is a feature-tile array: X is double buffered and filled by ONE bulk copy
+  uint32_t x_bytes;                // bytes of one X operand tile
   uint32_t smem_bytes;
   // TMEM columns: slot s accumulates in [s*acc_cols, (s+1)*acc_cols); wgrad accumulators (backward) follow
   uint32_t acc_cols, tm_cols;
@@ -70,7 +72,7 @@ struct MlpCfg {
 };
 
 struct SegPtrs { const float* p[kMaxSeg]; };
-struct SegGrads { float* p[kMaxSeg]; int64_t stride[kMaxSeg]; };
+struct SegGrads { float* p[kMaxSeg]; int64_t stride[kMaxSeg]; int tiles; };   // tiles: p[0] is a gradient-tile array (hashgrid.cu DYT)
 
 __device__ __forceinline__ float act_apply(int a, float z) {
   switch (a) {
@@ -235,6 +237,7 @@ struct StaticShape {
 // the two networks of the ngp_pl-shaped field (networks.py NGPCompact): density 32 -> 64 -> 16, colour [SH4(d) | h16] -> 64 -> 64 -> 3
 using SigmaShape = StaticShape<1, kSegPlain, 32, 0, 0, 64, 1, 16, kActReLU, kActNone>;
 using RgbShape = StaticShape<2, kSegSH4, 16, kSegPlain, 16, 64, 2, 3, kActReLU, kActSigmoid>;
+using SigmaTilesShape = StaticShape<1, kSegTiles, 32, 0, 0, 64, 1, 16, kActReLU, kActNone>;   // density net fed by feature tiles
 
 template <typename SH> __device__ __forceinline__ Dims make_dims(const MlpCfg& c) {
   Dims d;
@@ -345,6 +348,11 @@ __device__ __forceinline__ void stage_row(const MlpCfg& c, const Dims& d, const 
 // current tile and costs no registers and no LSU instructions.
 __device__ __forceinline__ bool tile_is_bulk(const MlpCfg& c, const Dims& d, int64_t tile, int64_t n) {
   return c.bulk && (tile + 1) * kTile <= n;
+}
+// feature tiles: tile k of a slot lands in X buffer (k & 1) — already bf16, already in operand layout
+__device__ __forceinline__ void issue_tile_prefetch(const MlpCfg& c, const SegPtrs& in, int64_t tile, int buf, const Slot& S) {
+  mbar_expect_tx(S.full, c.x_bytes);
+  bulk_g2s(S.base + c.off_x + buf * c.x_bytes, reinterpret_cast<const uint8_t*>(in.p[0]) + tile * (int64_t)c.x_bytes, c.x_bytes, S.full);
 }
 __device__ __forceinline__ void issue_prefetch(const MlpCfg& c, const Dims& d, const SegPtrs& in, int64_t tile, const Slot& S) {
   const int64_t row0 = tile * kTile;
@@ -512,21 +520,29 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
   const bool out_vec = ((out_stride & 3) == 0) && ((((uintptr_t)out) & 15) == 0);
   constexpr int CH = SLOTS > 6 ? 16 : (SLOTS > 4 ? 32 : 64);
 
-  zero_pad_cols(c, d, t, Xs);
+  const bool xt = d.seg_kind[0] == kSegTiles;
+  if (!xt) zero_pad_cols(c, d, t, Xs);
   {
     const int64_t first = (int64_t)blockIdx.x * SLOTS + S.id;
-    if (t == 0 && first < n_tiles && tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
+    if (t == 0 && first < n_tiles) {
+      if (xt) issue_tile_prefetch(c, in, first, 0, S);
+      else if (tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
+    }
     __syncwarp();
   }
-  for (int64_t tile = (int64_t)blockIdx.x * SLOTS + S.id; tile < n_tiles; tile += tstride) {
+  int buf = 0;
+  for (int64_t tile = (int64_t)blockIdx.x * SLOTS + S.id; tile < n_tiles; tile += tstride, buf ^= 1) {
     const int64_t row = tile * kTile + t;
-    if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
+    const uint32_t xoff = c.off_x + (xt ? buf * c.x_bytes : 0u);
+    if (xt) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; }
+    else if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
     else stage_row(c, d, in, row, row < n, t, Xs);
     publish(S);
     {   // the landing zone is free again: fetch the slot's next tile while this one is computed
       const int64_t nxt = tile + tstride;
       if (nxt < n_tiles) {
-        if (tile_is_bulk(c, d, nxt, n)) { if (t == 0) issue_prefetch(c, d, in, nxt, S); }
+        if (xt) { if (t == 0) issue_tile_prefetch(c, in, nxt, buf ^ 1, S); }
+        else if (tile_is_bulk(c, d, nxt, n)) { if (t == 0) issue_prefetch(c, d, in, nxt, S); }
         else if (row + tstride * kTile < n) prefetch_row(c, d, in, row + tstride * kTile);
       }
       __syncwarp();
@@ -537,7 +553,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
       const int K = l == 0 ? d.k0p : d.wp;
       if (t == 0) {
         fence_after_sync();
-        issue_fwd(S.tacc, S.sbase + (l == 0 ? c.off_x : c.off_h[0]), smem_u32(smem) + c.off_w[l], (uint32_t)N, N, K);
+        issue_fwd(S.tacc, S.sbase + (l == 0 ? xoff : c.off_h[0]), smem_u32(smem) + c.off_w[l], (uint32_t)N, N, K);
         mma_commit(S.bar);
       }
       __syncwarp();
@@ -609,25 +625,35 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
   // zero the CTA-wide weight-gradient accumulators (every slot accumulates into them from its first tile on)
   for (uint32_t c0 = 16 * part; c0 < c.wg_cols; c0 += 16 * SLOTS) tmem_st16_zero(S.twg + ((quad * 32u) << 16) + c0);
   tmem_wait_st();
-  zero_pad_cols(c, d, t, Xs);
+  if (d.seg_kind[0] != kSegTiles) zero_pad_cols(c, d, t, Xs);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
 
+  const bool xt = d.seg_kind[0] == kSegTiles;
   {
     const int64_t first = (int64_t)blockIdx.x * SLOTS + S.id;
-    if (t == 0 && first < n_tiles && tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
+    if (t == 0 && first < n_tiles) {
+      if (xt) issue_tile_prefetch(c, in, first, 0, S);
+      else if (tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
+    }
     __syncwarp();
   }
-  for (int64_t tile = (int64_t)blockIdx.x * SLOTS + S.id; tile < n_tiles; tile += tstride) {
+  int buf = 0;
+  for (int64_t tile = (int64_t)blockIdx.x * SLOTS + S.id; tile < n_tiles; tile += tstride, buf ^= 1) {
     const int64_t row = tile * kTile + t;
     const bool valid = row < n;
-    if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
+    const uint32_t xoff = c.off_x + (xt ? buf * c.x_bytes : 0u);
+    if (xt) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; }
+    else if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
     else stage_row(c, d, in, row, valid, t, Xs);
     publish(S);
     {
       const int64_t nxt = tile + tstride;
-      if (t == 0 && nxt < n_tiles && tile_is_bulk(c, d, nxt, n)) issue_prefetch(c, d, in, nxt, S);
+      if (t == 0 && nxt < n_tiles) {
+        if (xt) issue_tile_prefetch(c, in, nxt, buf ^ 1, S);
+        else if (tile_is_bulk(c, d, nxt, n)) issue_prefetch(c, d, in, nxt, S);
+      }
       __syncwarp();
     }
     // the first 16 columns of this row's dL/dy are requested NOW and consumed after the forward recompute,
@@ -654,7 +680,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     {
       const int64_t nrow = row + tstride * kTile;
       if (nrow < n) {
-        if (!tile_is_bulk(c, d, tile + tstride, n)) prefetch_row(c, d, in, nrow);
+        if (!xt && !tile_is_bulk(c, d, tile + tstride, n)) prefetch_row(c, d, in, nrow);
         for (int b = 0; b < d.no * 4; b += 128) prefetch_l2(reinterpret_cast<const char*>(dout + nrow * dout_stride) + b);
       }
     }
@@ -662,7 +688,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     for (int l = 0; l < d.nh; l++) {
       if (t == 0) {
         fence_after_sync();
-        issue_fwd(S.tacc, S.sbase + (l == 0 ? c.off_x : c.off_h[l - 1]), wbase + c.off_w[l], (uint32_t)d.wp, d.wp, l == 0 ? d.k0p : d.wp);
+        issue_fwd(S.tacc, S.sbase + (l == 0 ? xoff : c.off_h[l - 1]), wbase + c.off_w[l], (uint32_t)d.wp, d.wp, l == 0 ? d.k0p : d.wp);
         mma_commit(S.bar);
       }
       __syncwarp();
@@ -724,7 +750,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
       const bool is_out = l == d.nh;
       const int Nz = is_out ? d.nop : d.wp;                       // width of dZ_l
       const int Kin = l == 0 ? d.k0p : d.wp;                      // width of the layer's input
-      const uint32_t ain = S.sbase + (l == 0 ? c.off_x : c.off_h[l - 1]);
+      const uint32_t ain = S.sbase + (l == 0 ? xoff : c.off_h[l - 1]);
       const uint32_t dza = S.sbase + (is_out ? c.off_dz : c.off_h[l]);
       const bool need_dgrad = l > 0 || want_dx;
       if (t == 0) {
@@ -757,6 +783,20 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
           }
         }
         publish(S);
+      } else if (want_dx && dseg.tiles) {
+        // gradient tiles: row r of chunk q is 32 bytes at tile*(128*k0p) + q*(128*8) + r*8 floats — consecutive rows
+        // contiguous, so a warp's two 16-byte stores per chunk cover 1 KB of whole sectors
+        float* tbase = dseg.p[0] + tile * (int64_t)(kTile * d.k0p) + t * 8;
+        for (int c0 = 0; c0 < d.k0p; c0 += 16) {
+          float v[16];
+          tmem_ld16(S.trow + c0, v);
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            float4* dst = reinterpret_cast<float4*>(tbase + ((c0 >> 3) + q) * (kTile * 8));
+            dst[0] = make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]);
+            dst[1] = make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
+          }
+        }
       } else if (want_dx) {
         // input gradient straight from TMEM to global: each thread owns 64-byte runs of its row
         for (int c0 = 0; c0 < d.k0; c0 += 16) {
@@ -825,8 +865,10 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
 static int finalize_cfg(MlpCfg& c, bool backward) {
   if (c.n_seg < 1 || c.n_seg > kMaxSeg) return -1;
   c.k0 = 0;
+  c.x_tiles = 0;
   for (int s = 0; s < c.n_seg; s++) {
     if (c.seg_kind[s] == kSegSH4 && c.seg_w[s] != 16) return -2;
+    if (c.seg_kind[s] == kSegTiles) { if (c.n_seg != 1) return -6; c.x_tiles = 1; c.bulk = 0; }
     c.k0 += c.seg_w[s];
   }
   c.k0p = (c.k0 + 15) / 16 * 16;
@@ -845,7 +887,8 @@ static int finalize_cfg(MlpCfg& c, bool backward) {
   }
   c.slot_base = off;
   uint32_t rel = 0;
-  c.off_x = rel; rel += al(tile_bytes(kTile, c.k0p));
+  c.x_bytes = tile_bytes(kTile, c.k0p);                   // == ngp_feature_tile_bytes: a multiple of 128
+  c.off_x = rel; rel += al(c.x_bytes) * (c.x_tiles ? 2u : 1u);   // feature tiles: double buffered, filled by bulk copy
   const int n_h = backward ? c.nh : 1;
   for (int l = 0; l < n_h; l++) { c.off_h[l] = rel; rel += al(tile_bytes(kTile, c.wp)); }
   for (int l = n_h; l < kMaxHidden; l++) c.off_h[l] = c.off_h[0];
@@ -974,18 +1017,20 @@ NGP_API int64_t ngp_mlp_param_count(int n_input, int width, int n_hidden, int n_
     launched = true;                                                                                  \
   } break;
 
-// 0 generic, 1 SigmaShape, 2 RgbShape
+// 0 generic, 1 SigmaShape, 2 RgbShape, 3 SigmaTilesShape
 static int match_shape(const MlpCfg& c) {
   if (env_int("NGP_MLP_GENERIC") > 0) return 0;
   if (c.w != 64 || c.act_h != kActReLU) return 0;
   if (c.n_seg == 1 && c.seg_kind[0] == kSegPlain && c.seg_w[0] == 32 && c.nh == 1 && c.no == 16 && c.act_o == kActNone) return 1;
+  if (c.n_seg == 1 && c.seg_kind[0] == kSegTiles && c.seg_w[0] == 32 && c.nh == 1 && c.no == 16 && c.act_o == kActNone) return 3;
   if (c.n_seg == 2 && c.seg_kind[0] == kSegSH4 && c.seg_kind[1] == kSegPlain && c.seg_w[1] == 16 && c.nh == 2 && c.no == 3 &&
       c.act_o == kActSigmoid) return 2;
   return 0;
 }
 
 // out (N, n_out) = MLP(cat(segments)).  Segment kinds: 0 = fp32 rows of seg_width floats at
-// seg_ptr + row*seg_stride; 1 = degree-4 SH of the normalised (N,3) direction at seg_ptr (width 16).
+// seg_ptr + row*seg_stride; 1 = degree-4 SH of the normalised (N,3) direction at seg_ptr (width 16); 2 = bf16 feature
+// tiles written by ngp_hashgrid_fw_tiles (must be the only segment; its input gradient comes back as gradient tiles).
 // Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.  aux_exp_out (optional, N floats) = exp(out[:,0]) taken
 // before the output activation (the ngp_pl density head).
 NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
@@ -1007,7 +1052,7 @@ NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_wi
     NGP_MLP_DISPATCH(6, mlp_fw_kernel, SH_, FW_ARGS)     \
     NGP_MLP_DISPATCH(8, mlp_fw_kernel, SH_, FW_ARGS)     \
     default: break; }
-  if (shape == 1) { FW_STATIC(SigmaShape) } else if (shape == 2) { FW_STATIC(RgbShape) }
+  if (shape == 1) { FW_STATIC(SigmaShape) } else if (shape == 2) { FW_STATIC(RgbShape) } else if (shape == 3) { FW_STATIC(SigmaTilesShape) }
   if (!launched) switch (c.slots) {
     NGP_MLP_DISPATCH(1, mlp_fw_kernel, GenericShape, FW_ARGS)
     NGP_MLP_DISPATCH(2, mlp_fw_kernel, GenericShape, FW_ARGS)
@@ -1038,9 +1083,11 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   SegPtrs in; SegGrads dg;
   for (int s = 0; s < kMaxSeg; s++) {
     in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
-    dg.p[s] = (s < n_seg && dseg_ptr && seg_kind[s] == kSegPlain) ? dseg_ptr[s] : nullptr;
+    dg.p[s] = (s < n_seg && dseg_ptr && seg_kind[s] != kSegSH4) ? dseg_ptr[s] : nullptr;
     dg.stride[s] = (s < n_seg && dseg_stride) ? dseg_stride[s] : 0;
   }
+  // a feature-tile input gets its gradient back as gradient tiles (hashgrid.cu DYT layout): ceil(N/128)*128*k0p floats
+  dg.tiles = (n_seg == 1 && seg_kind[0] == kSegTiles) ? 1 : 0;
   bool launched = false;
   const int shape = match_shape(c);
 #define BW_ARGS c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp
@@ -1051,7 +1098,7 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
     NGP_MLP_DISPATCH(5, mlp_bw_kernel, SH_, BW_ARGS)     \
     NGP_MLP_DISPATCH(6, mlp_bw_kernel, SH_, BW_ARGS)     \
     default: break; }
-  if (shape == 1) { BW_STATIC(SigmaShape) } else if (shape == 2) { BW_STATIC(RgbShape) }
+  if (shape == 1) { BW_STATIC(SigmaShape) } else if (shape == 2) { BW_STATIC(RgbShape) } else if (shape == 3) { BW_STATIC(SigmaTilesShape) }
   if (!launched) switch (c.slots) {
     NGP_MLP_DISPATCH(1, mlp_bw_kernel, GenericShape, BW_ARGS)
     NGP_MLP_DISPATCH(2, mlp_bw_kernel, GenericShape, BW_ARGS)

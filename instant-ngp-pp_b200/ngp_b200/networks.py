@@ -279,9 +279,13 @@ class NGPCompact(nn.Module, _OccupancyMixin):
         return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
 
     has_normals = False     # no normal / semantic heads: the renderer takes the lite compositor path
+    fused_density = True    # encoder -> bf16 operand tiles -> MLP -> gradient tiles -> scatter (tcnn._DensityFieldFn)
 
     def density(self, x, return_feat=False):
-        h, sigmas = self.sigma_net.forward_density_head(self.xyz_encoder(x.contiguous(), self.aabb()))
+        if self.fused_density and self.xyz_encoder.params.dtype == torch.float32:
+            h, sigmas = self.sigma_net.forward_density_field(x, self.xyz_encoder, self.aabb())
+        else:
+            h, sigmas = self.sigma_net.forward_density_head(self.xyz_encoder(x.contiguous(), self.aabb()))
         return (sigmas, h) if return_feat else sigmas
 
     def forward(self, x, d, **kwargs):

@@ -206,14 +206,14 @@ def _seg_arrays(segs):
     P = (ctypes.c_void_p * k)(*[ptr(t) for t, _, _ in segs])
     W = (ctypes.c_int * k)(*[int(w) for _, w, _ in segs])
     K = (ctypes.c_int * k)(*[int(kd) for _, _, kd in segs])
-    S = (ctypes.c_int64 * k)(*[int(t.stride(0)) for t, _, _ in segs])
+    S = (ctypes.c_int64 * k)(*[int(t.stride(0)) if kd != 2 else 0 for t, _, kd in segs])
     return P, W, K, S
 
 
-def mlp_forward(segs, params, m: MlpConfig, aux_exp=False):
-    """segs: [(tensor (N,w) fp32 | dirs (N,3), width, kind)]; kind 0 plain, 1 SH4-of-normalised-dirs.
-    aux_exp=True additionally returns exp(out[:,0]) (N) from the same epilogue."""
-    n = segs[0][0].shape[0]
+def mlp_forward(segs, params, m: MlpConfig, aux_exp=False, n=None):
+    """segs: [(tensor (N,w) fp32 | dirs (N,3), width, kind)]; kind 0 plain, 1 SH4-of-normalised-dirs, 2 bf16 feature
+    tiles (pass n).  aux_exp=True additionally returns exp(out[:,0]) (N) from the same epilogue."""
+    n = segs[0][0].shape[0] if n is None else n
     out = torch.empty(n, m.n_out, dtype=torch.float32, device=params.device)
     aux = torch.empty(n, dtype=torch.float32, device=params.device) if aux_exp else None
     P, W, K, S = _seg_arrays(segs)
@@ -222,15 +222,16 @@ def mlp_forward(segs, params, m: MlpConfig, aux_exp=False):
     return (out, aux) if aux_exp else out
 
 
-def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None):
-    n = segs[0][0].shape[0]
+def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None, n=None, dseg_numel=None):
+    n = segs[0][0].shape[0] if n is None else n
     dparams = torch.zeros_like(params)
     P, W, K, S = _seg_arrays(segs)
-    dsegs = [torch.empty(n, w, dtype=torch.float32, device=params.device) if (nd and kd == 0) else None
+    dsegs = [(torch.empty(dseg_numel, dtype=torch.float32, device=params.device) if kd == 2 else
+              torch.empty(n, w, dtype=torch.float32, device=params.device)) if (nd and kd != 1) else None
              for (_, w, kd), nd in zip(segs, need_dseg)]
     k = len(segs)
     DP = (ctypes.c_void_p * k)(*[ptr(d) for d in dsegs])
-    DS = (ctypes.c_int64 * k)(*[int(d.stride(0)) if d is not None else 0 for d in dsegs])
+    DS = (ctypes.c_int64 * k)(*[int(d.stride(0)) if (d is not None and d.dim() == 2) else 0 for d in dsegs])
     dout = dout.contiguous()
     check(lib.ngp_mlp_bw(k, P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n, ptr(dout),
                          dout.stride(0), ptr(dparams), DP, DS, ptr(d_aux.contiguous()) if d_aux is not None else None,
@@ -282,6 +283,52 @@ class _MlpDensityHeadFn(torch.autograd.Function):
         return (dparams if ctx.needs_input_grad[0] else None), None, dsegs[0]
 
 
+# --------------------------------------------------------------------------------------- fused density path
+def grid_forward_tiles(x, table, g: GridConfig, aabb=None):
+    """bf16 feature tiles (uint8 blob, ceil(N/128) tiles) in the MLP's tcgen05 operand layout."""
+    n = x.shape[0]
+    tb = int(lib.ngp_feature_tile_bytes(g.n_levels, g.n_features))
+    tiles = torch.empty((n + 127) // 128 * tb, dtype=torch.uint8, device=x.device)
+    check(lib.ngp_hashgrid_fw_tiles(ptr(x), _aabb_arg(aabb), ptr(table), 0 if table.dtype == torch.float32 else 1, *g.args(), n,
+                                    ptr(tiles), stream()), "hashgrid_fw_tiles")
+    return tiles
+
+
+class _DensityFieldFn(torch.autograd.Function):
+    """(h, sigma) = density_head(MLP(encode(x))) of the ngp_pl-shaped field as ONE autograd node over three kernels
+    per direction: the encoder writes bf16 operand tiles, the MLP bulk-copies them (no fp32 feature matrix, no
+    conversion pass), the MLP backward writes dL/dy as gradient tiles that the scatter reads sector by sector.
+    Same arithmetic as Encoding -> Network.forward_density_head (the MLP rounds its operands to bf16 either way)."""
+
+    @staticmethod
+    def forward(ctx, x, table, params, g, m, aabb):
+        _lib.require_device()
+        x = x.contiguous()
+        n = x.shape[0]
+        tiles = grid_forward_tiles(x.detach(), table.detach(), g, aabb)
+        ctx.g, ctx.m, ctx.aabb = g, m, aabb
+        ctx.save_for_backward(x, table, params, tiles)
+        h, sigma = mlp_forward([(tiles, g.n_levels * g.n_features, 2)], params.detach(), m, aux_exp=True, n=n)
+        return h, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dh, dsigma):
+        x, table, params, tiles = ctx.saved_tensors
+        g, m = ctx.g, ctx.m
+        n = x.shape[0]
+        k0p = (g.n_levels * g.n_features + 15) // 16 * 16
+        need_table = ctx.needs_input_grad[1]
+        dparams, dsegs = mlp_backward([(tiles, g.n_levels * g.n_features, 2)], params, m, dh, [need_table], d_aux=dsigma, n=n,
+                                      dseg_numel=(n + 127) // 128 * 128 * k0p)
+        dtable = None
+        if need_table:
+            dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device)
+            check(lib.ngp_hashgrid_bw_params_tiles(ptr(x), _aabb_arg(ctx.aabb), ptr(dsegs[0]), *g.args(), n, ptr(dtable), stream()),
+                  "hashgrid_bw_params_tiles")
+        return None, dtable, (dparams if ctx.needs_input_grad[2] else None), None, None, None
+
+
 def xavier_uniform_flat(shapes, seed):
     gen = torch.Generator().manual_seed(seed)
     parts = []
@@ -308,6 +355,11 @@ class Network(nn.Module):
     def forward_density_head(self, x):
         """-> (out (N,n_out), exp(out[:,0]) (N))"""
         return _MlpDensityHeadFn.apply(self.params, self.mlp, x.float())
+
+    def forward_density_field(self, x, encoding, aabb=None):
+        """-> (out (N,n_out), exp(out[:,0]) (N)) = forward_density_head(encoding(x, aabb)) through the fused
+        feature-tile path (one autograd node; the fp32 feature matrix is never materialised)."""
+        return _DensityFieldFn.apply(x.float(), encoding.params, self.params, encoding.grid, self.mlp, aabb)
 
     def forward_segments(self, tensors, kinds):
         """Fused input assembly: MLP(cat(segments)) without materialising the concatenation

@@ -241,3 +241,30 @@ def test_hashgrid_fused_aabb_is_bit_identical_to_normalising_first():
     ga, pa = xa.grad.clone(), enc.params.grad.clone(); enc.params.grad = None
     tcnn._GridFn.apply(xb, enc.params, enc.grid).square().sum().backward()
     assert torch.allclose(ga, xb.grad / rng, rtol=1e-6, atol=0) and rel(pa, enc.params.grad) < 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 40001])
+def test_fused_density_field_matches_unfused_path(n):
+    """Encoder -> bf16 operand tiles -> MLP (one bulk copy per tile) -> gradient tiles -> scatter must equal
+    Encoding -> Network.forward_density_head: the forward bit for bit (the MLP rounds the same fp32 features to the
+    same bf16 operands either way), the gradients up to fp32 atomic ordering."""
+    from ngp_b200 import tcnn
+    enc, _ = _grid(16, 2, 19, 16, 0.5)
+    net = tcnn.Network(32, 16, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                                "n_neurons": 64, "n_hidden_layers": 1}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = (torch.rand(n, 3, device="cuda", generator=g) - 0.5)
+    aabb = (-0.5, -0.5, -0.5, 1.0, 1.0, 1.0)
+    gh = torch.randn(n, 16, device="cuda", generator=g); gs = torch.randn(n, device="cuda", generator=g)
+    outs = []
+    for fused in (False, True):
+        enc.params.grad = None; net.params.grad = None
+        if fused:
+            h, sig = net.forward_density_field(x, enc, aabb)
+        else:
+            h, sig = net.forward_density_head(enc(x, aabb))
+        ((h * gh).sum() + (sig * gs).sum()).backward()
+        outs.append((h.detach().clone(), sig.detach().clone(), enc.params.grad.clone(), net.params.grad.clone()))
+    (h0, s0, dt0, dp0), (h1, s1, dt1, dp1) = outs
+    assert torch.equal(h0, h1) and torch.equal(s0, s1)
+    assert rel(dp1, dp0) < 1e-5 and rel(dt1, dt0) < 1e-5

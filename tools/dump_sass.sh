@@ -1,10 +1,24 @@
 #!/bin/bash
-# Regenerates profiles/sass/*.sass (cuobjdump -sass of the hot kernels in libngp_b200.so).
+# Regenerates profiles/sass/*.sass (cuobjdump -sass of the hot kernels in libngp_b200.so) — the instantiations the
+# headline step launches: density net fw<5 slots>/bw<4>, colour net fw<8>/bw<4>, hash grid F=2 fp32, marcher, compositors.
 set -e
 cd "$(dirname "$0")/../profiles/sass"
 SO="../../instant-ngp-pp_b200/libngp_b200.so"
 cuobjdump -sass $SO | grep "Function :" | sed 's/.*Function : //' > /tmp/fn_list.txt
-for pat in mlp_fw_kernel mlp_bw_kernel hashgrid_fw_kernelILi2EfE hashgrid_bw_params_kernelILi2E march_count_kernelILb1E composite_train_fw_kernelILi16E composite_train_bw_kernelILi16E; do
-  fn=$(grep "$pat" /tmp/fn_list.txt | head -1)
-  cuobjdump -sass -fun "$fn" $SO | sed 's#/\*[0-9a-f]\{4\}\*/##; s#/\* 0x[0-9a-f]* \*/##' | grep -v "^\s*$" > "$pat.sass"
-done
+rm -f mlp_fw_kernel.sass mlp_bw_kernel.sass
+dump() {  # pattern outname
+  fn=$(grep -E "$1" /tmp/fn_list.txt | head -1)
+  [ -z "$fn" ] && { echo "no function matches $1"; return; }
+  cuobjdump -sass -fun "$fn" $SO 2>/dev/null | sed 's#/\*[0-9a-f]\{4\}\*/##; s#/\* 0x[0-9a-f]* \*/##' | grep -v "^\s*$" > "$2.sass"
+}
+dump 'mlp_fw_kernelILi5ENS_11StaticShapeILi1E' mlp_fw_sigma_slots5
+dump 'mlp_fw_kernelILi8ENS_11StaticShapeILi2E' mlp_fw_rgb_slots8
+dump 'mlp_bw_kernelILi4ENS_11StaticShapeILi1E' mlp_bw_sigma_slots4
+dump 'mlp_bw_kernelILi4ENS_11StaticShapeILi2E' mlp_bw_rgb_slots4
+dump 'hashgrid_fw_kernelILi2EfE' hashgrid_fw_kernelILi2EfE
+dump 'hashgrid_bw_params_kernelILi2ELi4E' hashgrid_bw_params_kernelILi2ELi4E
+rm -f hashgrid_bw_params_kernelILi2E.sass
+dump 'march_count_kernelILb1E' march_count_kernelILb1E
+dump 'composite_train_fw_kernelILi16E' composite_train_fw_kernelILi16E
+dump 'composite_train_bw_kernelILi16E' composite_train_bw_kernelILi16E
+grep -c "UTCHMMA" mlp_*.sass; grep -c "UBLKCP" mlp_*.sass; grep -c "LDTM\|STTM" mlp_*.sass
