@@ -114,31 +114,38 @@ def time_kernel(fn, iters=10):
 
 
 def kernel_breakdown(model, xyzs, dirs):
-    """Times the individual hot kernels on the step's real sample set; returns {name: (seconds, algorithmic bytes or flops, unit)}."""
+    """Times the individual hot kernels of the step — the ones the fused density path launches — on the step's real
+    sample set; returns {name: (seconds, algorithmic bytes or flops, unit)}."""
     from ngp_b200 import tcnn
+    from ngp_b200._lib import lib, ptr, check, stream
     S = xyzs.shape[0]
     g = model.xyz_encoder.grid
     LF = g.n_levels * g.n_features
-    xn = ((xyzs - model.xyz_min) / (model.xyz_max - model.xyz_min)).contiguous()
+    k0p = (LF + 15) // 16 * 16
+    aabb = model.aabb()
+    xw = xyzs.contiguous()
     table = model.xyz_encoder.params.detach()
-    y = tcnn.grid_forward(xn, table, g)
-    dy = torch.randn_like(y)
+    tiles = tcnn.grid_forward_tiles(xw, table, g, aabb)
+    dy_tiles = torch.randn((S + 127) // 128 * 128 * k0p, device=xw.device)
     dtab = torch.zeros_like(table)
     out = {}
-    # SURVEY.md §8(d): fw 12 + 8*L*F*s_p + L*F*s_o ; bw(params) 12 + L*F*s_o + 2*8*L*F*s_g   (s = 4 bytes here)
-    out["hashgrid_fw"] = (time_kernel(lambda: tcnn.grid_forward(xn, table, g)), S * (12 + 8 * LF * 4 + LF * 4), "B")
-    out["hashgrid_bw_params"] = (time_kernel(lambda: tcnn.grid_backward_params(xn, dy, g, out=dtab)), S * (12 + LF * 4 + 16 * LF * 4), "B")
+    # SURVEY.md §8(d): fw 12 + 8*L*F*s_p + L*F*s_o (s_o = 2: bf16 operand tiles) ; bw(params) 12 + L*F*s_o + 2*8*L*F*s_g
+    out["hashgrid_fw"] = (time_kernel(lambda: tcnn.grid_forward_tiles(xw, table, g, aabb)), S * (12 + 8 * LF * 4 + LF * 2), "B")
+    scatter = lambda: check(lib.ngp_hashgrid_bw_params_tiles(ptr(xw), tcnn._aabb_arg(aabb), ptr(dy_tiles), *g.args(), S, ptr(dtab), stream()), "bw")
+    out["hashgrid_bw_params"] = (time_kernel(scatter), S * (12 + LF * 4 + 16 * LF * 4), "B")
     m1, m2 = model.sigma_net.mlp, model.rgb_net.mlp
-    h = tcnn.mlp_forward([(y, LF, 0)], model.sigma_net.params.detach(), m1)
+    p1, p2 = model.sigma_net.params.detach(), model.rgb_net.params.detach()
+    h, _ = tcnn.mlp_forward([(tiles, LF, 2)], p1, m1, aux_exp=True, n=S)
     flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
-    out["mlp_sigma_fw"] = (time_kernel(lambda: tcnn.mlp_forward([(y, LF, 0)], model.sigma_net.params.detach(), m1)), S * flops(m1, LF), "F")
-    dh = torch.randn_like(h)
-    out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(y, LF, 0)], model.sigma_net.params.detach(), m1, dh, [True])), S * flops(m1, LF) * 3, "F")
+    out["mlp_sigma_fw"] = (time_kernel(lambda: tcnn.mlp_forward([(tiles, LF, 2)], p1, m1, aux_exp=True, n=S)), S * flops(m1, LF), "F")
+    dh = torch.randn_like(h); ds = torch.randn(S, device=xw.device)
+    out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(tiles, LF, 2)], p1, m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel())),
+                           S * flops(m1, LF) * 3, "F")
     segs = [(dirs, 16, 1), (h, 16, 0)]
-    rgb = tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)
-    out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)), S * flops(m2, 32), "F")
+    rgb = tcnn.mlp_forward(segs, p2, m2)
+    out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, p2, m2)), S * flops(m2, 32), "F")
     drgb = torch.randn_like(rgb)
-    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True])), S * flops(m2, 32) * 3, "F")
+    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, p2, m2, drgb, [False, True])), S * flops(m2, 32) * 3, "F")
     return out
 
 

@@ -103,26 +103,25 @@ template <int F> constexpr int levels_per_thread() { return F >= 8 ? 1 : 8 / F; 
 __host__ __device__ __forceinline__ uint32_t feat_chunk_stride() { return 128u * 16u + 64u; }
 __host__ __device__ __forceinline__ uint32_t feat_tile_bytes(int k0p) { return (uint32_t)(k0p / 8) * feat_chunk_stride(); }
 
+// The gather is bound by the L1 tag stage: ONE 128-byte line per clock per SM, whatever the sectors
+// (tools/probes/l1_probe.cu: 32 lanes on 32 lines 285 G loads/s, lane pairs on the same line 562 G, octets 1159 G).
+// So the two x-neighbours of a corner pair — adjacent entries for dense levels, h(x) and h(x+1) = entries that differ
+// only in their low bits for hashed ones, i.e. the same line 15 times out of 16 — are fetched by the two lanes of a
+// lane PAIR in the same instruction: ~4.3 line lookups per (sample, level) instead of 6 (4 when x is even and the pair
+// could go out as one 16-byte load, 8 when it is odd).  The pair's partial sums meet through one shuffle per feature.
 template <int F, typename TP, bool TILES>
 __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
                                                           GridMeta m, int64_t n, float* __restrict__ y) {
   constexpr int LC = levels_per_thread<F>();
-  // level chunk is the FASTEST block coordinate: the n_chunks CTAs that touch the same 128-byte rows of
-  // x / y run back to back, so the rows are served from L2 instead of being swept from HBM once per chunk
+  // level chunk is the FASTEST block coordinate: the n_chunks CTAs that touch the same rows of x / y run back to
+  // back, so the rows are served from L2 instead of being swept from HBM once per chunk
   const int n_chunks = TILES ? m.k0p / 8 : (m.n_levels + LC - 1) / LC;
-  const int64_t i = (int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)(blockIdx.x / n_chunks) * (blockDim.x >> 1) + (threadIdx.x >> 1);   // 128 samples per CTA
+  const uint32_t xh = threadIdx.x & 1u;                                                            // which x-neighbour
   const int l0 = (blockIdx.x % n_chunks) * LC;
-  if (TILES) {
-    // n_chunks covers the PADDED width (k0p/8 chunks); rows past n of the last tile and chunks past the last
-    // level are written as zeros: the MLP multiplies whole 128-row tiles
-    if (i >= ((n + 127) >> 7 << 7)) return;
-    if (i >= n || l0 >= m.n_levels) {
-      uint8_t* dst = reinterpret_cast<uint8_t*>(y) + (i >> 7) * (int64_t)feat_tile_bytes(m.k0p) + (uint32_t)(l0 / LC) * feat_chunk_stride() + (uint32_t)(i & 127) * 16u;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-      return;
-    }
-  } else if (i >= n) return;
-  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  const bool in_range = i < n;
+  const int64_t ii = in_range ? i : n - 1;          // out-of-range lanes still take part in the pair shuffles
+  float xx = __ldg(x + 3 * ii), xy = __ldg(x + 3 * ii + 1), xz = __ldg(x + 3 * ii + 2);
   to_unit(m, xx, xy, xz);
   float out[LC * F];
 #pragma unroll
@@ -135,42 +134,41 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
       const TP* base = table + (size_t)m.offset[l] * F;
       const uint32_t res = m.res[l], size = m.size[l];
       const bool dense = m.dense[l];
-      float v[8][F];
+      const float wxs = xh ? c.wx : 1.f - c.wx;
+      float v[4][F];
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        const uint32_t i0 = grid_index(c.px, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-        const uint32_t i1 = grid_index(c.px + 1, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-        if constexpr (F == 2 && sizeof(TP) == 4) {
-          // the two x-neighbours are adjacent entries whenever the lower index is even (always for hashed
-          // levels with even x): one 16-byte gather instead of two 8-byte ones
-          if (i1 == i0 + 1 && (i0 & 1u) == 0) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(base + (size_t)i0 * 2));
-            v[2 * p][0] = q.x; v[2 * p][1] = q.y; v[2 * p + 1][0] = q.z; v[2 * p + 1][1] = q.w;
-            continue;
-          }
-        }
-        Vec<F, TP>::ld(base + (size_t)i0 * F, v[2 * p]);
-        Vec<F, TP>::ld(base + (size_t)i1 * F, v[2 * p + 1]);
+        const uint32_t idx = grid_index(c.px + xh, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+        Vec<F, TP>::ld(base + (size_t)idx * F, v[p]);
       }
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+      for (int p = 0; p < 4; p++) {
+        const float w = wxs * ((p & 1) ? c.wy : 1.f - c.wy) * (((p >> 1) & 1) ? c.wz : 1.f - c.wz);
 #pragma unroll
-        for (int f = 0; f < F; f++) out[li * F + f] = fmaf(w, v[k][f], out[li * F + f]);
+        for (int f = 0; f < F; f++) out[li * F + f] = fmaf(w, v[p][f], out[li * F + f]);
       }
     }
   }
+#pragma unroll
+  for (int k = 0; k < LC * F; k++) out[k] += __shfl_xor_sync(0xffffffffu, out[k], 1);
+  if (xh) return;
   if (TILES) {
-    static_assert(LC * F == 8, "one 16-byte bf16 row chunk per thread");
+    static_assert(LC * F == 8, "one 16-byte bf16 row chunk per (sample, level chunk)");
+    // n_chunks covers the PADDED width (k0p/8 chunks); rows past n of the last tile and chunks past the last level
+    // come out as zeros (out[] is 0 there / forced here): the MLP multiplies whole 128-row tiles
+    if (i >= ((n + 127) >> 7 << 7)) return;
     uint8_t* dstt = reinterpret_cast<uint8_t*>(y) + (i >> 7) * (int64_t)feat_tile_bytes(m.k0p) + (uint32_t)(l0 / LC) * feat_chunk_stride() + (uint32_t)(i & 127) * 16u;
-    uint4 q;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(out[0], out[1]), h1 = __floats2bfloat162_rn(out[2], out[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(out[4], out[5]), h3 = __floats2bfloat162_rn(out[6], out[7]);
-    q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-    q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (in_range) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(out[0], out[1]), h1 = __floats2bfloat162_rn(out[2], out[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(out[4], out[5]), h3 = __floats2bfloat162_rn(out[6], out[7]);
+      q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+      q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+    }
     *reinterpret_cast<uint4*>(dstt) = q;
     return;
   }
+  if (!in_range) return;
   const int LF = m.n_levels * F;
   float* dst = y + i * LF + (int64_t)l0 * F;
   if (l0 + LC <= m.n_levels && (LF % 4) == 0 && ((l0 * F) % 4) == 0) {
@@ -190,45 +188,41 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
 //  * a thread owns SPT consecutive samples (consecutive samples of a ray are packed together, and at a
 //    level whose cells are wider than the marching step they fall into the same cell): contributions
 //    to the same cell are merged in registers and flushed once per run;
-//  * the two x-neighbours of a corner pair are adjacent entries whenever the lower index is even
-//    (always for hashed levels with even x: h(x+1) = h(x)^1), so for F=2 the pair goes out as ONE
-//    16-byte red.global.add.v4.f32 instead of two 8-byte ones;
+//  * the two x-neighbours of a corner pair are issued by the two lanes of a lane pair in the same
+//    instruction, so that they are ONE sector request whenever they share a sector (below);
 //  * exactly-zero upstream rows (samples past early termination) are skipped.
 constexpr int kSPT = 24;   // 8 -> 16: one forced flush per run, -8 % (tools/hash_sweep.py)
 
+// Lane pairs again (see hashgrid_fw_kernel): lane xh of a pair accumulates the four corners with x = px + xh.  The L2
+// reduction rate is bound by 32-byte SECTOR requests (~220 G/s, tools/probes/l2_red_probe.cu), and two lanes of one
+// instruction that hit the same sector are one request: the x-neighbours share a sector whenever x is even (adjacent
+// entries, what the former 16-byte pair red exploited) AND when x = 1 mod 4 for hashed levels (h(x+1) = h(x) ^ 3), i.e.
+// 1.25 requests per corner pair instead of 1.5; halving the per-thread accumulators also lifts the occupancy.
 template <int F> struct CellAcc {
   uint32_t px, py, pz;
   bool has;
-  float a[8][F];
+  float a[4][F];
 };
 
 template <int F>
-__device__ __forceinline__ void flush_cell(const CellAcc<F>& c, float* __restrict__ base, uint32_t res, uint32_t size, bool dense) {
+__device__ __forceinline__ void flush_cell(const CellAcc<F>& c, uint32_t xh, float* __restrict__ base, uint32_t res, uint32_t size, bool dense) {
 #pragma unroll
   for (int p = 0; p < 4; p++) {
-    const uint32_t i0 = grid_index(c.px, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-    const uint32_t i1 = grid_index(c.px + 1, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-    if constexpr (F == 2) {
-      if (i1 == i0 + 1 && (i0 & 1u) == 0) {
-        atomicAdd(reinterpret_cast<float4*>(base + (size_t)i0 * 2),
-                  make_float4(c.a[2 * p][0], c.a[2 * p][1], c.a[2 * p + 1][0], c.a[2 * p + 1][1]));
-        continue;
-      }
-    }
-    red_add<F>(base + (size_t)i0 * F, c.a[2 * p]);
-    red_add<F>(base + (size_t)i1 * F, c.a[2 * p + 1]);
+    const uint32_t idx = grid_index(c.px + xh, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
+    red_add<F>(base + (size_t)idx * F, c.a[p]);
   }
 }
 
 // DYT: dL/dy arrives in "gradient tiles" (written by the MLP backward, mlp.cu): fp32, per 128-sample tile
 //     float(tile, r, c) at tile*(128*k0p) + (c/8)*(128*8) + r*8 + (c%8)
 // i.e. the 8 columns of a level chunk are one 32-byte sector per sample and consecutive samples are contiguous —
-// exactly what a (run of samples, level chunk) thread reads, and what a row-per-thread MLP epilogue writes coalesced.
+// exactly what a (run of samples, level chunk) lane pair reads, and what a row-per-thread MLP epilogue writes coalesced.
 template <int F, int LC, bool DYT>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
   const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
-  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * blockDim.x + threadIdx.x) * spt;
+  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
+  const uint32_t xh = threadIdx.x & 1u;
   if (s0 >= n) return;
   const int l0 = (blockIdx.x % n_chunks) * LC;
   const int LF = m.n_levels * F;
@@ -265,16 +259,17 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
         const Cell c = locate(xx, xy, xz, m.scale[l]);
         CellAcc<F>& A = acc[li];
         if (!A.has || A.px != c.px || A.py != c.py || A.pz != c.pz) {
-          if (A.has) flush_cell<F>(A, dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
+          if (A.has) flush_cell<F>(A, xh, dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
           A.px = c.px; A.py = c.py; A.pz = c.pz; A.has = true;
 #pragma unroll
-          for (int k = 0; k < 8; k++)
+          for (int k = 0; k < 4; k++)
 #pragma unroll
             for (int f = 0; f < F; f++) A.a[k][f] = 0.f;
         }
+        const float wxs = xh ? c.wx : 1.f - c.wx;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const float w = ((k & 1) ? c.wx : 1.f - c.wx) * (((k >> 1) & 1) ? c.wy : 1.f - c.wy) * (((k >> 2) & 1) ? c.wz : 1.f - c.wz);
+        for (int k = 0; k < 4; k++) {
+          const float w = wxs * ((k & 1) ? c.wy : 1.f - c.wy) * (((k >> 1) & 1) ? c.wz : 1.f - c.wz);
 #pragma unroll
           for (int f = 0; f < F; f++) A.a[k][f] = fmaf(w, g[li * F + f], A.a[k][f]);
         }
@@ -285,7 +280,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
   for (int li = 0; li < LC; li++) {
     const int l = l0 + li;
     if (l < m.n_levels && acc[li].has)
-      flush_cell<F>(acc[li], dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
+      flush_cell<F>(acc[li], xh, dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
   }
 }
 
@@ -458,7 +453,7 @@ NGP_API int ngp_hashgrid_fw(const float* x, const float* aabb, const void* table
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const unsigned grid = (unsigned)(ceil_div(n, 256) * ceil_div(n_levels, LC));
+    const unsigned grid = (unsigned)(ceil_div(n, 128) * ceil_div(n_levels, LC));     // lane pair per (sample, level chunk)
     if (table_dtype == 0) hashgrid_fw_kernel<F, float, false><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
     else hashgrid_fw_kernel<F, __half, false><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
   });
@@ -481,10 +476,10 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     const char* e2 = getenv("NGP_HASH_LC");
     if (e2 && atoi(e2) == 2 && LC >= 2) {
       constexpr int LC2 = LC >= 2 ? LC / 2 : 1;
-      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC2));
+      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC2));
       hashgrid_bw_params_kernel<F, LC2, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     } else {
-      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 128) * ceil_div(n_levels, LC));
+      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC));
       hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     }
   });
@@ -546,7 +541,7 @@ NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void*
     return set_error_msg("ngp_hashgrid_fw_tiles: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
-    const unsigned grid = (unsigned)(ceil_div(n, 256) * (m.k0p / 8));      // one thread per (sample, 16-byte chunk), padded width
+    const unsigned grid = (unsigned)(ceil_div(n, 128) * (m.k0p / 8));      // one lane pair per (sample, 16-byte chunk), padded width
     if (table_dtype == 0) hashgrid_fw_kernel<F, float, true><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, (float*)y_tiles);
     else hashgrid_fw_kernel<F, __half, true><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, (float*)y_tiles);
   });
@@ -563,7 +558,7 @@ NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, cons
     return set_error_msg("ngp_hashgrid_bw_params_tiles: bad grid config");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
-    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 128) * ceil_div(n_levels, LC));
+    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
     hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");

@@ -27,7 +27,7 @@ def tm(fn, it=5):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / it
 import itertools
-for lc, spt in itertools.product((4, 2), (8, 16, 24)):
+for lc, spt in itertools.product((4, 2), (16, 24, 32)):
     os.environ["NGP_HASH_SPT"] = str(spt); os.environ["NGP_HASH_LC"] = str(lc)
     dt = torch.zeros(g.n_params, device=dev)
     t = tm(lambda: tcnn.grid_backward_params(xn, dy, g, out=dt))

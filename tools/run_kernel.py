@@ -22,20 +22,22 @@ with torch.no_grad():
     for _ in range(2):
         ra, xyzs, dirs, deltas, ts, tot = RayMarcher.apply(ro, rd, hits_t[:, 0].contiguous(), model.density_bitfield, 1, 0.5, 0.0, 128, 1024)
     S = xyzs.shape[0]
+    from ngp_b200._lib import lib, ptr, check, stream
     g = model.xyz_encoder.grid
-    xn = ((xyzs - model.xyz_min) / (model.xyz_max - model.xyz_min)).contiguous()
+    aabb = model.aabb()
+    xw = xyzs.contiguous()
     table = model.xyz_encoder.params.detach()
     for _ in range(2):
-        y = tcnn.grid_forward(xn, table, g)
-    dy = torch.randn_like(y); dtab = torch.zeros_like(table)
+        tiles = tcnn.grid_forward_tiles(xw, table, g, aabb)
+    dy_tiles = torch.randn((S + 127) // 128 * 128 * 32, device=dev); dtab = torch.zeros_like(table)
     for _ in range(2):
-        tcnn.grid_backward_params(xn, dy, g, out=dtab)
+        check(lib.ngp_hashgrid_bw_params_tiles(ptr(xw), tcnn._aabb_arg(aabb), ptr(dy_tiles), *g.args(), S, ptr(dtab), stream()), "bw")
     m1, m2 = model.sigma_net.mlp, model.rgb_net.mlp
     for _ in range(2):
-        h, sig = tcnn.mlp_forward([(y, 32, 0)], model.sigma_net.params.detach(), m1, aux_exp=True)
+        h, sig = tcnn.mlp_forward([(tiles, 32, 2)], model.sigma_net.params.detach(), m1, aux_exp=True, n=S)
     dh = torch.randn_like(h); ds = torch.randn_like(sig)
     for _ in range(2):
-        tcnn.mlp_backward([(y, 32, 0)], model.sigma_net.params.detach(), m1, dh, [True], d_aux=ds)
+        tcnn.mlp_backward([(tiles, 32, 2)], model.sigma_net.params.detach(), m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel())
     segs = [(dirs, 16, 1), (h, 16, 0)]
     for _ in range(2):
         rgb = tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)
