@@ -28,6 +28,14 @@ import torch  # noqa: E402
 
 R_PER_GPU = 1 << 18
 WORKLOAD = "lego-shaped 800x800x100 views, scale 0.5, hashgrid L16 F2 T2^19 + 64-wide MLPs, 2^18 rays/GPU/step"
+# --workload street: BASELINE.json configs[3] shape (not the headline): unbounded street scene, scale 8 -> 5 cascades,
+# exponential stepping 1/256, T = 2^22 table (363 MB fp32: does NOT fit the L2), distortion loss
+WORKLOADS = {
+    "lego": dict(scene="lego", scale=0.5, log2_T=19, esf=0.0, lr=1e-2, views=100, name=WORKLOAD),
+    "street": dict(scene="street", scale=8.0, log2_T=22, esf=1.0 / 256, lr=2e-3, views=128,
+                   name="street-shaped (KITTI-360-1538 shape) 1408x376x128 views, scale 8 (5 cascades), exp_step 1/256, "
+                        "hashgrid L16 F2 T2^22 + 64-wide MLPs, distortion loss, 2^18 rays/GPU/step"),
+}
 
 
 def peaks():
@@ -149,7 +157,7 @@ def kernel_breakdown(model, xyzs, dirs):
     return out
 
 
-def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1):
+def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1, esf=0.0):
     """Test-time rendering (BASELINE.json configs[4]): full frames through raymarching_test +
     composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules.
     With world > 1 every frame's rays are split into `world` contiguous tiles, one per rank, no collective on
@@ -170,7 +178,7 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
                 ro, rd = scene.rays_from_pixels(poses[i % poses.shape[0]][None], torch.zeros(a1 - a0, dtype=torch.long, device="cuda"), u, v)
                 tot = 0
                 for a in range(0, ro.shape[0], chunk):
-                    r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=0.0, num_classes=0, test_time=True,
+                    r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=esf, num_classes=0, test_time=True,
                                T_threshold=1e-2, sample_schedule=sched if sched != "wavefront" else "geometric",
                                renderer="wavefront" if sched == "wavefront" else "loop")
                     tot += int(r["total_samples"])
@@ -222,12 +230,14 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(20220806); np.random.seed(20220806)          # train.py:402-404
 
-    scene = BoxScene("lego", device=dev)
-    poses = scene.poses(100)
-    model = NGPCompact(scale=0.5).to(dev)
+    wl = WORKLOADS[args.workload]
+    scene = BoxScene(wl["scene"], device=dev)
+    poses = scene.poses(wl["views"])
+    model = NGPCompact(scale=wl["scale"], log2_T=wl["log2_T"]).to(dev)
     model.density_grid.copy_(scene_density_grid(scene))             # converged-occupancy proxy; maintained by update_density_grid afterwards
     vren.packbits(model.density_grid, 0.5, model.density_bitfield)
-    tr = Trainer(model, lr=1e-2, render_kwargs=dict(exp_step_factor=0.0, num_classes=0), world_size=world)
+    rkw = dict(exp_step_factor=wl["esf"], num_classes=0)
+    tr = Trainer(model, lr=wl["lr"], render_kwargs=rkw, world_size=world)
 
     R = R_PER_GPU
     n_batches = 8
@@ -290,15 +300,15 @@ def gpu_arm(args):
     with torch.no_grad():
         ro, rd = scene.sample_rays(1 << 16, poses, gen)
         gt, *_ = scene.shade(ro, rd)
-        out = render(model, ro, rd, exp_step_factor=0.0, num_classes=0)
+        out = render(model, ro, rd, **rkw)
         q = float(psnr(out["rgb"], gt))
         spr = float(out["total_samples"]) / ro.shape[0]
         rays_a, xyzs, dirs = out["rays_a"], out["xyzs"], None
     rend = None
     if not args.no_render:
-        rend = render_bench(model, scene, poses, rank=rank, world=world)
+        rend = render_bench(model, scene, poses, rank=rank, world=world, esf=wl["esf"])
         if args.render_4k:
-            rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world)
+            rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world, esf=wl["esf"])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -310,7 +320,7 @@ def gpu_arm(args):
     with torch.no_grad():
         _, hits_t, _ = vren.ray_aabb_intersect(pool_o[0], pool_d[0], model.center, model.half_size, 1)
         ra, xyzs, dirs, deltas, ts, tot = RayMarcher.apply(pool_o[0], pool_d[0], hits_t[:, 0].contiguous(), model.density_bitfield,
-                                                           model.cascades, model.scale, 0.0, model.grid_size, MAX_SAMPLES)
+                                                           model.cascades, model.scale, wl["esf"], model.grid_size, MAX_SAMPLES)
         kb = kernel_breakdown(model, xyzs, dirs)
     pk, pk_src = peaks()
     kern = {}
@@ -333,17 +343,23 @@ def gpu_arm(args):
             roof["traffic_source"] = tr_["source"]
     except Exception:
         pass
-    roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the 43.6 MB fp32 "
-                    "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 — the kernel is bound by L2 "
-                    "atomic throughput (ncu lts__throughput 77 %, 50 red sectors/sample), see profiles/r01b_ncu_hashgrid_bw_params_kernel.txt")
-
+    table_mb = model.xyz_encoder.params.numel() * 4 / 2 ** 20
+    if table_mb < 100:
+        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the %.0f MB fp32 "
+                        "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 - the kernel is bound by L2 "
+                        "reduction sector requests (~220 G/s, tools/probes/l2_red_probe.cu; ncu lts__throughput 77 %%), see "
+                        "profiles/r01b_ncu_hashgrid_bw_params_kernel.txt" % table_mb)
+    else:
+        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time; the %.0f MB fp32 table exceeds the 126 MB L2, "
+                        "random 8-byte entries of 32-byte sectors: DRAM traffic is up to 4x the algorithmic table bytes" % table_mb)
+        roof["traffic"] = None
     cpu, _ = cpu_arm(steps=4, warmup=1)
     value = world * R * args.steps / t_res
     line = {
         "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32 (bf16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr, "samples_per_ray_timed_steps": {"min": min(spr_timed), "max": max(spr_timed), "mean": sum(spr_timed) / len(spr_timed)},
+        "config": {"workload": wl["name"], "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr, "samples_per_ray_timed_steps": {"min": min(spr_timed), "max": max(spr_timed), "mean": sum(spr_timed) / len(spr_timed)},
                    "pretrain_steps": args.pretrain, "psnr_after_pretrain": q, "l2": "inputs_exceed_l2 (>250 MB of samples per step)",
                    "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of table+MLP gradients" if world > 1 else "single GPU",
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
@@ -363,6 +379,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pretrain", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lego", choices=sorted(WORKLOADS), help="lego = BASELINE.json configs[1] (the headline); street = configs[3] shape")
     ap.add_argument("--no-render", action="store_true", help="skip the test-time render sweep")
     ap.add_argument("--render-4k", action="store_true", help="also render 3840x2160 frames (BASELINE.json configs[4])")
     args = ap.parse_args()
