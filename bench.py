@@ -147,13 +147,13 @@ def kernel_breakdown(model, xyzs, dirs):
     flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
     out["mlp_sigma_fw"] = (time_kernel(lambda: tcnn.mlp_forward([(tiles, LF, 2)], p1, m1, aux_exp=True, n=S)), S * flops(m1, LF), "F")
     dh = torch.randn_like(h); ds = torch.randn(S, device=xw.device)
-    out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(tiles, LF, 2)], p1, m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel())),
+    out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(tiles, LF, 2)], p1, m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel(), saved_out=h)),
                            S * flops(m1, LF) * 3, "F")
     segs = [(dirs, 16, 1), (h, 16, 0)]
     rgb = tcnn.mlp_forward(segs, p2, m2)
     out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, p2, m2)), S * flops(m2, 32), "F")
     drgb = torch.randn_like(rgb)
-    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, p2, m2, drgb, [False, True])), S * flops(m2, 32) * 3, "F")
+    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, p2, m2, drgb, [False, True], saved_out=rgb)), S * flops(m2, 32) * 3, "F")
     return out
 
 

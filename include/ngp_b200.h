@@ -182,7 +182,9 @@ int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, con
 int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out, int act_hidden,
                int act_out, int64_t n, const float* dL_dout, int64_t dout_stride, float* dparams,
-               float* const* dseg_ptr, const int64_t* dseg_stride, const float* dL_daux_exp, void* stream);
+               float* const* dseg_ptr, const int64_t* dseg_stride, const float* dL_daux_exp,
+               const float* saved_out /* optional: forward output, skips the output-layer recompute */,
+               int64_t saved_out_stride, void* stream);
 
 /* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
  * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */

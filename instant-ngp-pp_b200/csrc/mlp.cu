@@ -606,7 +606,8 @@ template <int SLOTS, typename SH>
 __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, SegPtrs in, const float* __restrict__ params, int64_t n,
                                                                       const float* __restrict__ dout, int64_t dout_stride,
                                                                       float* __restrict__ dparams, SegGrads dseg,
-                                                                      const float* __restrict__ d_aux_exp) {
+                                                                      const float* __restrict__ d_aux_exp,
+                                                                      const float* __restrict__ yout, int64_t yout_stride) {
   extern __shared__ __align__(128) uint8_t smem[];
   const Dims d = make_dims<SH>(c);
   const uint32_t tmem = cta_setup(c, d, params, smem);
@@ -621,6 +622,9 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
   _Pragma("unroll") for (int s = 0; s < kMaxSeg; s++) if (s < d.n_seg) want_dx |= dseg.p[s] != nullptr;
   const bool dout_vec = ((dout_stride & 3) == 0) && ((((uintptr_t)dout) & 15) == 0);
   const uint32_t warp = threadIdx.x >> 5, quad = warp & 3u, part = warp >> 2;
+  // The forward's OUTPUT (saved by autograd anyway) replaces the recompute of the output layer: act_o' is a function
+  // of y, and the density head's z0 is y0 when act_o is None — one MMA -> TMEM -> epilogue round trip less per tile.
+  const bool skip_out = yout != nullptr && (d.act_o == kActNone || (d.no <= 4 && d_aux_exp == nullptr));
 
   // zero the CTA-wide weight-gradient accumulators (every slot accumulates into them from its first tile on)
   for (uint32_t c0 = 16 * part; c0 < c.wg_cols; c0 += 16 * SLOTS) tmem_st16_zero(S.twg + ((quad * 32u) << 16) + c0);
@@ -677,6 +681,14 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
       }
     }
     const float daux = (d_aux_exp && valid) ? __ldg(d_aux_exp + row) : 0.f;
+    float yreg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (skip_out && valid) {
+      const float* yr = yout + row * yout_stride;
+      if (d.no <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (i < d.no) yreg[i] = __ldg(yr + i);
+      } else yreg[0] = __ldg(yr);
+    }
     {
       const int64_t nrow = row + tstride * kTile;
       if (nrow < n) {
@@ -694,9 +706,41 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
       __syncwarp();
       wait_mma(S);
       epilogue_hidden<(SLOTS > 4 ? 32 : 64)>(c, d, S, S.base + c.off_h[l]);
+      if (skip_out && l == d.nh - 1) {
+        // dZ_out = dL/dy * act_o'(y) from the saved output, written together with the last hidden tile
+        if (d.no <= 4) {
+          float g[16];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float y = yreg[i];
+            float dy = 1.f;
+            if (d.act_o == kActSigmoid) dy = y * (1.f - y);
+            else if (d.act_o == kActExp) dy = y;
+            else if (d.act_o == kActReLU) dy = y > 0.f ? 1.f : 0.f;
+            g[i] = i < d.no ? dreg[i] * dy : 0.f;
+          }
+          if (d_aux_exp) g[0] = fmaf(daux, __expf(fminf(fmaxf(yreg[0], -7.f), 7.f)), g[0]);
+#pragma unroll
+          for (int i = 4; i < 16; i++) g[i] = 0.f;
+          st_chunk(dZ, kTile, t, 0, g);
+          st_chunk(dZ, kTile, t, 8, g + 8);
+        } else {
+          for (int c0 = 0; c0 < d.nop; c0 += 16) {
+            float g[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) g[i] = c0 == 0 ? dreg[i] : ((valid && c0 + i < d.no) ? __ldg(dout + row * dout_stride + c0 + i) : 0.f);
+            if (c0 == 0 && d_aux_exp) g[0] = fmaf(daux, __expf(fminf(fmaxf(yreg[0], -7.f), 7.f)), g[0]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) if (c0 + i >= d.no) g[i] = 0.f;
+            st_chunk(dZ, kTile, t, c0, g);
+            st_chunk(dZ, kTile, t, c0 + 8, g + 8);
+          }
+        }
+      }
       publish(S);
     }
     // ---- output layer pre-activation -> dZ_out = dL/dy * act_o'(z)
+    if (!skip_out) {
     if (t == 0) {
       fence_after_sync();
       issue_fwd(S.tacc, S.sbase + c.off_h[d.nh - 1], wbase + c.off_w[d.nh], (uint32_t)d.nop, d.nop, d.wp);
@@ -743,6 +787,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
       st_chunk(dZ, kTile, t, c0 + 8, v + 8);
     }
     publish(S);
+    }
     // ---- top-down: wgrad + dgrad per layer.  dZ_out lives in its own (narrow) tile; every hidden dZ_l is
     // written IN PLACE over H_{l} (the thread that reads a 16-byte chunk for the activation mask is the one
     // that overwrites it), so no wp-wide gradient tile is needed.
@@ -1069,12 +1114,13 @@ NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_wi
 
 // dparams (+=, fp32 atomics; caller zeroes) and optional per-segment input gradients
 // dseg_ptr[s] (N, seg_width[s]) with row stride dseg_stride[s] (NULL = not needed; SH segments
-// never receive one).  dL_dout is (N, n_out) with row stride dout_stride.
+// never receive one).  dL_dout is (N, n_out) with row stride dout_stride.  saved_out (optional): the forward's
+// output (N, n_out), row stride saved_out_stride — lets the kernel skip recomputing the output layer.
 NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                        const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
                        int act_hidden, int act_out, int64_t n, const float* dL_dout, int64_t dout_stride,
                        float* dparams, float* const* dseg_ptr, const int64_t* dseg_stride, const float* dL_daux_exp,
-                       void* stream) {
+                       const float* saved_out, int64_t saved_out_stride, void* stream) {
   if (n <= 0) return 0;
   MlpCfg c;
   const int rc = build_cfg(c, n_seg, seg_ptr, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, true);
@@ -1090,7 +1136,7 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   dg.tiles = (n_seg == 1 && seg_kind[0] == kSegTiles) ? 1 : 0;
   bool launched = false;
   const int shape = match_shape(c);
-#define BW_ARGS c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp
+#define BW_ARGS c, in, params, n, dL_dout, dout_stride, dparams, dg, dL_daux_exp, saved_out, saved_out_stride
 #define BW_STATIC(SH_) switch (c.slots) {                \
     NGP_MLP_DISPATCH(2, mlp_bw_kernel, SH_, BW_ARGS)     \
     NGP_MLP_DISPATCH(3, mlp_bw_kernel, SH_, BW_ARGS)     \

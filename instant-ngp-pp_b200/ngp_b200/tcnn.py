@@ -222,7 +222,7 @@ def mlp_forward(segs, params, m: MlpConfig, aux_exp=False, n=None):
     return (out, aux) if aux_exp else out
 
 
-def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None, n=None, dseg_numel=None):
+def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None, n=None, dseg_numel=None, saved_out=None):
     n = segs[0][0].shape[0] if n is None else n
     dparams = torch.zeros_like(params)
     P, W, K, S = _seg_arrays(segs)
@@ -235,6 +235,7 @@ def mlp_backward(segs, params, m: MlpConfig, dout, need_dseg, d_aux=None, n=None
     dout = dout.contiguous()
     check(lib.ngp_mlp_bw(k, P, W, K, S, ptr(params), m.width, m.n_hidden, m.n_out, m.act_h, m.act_o, n, ptr(dout),
                          dout.stride(0), ptr(dparams), DP, DS, ptr(d_aux.contiguous()) if d_aux is not None else None,
+                         ptr(saved_out) if saved_out is not None else None, saved_out.stride(0) if saved_out is not None else 0,
                          stream()), "mlp_bw")
     return dparams, dsegs
 
@@ -248,17 +249,18 @@ class _MlpFn(torch.autograd.Function):
         tensors = tuple(t.contiguous() for t in tensors)
         segs = [(t.detach(), (16 if kd == 1 else t.shape[1]), kd) for t, kd in zip(tensors, kinds)]
         ctx.m, ctx.kinds = m, kinds
-        ctx.save_for_backward(params, *tensors)
-        return mlp_forward(segs, params.detach(), m)
+        out = mlp_forward(segs, params.detach(), m)
+        ctx.save_for_backward(params, out, *tensors)        # the output lets the backward skip the output-layer recompute
+        return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
-        params, *tensors = ctx.saved_tensors
+        params, out, *tensors = ctx.saved_tensors
         m, kinds = ctx.m, ctx.kinds
         segs = [(t, (16 if kd == 1 else t.shape[1]), kd) for t, kd in zip(tensors, kinds)]
         need = [ctx.needs_input_grad[3 + i] for i in range(len(tensors))]
-        dparams, dsegs = mlp_backward(segs, params, m, dout, need)
+        dparams, dsegs = mlp_backward(segs, params, m, dout, need, saved_out=out)
         return (dparams if ctx.needs_input_grad[0] else None, None, None, *dsegs)
 
 
@@ -271,15 +273,15 @@ class _MlpDensityHeadFn(torch.autograd.Function):
         _lib.require_device()
         x = x.contiguous()
         ctx.m = m
-        ctx.save_for_backward(params, x)
         h, sigma = mlp_forward([(x.detach(), x.shape[1], 0)], params.detach(), m, aux_exp=True)
+        ctx.save_for_backward(params, x, h)
         return h, sigma
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dh, dsigma):
-        params, x = ctx.saved_tensors
-        dparams, dsegs = mlp_backward([(x, x.shape[1], 0)], params, ctx.m, dh, [ctx.needs_input_grad[2]], d_aux=dsigma)
+        params, x, h = ctx.saved_tensors
+        dparams, dsegs = mlp_backward([(x, x.shape[1], 0)], params, ctx.m, dh, [ctx.needs_input_grad[2]], d_aux=dsigma, saved_out=h)
         return (dparams if ctx.needs_input_grad[0] else None), None, dsegs[0]
 
 
@@ -307,20 +309,20 @@ class _DensityFieldFn(torch.autograd.Function):
         n = x.shape[0]
         tiles = grid_forward_tiles(x.detach(), table.detach(), g, aabb)
         ctx.g, ctx.m, ctx.aabb = g, m, aabb
-        ctx.save_for_backward(x, table, params, tiles)
         h, sigma = mlp_forward([(tiles, g.n_levels * g.n_features, 2)], params.detach(), m, aux_exp=True, n=n)
+        ctx.save_for_backward(x, table, params, tiles, h)
         return h, sigma
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dh, dsigma):
-        x, table, params, tiles = ctx.saved_tensors
+        x, table, params, tiles, h = ctx.saved_tensors
         g, m = ctx.g, ctx.m
         n = x.shape[0]
         k0p = (g.n_levels * g.n_features + 15) // 16 * 16
         need_table = ctx.needs_input_grad[1]
         dparams, dsegs = mlp_backward([(tiles, g.n_levels * g.n_features, 2)], params, m, dh, [need_table], d_aux=dsigma, n=n,
-                                      dseg_numel=(n + 127) // 128 * 128 * k0p)
+                                      dseg_numel=(n + 127) // 128 * 128 * k0p, saved_out=h)
         dtable = None
         if need_table:
             dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device)

@@ -268,3 +268,25 @@ def test_fused_density_field_matches_unfused_path(n):
     (h0, s0, dt0, dp0), (h1, s1, dt1, dp1) = outs
     assert torch.equal(h0, h1) and torch.equal(s0, s1)
     assert rel(dp1, dp0) < 1e-5 and rel(dt1, dt0) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(32, 64, 2, 3, "Sigmoid"), (32, 64, 1, 16, "None"), (144, 128, 1, 3, "Sigmoid"), (128, 32, 1, 7, "None")])
+def test_mlp_backward_from_saved_output_equals_recompute(shape):
+    """ngp_mlp_bw(saved_out=forward output) skips the output-layer recompute; the gradients must not change."""
+    from ngp_b200 import tcnn
+    n_in, width, nh, n_out, oact = shape
+    net = tcnn.Network(n_in, n_out, {"otype": "CutlassMLP", "activation": "ReLU", "output_activation": oact,
+                                     "n_neurons": width, "n_hidden_layers": nh}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 128 * 9 + 77
+    x = torch.randn(n, n_in, device="cuda", generator=g)
+    dy = torch.randn(n, n_out, device="cuda", generator=g)
+    p = net.params.detach()
+    aux = oact == "None"
+    out = tcnn.mlp_forward([(x, n_in, 0)], p, net.mlp, aux_exp=aux)
+    y = out[0] if aux else out
+    da = torch.randn(n, device="cuda", generator=g) if aux else None
+    dp0, dx0 = tcnn.mlp_backward([(x, n_in, 0)], p, net.mlp, dy, [True], d_aux=da)
+    dp1, dx1 = tcnn.mlp_backward([(x, n_in, 0)], p, net.mlp, dy, [True], d_aux=da, saved_out=y)
+    assert torch.equal(dx0[0], dx1[0])
+    assert rel(dp1, dp0) < 1e-5

@@ -37,13 +37,13 @@ with torch.no_grad():
         h, sig = tcnn.mlp_forward([(tiles, 32, 2)], model.sigma_net.params.detach(), m1, aux_exp=True, n=S)
     dh = torch.randn_like(h); ds = torch.randn_like(sig)
     for _ in range(2):
-        tcnn.mlp_backward([(tiles, 32, 2)], model.sigma_net.params.detach(), m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel())
+        tcnn.mlp_backward([(tiles, 32, 2)], model.sigma_net.params.detach(), m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel(), saved_out=h)
     segs = [(dirs, 16, 1), (h, 16, 0)]
     for _ in range(2):
         rgb = tcnn.mlp_forward(segs, model.rgb_net.params.detach(), m2)
     drgb = torch.randn_like(rgb)
     for _ in range(2):
-        tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True])
+        tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True], saved_out=rgb)
     sigmas = torch.rand(S, device=dev) * 20
     for _ in range(2):
         out = vren.composite_train_fw(sigmas, rgb, rgb, torch.zeros(S, 0, device=dev), deltas, ts, ra, 1e-4, 0)
