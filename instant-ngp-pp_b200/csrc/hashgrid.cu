@@ -17,6 +17,7 @@
 // 43 MB fp32 table of the L16/F2/T2^19 shape fits the 126 MB L2 outright).  Gradients are
 // scattered with vector reductions (red.global.add.v2/v4.f32).
 #include "common.cuh"
+#include <math.h>
 #include <stdlib.h>
 
 namespace ngp {
@@ -33,12 +34,16 @@ struct GridMeta {
   uint8_t dense[kMaxLevels];
   // optional world -> unit-cube map fused into every kernel: x01 = (x - lo) / range with IEEE sub and div, i.e.
   // bit-identical to the (x - xyz_min) / (xyz_max - xyz_min) tensor pass of models/networks.py:174,188
-  int affine;
-  float lo[3], range[3];
+  int affine;              // 0 none, 1 (x - lo) / range, 2 (x - lo) * (1/range) with power-of-two ranges (exact)
+  float lo[3], range[3], inv_range[3];
   int k0p;                 // L*F rounded up to 16: operand-tile width of the feature-tile / gradient-tile layouts
 };
 __device__ __forceinline__ void to_unit(const GridMeta& m, float& x, float& y, float& z) {
-  if (m.affine) {
+  if (m.affine == 2) {            // every range is a power of two: the multiplication by 1/range is exact, same bits as the division
+    x = __fmul_rn(__fsub_rn(x, m.lo[0]), m.inv_range[0]);
+    y = __fmul_rn(__fsub_rn(y, m.lo[1]), m.inv_range[1]);
+    z = __fmul_rn(__fsub_rn(z, m.lo[2]), m.inv_range[2]);
+  } else if (m.affine) {
     x = __fdiv_rn(__fsub_rn(x, m.lo[0]), m.range[0]);
     y = __fdiv_rn(__fsub_rn(y, m.lo[1]), m.range[1]);
     z = __fdiv_rn(__fsub_rn(z, m.lo[2]), m.range[2]);
@@ -54,6 +59,31 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
   }
   const uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
   return (size & (size - 1)) == 0 ? (h & (size - 1)) : (h % size);
+}
+
+// The four (y, z) corners of x-neighbour xh of a cell, with the level's addressing mode decided ONCE (the per-corner
+// form above re-tests dense / power-of-two for every corner: index arithmetic was most of the gather's instructions
+// once the lane-pair layout had lifted the L1 bound, ncu r01c: issue slots 89 % busy).  Same values as grid_index.
+__device__ __forceinline__ void corner4(uint32_t x, uint32_t py, uint32_t pz, uint32_t res, uint32_t size, bool dense,
+                                        uint32_t* idx) {
+  if (dense) {
+    const uint32_t r2 = res * res;
+    const uint32_t b = x + py * res + pz * r2;
+    idx[0] = b; idx[1] = b + res; idx[2] = b + r2; idx[3] = b + res + r2;
+#pragma unroll
+    for (int p = 0; p < 4; p++) if (idx[p] >= size) idx[p] -= size;   // == % size for the reachable range
+  } else {
+    const uint32_t hy0 = py * 2654435761u, hy1 = hy0 + 2654435761u;
+    const uint32_t hz0 = pz * 805459861u, hz1 = hz0 + 805459861u;
+    idx[0] = x ^ hy0 ^ hz0; idx[1] = x ^ hy1 ^ hz0; idx[2] = x ^ hy0 ^ hz1; idx[3] = x ^ hy1 ^ hz1;
+    if ((size & (size - 1)) == 0) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) idx[p] &= size - 1;
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; p++) idx[p] %= size;
+    }
+  }
 }
 
 template <int F, typename TP> struct Vec;
@@ -139,11 +169,10 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
       const bool dense = m.dense[l];
       const float wxs = xh ? c.wx : 1.f - c.wx;
       float v[4][F];
+      uint32_t idx[4];
+      corner4(c.px + xh, c.py, c.pz, res, size, dense, idx);
 #pragma unroll
-      for (int p = 0; p < 4; p++) {
-        const uint32_t idx = grid_index(c.px + xh, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-        Vec<F, TP>::ld(base + (size_t)idx * F, v[p]);
-      }
+      for (int p = 0; p < 4; p++) Vec<F, TP>::ld(base + (size_t)idx[p] * F, v[p]);
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         const float w = wxs * ((p & 1) ? c.wy : 1.f - c.wy) * (((p >> 1) & 1) ? c.wz : 1.f - c.wz);
@@ -209,11 +238,10 @@ template <int F> struct CellAcc {
 
 template <int F>
 __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, uint32_t xh, float* __restrict__ base, uint32_t res, uint32_t size, bool dense) {
+  uint32_t idx[4];
+  corner4(c.px + xh, c.py, c.pz, res, size, dense, idx);
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    const uint32_t idx = grid_index(c.px + xh, c.py + (p & 1), c.pz + ((p >> 1) & 1), res, size, dense);
-    red_add<F>(base + (size_t)idx * F, c.a[p]);
-  }
+  for (int p = 0; p < 4; p++) red_add<F>(base + (size_t)idx[p] * F, c.a[p]);
 }
 
 // DYT: dL/dy arrives in "gradient tiles" (written by the MLP backward, mlp.cu): fp32, per 128-sample tile
@@ -389,7 +417,14 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
   m.n_levels = n_levels; m.n_features = F;
   m.k0p = (n_levels * F + 15) / 16 * 16;
   m.affine = aabb != nullptr;
-  for (int d = 0; d < 3; d++) { m.lo[d] = aabb ? aabb[d] : 0.f; m.range[d] = aabb ? aabb[3 + d] : 1.f; }
+  bool pow2 = aabb != nullptr;
+  for (int d = 0; d < 3; d++) {
+    m.lo[d] = aabb ? aabb[d] : 0.f; m.range[d] = aabb ? aabb[3 + d] : 1.f;
+    int e; const float fr = frexpf(m.range[d], &e);
+    pow2 = pow2 && fr == 0.5f && e > -100 && e < 100;      // normal power of two: x * (1/range) == x / range bit for bit
+    m.inv_range[d] = 1.0f / m.range[d];
+  }
+  if (pow2) m.affine = 2;
   const float log2_pls = log2f(per_level_scale);
   uint32_t off = 0;
   for (int l = 0; l < n_levels; l++) {

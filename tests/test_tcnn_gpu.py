@@ -216,7 +216,8 @@ def test_mlp_density_head_fused_exp():
     assert rel(gx, gxo) < 1.5e-2 and rel(gp, gpo) < 1.5e-2, (rel(gx, gxo), rel(gp, gpo))
 
 
-def test_hashgrid_fused_aabb_is_bit_identical_to_normalising_first():
+@pytest.mark.parametrize("half", [8.0, 1.5])          # range 16 (power of two: exact reciprocal path) and 3 (IEEE division path)
+def test_hashgrid_fused_aabb_is_bit_identical_to_normalising_first(half):
     """The (x - xyz_min) / (xyz_max - xyz_min) pass of models/networks.py:174 fused into the grid kernels: IEEE sub + div
     in the kernel give the same bits as the two tensor ops, for the forward, both first-order gradients and the
     double backward."""
@@ -224,8 +225,8 @@ def test_hashgrid_fused_aabb_is_bit_identical_to_normalising_first():
     enc, _ = _grid(16, 2, 19, 16, 8.0)
     g = torch.Generator(device="cuda").manual_seed(3)
     n = 20011
-    lo = torch.tensor([-8.0, -8.0, -8.0], device="cuda"); rng = torch.tensor([16.0, 16.0, 16.0], device="cuda")
-    xw = (torch.rand(n, 3, device="cuda", generator=g) * 2 - 1) * 8.0
+    lo = torch.full((3,), -half, device="cuda"); rng = torch.full((3,), 2 * half, device="cuda")
+    xw = (torch.rand(n, 3, device="cuda", generator=g) * 2 - 1) * half
     xn = ((xw - lo) / rng).contiguous()
     aabb = tuple(lo.tolist()) + tuple(rng.tolist())
     table = enc.params.detach()
