@@ -275,9 +275,13 @@ def gpu_arm(args):
 
     def timed(fn, steps):
         sampler = ClockSampler(local)
-        barrier()
         if rank == 0:
             sampler.start()
+        # nvidia-smi's start-up (NVML init, device enumeration) stalls kernel launches for tens of ms on a fresh box:
+        # let it finish under load BEFORE the timed region (3 more untimed steps), then sample through the region
+        for i in range(3):
+            fn(i)
+        barrier()
         calls0 = _lib.lib_calls() if hasattr(_lib, "lib_calls") else 0
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()

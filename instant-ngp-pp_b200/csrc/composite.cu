@@ -12,6 +12,7 @@
 // per-ray accumulators live in registers and are written once.  Every output element is written
 // by the kernel (zeros after early termination), so no host-side fill is needed.
 #include "scan.cuh"
+#include <stdlib.h>
 
 namespace ngp {
 
@@ -249,10 +250,13 @@ __global__ void __launch_bounds__(256) composite_test_fw_kernel(
 
 // lanes per ray from the mean segment length (host-known: N / N_rays)
 int pick_group(int64_t n_samples, int64_t n_rays) {
+  if (const char* e = getenv("NGP_COMPOSITE_G")) { const int g = atoi(e); if (g == 4 || g == 8 || g == 16 || g == 32) return g; }   // tuning only
+  // The mean is over ALL rays, and most rays of a batch are empty (Lego-shaped scene: 77 % of 2^18 random rays carry no
+  // sample, the others 127 on average: tools/composite_sweep.py) — so the thresholds sit well below the group size.
   const double avg = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
-  if (avg > 40.0) return 32;
-  if (avg > 16.0) return 16;
-  if (avg > 5.0) return 8;
+  if (avg > 12.0) return 32;
+  if (avg > 6.0) return 16;
+  if (avg > 2.5) return 8;
   return 4;
 }
 
