@@ -277,10 +277,17 @@ def gpu_arm(args):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        # nvidia-smi's start-up (NVML init, device enumeration) stalls kernel launches for tens of ms on a fresh box:
-        # let it finish under load BEFORE the timed region (3 more untimed steps), then sample through the region
-        for i in range(3):
-            fn(i)
+        # nvidia-smi's start-up (NVML init, device enumeration) stalls kernel launches for ~100 ms on a fresh box:
+        # keep stepping (untimed) until its first samples have arrived, THEN time; it keeps sampling through the region
+        t_wait, k = time.time(), 0
+        while True:
+            fn(k); k += 1
+            torch.cuda.synchronize()
+            ready = torch.tensor([1 if (rank != 0 or len(sampler.lines) >= 2 or time.time() - t_wait > 8.0) else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(ready, op=dist.ReduceOp.MIN)
+            if int(ready):
+                break
         barrier()
         calls0 = _lib.lib_calls() if hasattr(_lib, "lib_calls") else 0
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
