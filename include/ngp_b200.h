@@ -53,6 +53,7 @@ int ngp_packbits_dthr(const float* density_grid, int64_t n_bytes, const float* d
  *   write : rays_a (R,3) i64 [ray_idx,start_idx,N] in ray-index order, xyzs/dirs (S,3), deltas/ts (S)
  * workspace: ngp_raymarching_train_workspace_bytes(n_rays) bytes of device memory shared by both. */
 int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays);
+int64_t ngp_render_workspace_bytes(int64_t n_slots);   /* workspace of ngp_render_advance / ngp_render_emit */
 int ngp_raymarching_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
                                 const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
                                 const float* noise, int grid_size, int max_samples, int64_t n_rays, int32_t* counter,

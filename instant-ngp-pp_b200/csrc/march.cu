@@ -22,7 +22,11 @@
 namespace ngp {
 
 constexpr int kMarchBlock = 256;
-constexpr int kScratch = 256;    // samples per ray recorded by pass 1 (8 B each; only touched rows cost bandwidth)
+constexpr int kScratch = 256;    // test-time wavefront: samples per slot and round recorded in the scratch row (n_next <= 256)
+constexpr int kTrainRow = 1024;  // training: scratch row = max_samples (models/rendering.py:9) entries of 8 B, so pass 2 never
+                                 // re-marches (a 256-entry row left the tails of the longest rays — 407 samples in the Lego-shaped
+                                 // scene, most rays of the street-shaped one — to ONE serial thread each: the emit kernel's critical
+                                 // path).  2 GiB of address space at 2^18 rays; only touched entries cost bandwidth.
 
 struct MarchParams {
   float dt0, mb0, mb0_inv;   // kSimple constants: dt = clamp(0, dt_min, dt_max), mip_bound = min(0.5, scale), 1/mip_bound
@@ -117,7 +121,7 @@ template <bool kSimple>
 __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
     const float* __restrict__ noise, MarchParams p, int max_samples, int64_t n_rays,
-    int32_t* __restrict__ n_samples, float2* __restrict__ scratch, int* __restrict__ next_ray) {
+    int32_t* __restrict__ n_samples, float2* __restrict__ scratch, int row_len, int* __restrict__ next_ray) {
   const unsigned lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;     // exhausted: the counter has run past n_rays, stop asking
   int64_t r = 0;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
           float t1 = __ldg(hits_t + 2 * r);
           t2 = __ldg(hits_t + 2 * r + 1);
           if (t1 >= 0) t1 = __fmaf_rn(kSimple ? p.dt0 : calc_dt(t1, p.dt), __ldg(noise + r), t1);  // raymarching.cu:195-198
-          t = t1; N = 0; row = scratch + r * kScratch;
+          t = t1; N = 0; row = scratch + r * (int64_t)row_len;
         }
       }
     }
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     if (have) {
       if (0 <= t && t < t2 && N < max_samples) {
         if (march_step<kSimple>(q, p, t, x, y, z, dt)) {
-          if (N < kScratch) row[N] = make_float2(t, dt);
+          if (N < row_len) row[N] = make_float2(t, dt);
           t = __fadd_rn(t, dt); N++;
         }
       } else {
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     MarchParams p, int64_t n_rays, const int32_t* __restrict__ n_samples,
     const int64_t* __restrict__ block_offsets, const float2* __restrict__ scratch, int64_t capacity,
     int64_t* __restrict__ rays_a, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-    float* __restrict__ ts, const int64_t* __restrict__ slot_to_ray) {
+    float* __restrict__ ts, const int64_t* __restrict__ slot_to_ray, int row_len) {
   // slot_to_ray (optional): position i of n_samples / scratch / rays_a belongs to ray slot_to_ray[i]
   // (test-time wavefront: slots are the currently alive rays); NULL = identity (training).
   __shared__ int s_start[kMarchBlock + 1];       // block-local exclusive prefix of the sample counts
@@ -248,12 +252,12 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     for (int it = 0; it < 8; it++) { const int m = (a + b) >> 1; if (s_start[m] <= lo) a = m; else b = m; }
     const int s = lo - s_start[a];
     const int64_t o = boff + lo;
-    if (s >= kScratch || o >= capacity) continue;   // the tail of a long ray is re-marched below
+    if (s >= row_len || o >= capacity) continue;    // beyond the scratch row (max_samples > row length only): re-marched below
     const int64_t r = r0 + a;
     const int64_t ray = slot_to_ray ? slot_to_ray[r] : r;
     const float ox = __ldg(rays_o + 3 * ray), oy = __ldg(rays_o + 3 * ray + 1), oz = __ldg(rays_o + 3 * ray + 2);
     const float dx = __ldg(rays_d + 3 * ray), dy = __ldg(rays_d + 3 * ray + 1), dz = __ldg(rays_d + 3 * ray + 2);
-    const float2 td = scratch[r * kScratch + s];
+    const float2 td = scratch[r * (int64_t)row_len + s];
     xyzs[3 * o] = __fmaf_rn(td.x, dx, ox); xyzs[3 * o + 1] = __fmaf_rn(td.x, dy, oy); xyzs[3 * o + 2] = __fmaf_rn(td.x, dz, oz);
     dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
     ts[o] = td.x; deltas[o] = td.y;
@@ -263,14 +267,14 @@ __global__ void __launch_bounds__(kMarchBlock) march_emit_kernel(
     // recorded sample
     const int64_t r = r0 + threadIdx.x;
     const int N = r < n_rays ? n_samples[r] : 0;
-    if (N > kScratch) {
+    if (N > row_len) {
       const int64_t ray = slot_to_ray ? slot_to_ray[r] : r;
       const int64_t start = boff + s_start[threadIdx.x];
       const Ray q = load_ray(rays_o, rays_d, ray);
       const float t2 = __ldg(hits_t + 2 * ray + 1);
-      const float2 last = scratch[r * kScratch + kScratch - 1];
+      const float2 last = scratch[r * (int64_t)row_len + row_len - 1];
       float t = __fadd_rn(last.x, last.y), x, y, z, dt;
-      int s = kScratch;
+      int s = row_len;
       while (t < t2 && s < N) {
         if (march_step(q, p, t, x, y, z, dt)) {
           const int64_t o = start + s;
@@ -417,12 +421,15 @@ using namespace ngp;
 
 // Workspace layout for the training marcher (caller-provided device memory):
 //   int32 n_samples[R] | float t_start[R] | int32 block_sums[B] | int64 block_offsets[B] | int64 total |
-//   float2 scratch[R][kScratch]
-NGP_API int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays) {
+//   float2 scratch[R][row]      row = kTrainRow (training) / kScratch (test-time wavefront)
+static int64_t march_ws_bytes(int64_t n_rays, int row) {
   const int64_t B = ceil_div(n_rays, kMarchBlock);
   auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
-  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256 + al(n_rays * kScratch * 8);
+  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256 + al(n_rays * row * 8);
 }
+NGP_API int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays) { return march_ws_bytes(n_rays, kTrainRow); }
+// workspace of ngp_render_advance / ngp_render_emit for n_alive_in slots
+NGP_API int64_t ngp_render_workspace_bytes(int64_t n_slots) { return march_ws_bytes(n_slots, kScratch); }
 
 struct MarchWs { int32_t* n_samples; float* t_start; int32_t* block_sums; int64_t* block_offsets; int64_t* total; float2* scratch; };
 static MarchWs carve(void* ws, int64_t n_rays) {
@@ -458,8 +465,9 @@ NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d
   static const int ctas_per_sm = getenv("NGP_MARCH_CTAS_PER_SM") ? atoi(getenv("NGP_MARCH_CTAS_PER_SM")) : 4;   // swept 1..6 on B200 (r01 call 19): 4 is the minimum
   const int64_t gmax = (int64_t)kSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
   const int G = (int)(ceil_div(n_rays, kMarchBlock) < gmax ? ceil_div(n_rays, kMarchBlock) : gmax);
-  if (simple) march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, next_ray);
-  else march_count_kernel<false><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, next_ray);
+  const int row_len = max_samples < kTrainRow ? (max_samples < 1 ? 1 : max_samples) : kTrainRow;
+  if (simple) march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray);
+  else march_count_kernel<false><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/count");
   block_sums_kernel<<<B, kMarchBlock, 0, s>>>(w.n_samples, n_rays, w.block_sums);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/sums");
@@ -479,9 +487,10 @@ NGP_API int ngp_raymarching_train_write(const float* rays_o, const float* rays_d
   const MarchWs w = carve((void*)workspace, n_rays);
   const MarchParams p = make_params(density_bitfield, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
   const int B = (int)ceil_div(n_rays, kMarchBlock);
+  const int row_len = max_samples < kTrainRow ? (max_samples < 1 ? 1 : max_samples) : kTrainRow;
   march_emit_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, p, n_rays, w.n_samples,
                                                                  w.block_offsets, w.scratch, capacity,
-                                                                 rays_a, xyzs, dirs, deltas, ts, nullptr);
+                                                                 rays_a, xyzs, dirs, deltas, ts, nullptr, row_len);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_write");
   return 0;
 }
@@ -506,7 +515,7 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
 // round's packed samples of every alive ray (prev_rays_a (n_alive_in,3) = [ray, start, N] per slot, NULL in
 // round 0), appends survivors to alive_out (counters[0] = their number) and marches their next <= n_next
 // samples into the workspace; ngp_render_emit then packs them.  n_next = 0 -> composite only (last round).
-// n_next must be <= 256.  workspace: ngp_raymarching_train_workspace_bytes(n_alive_in).
+// n_next must be <= 256.  workspace: ngp_render_workspace_bytes(n_alive_in).
 NGP_API int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
                                int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
                                const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
@@ -546,7 +555,7 @@ NGP_API int ngp_render_emit(const float* rays_o, const float* rays_d, const floa
   block_scan_kernel<<<1, 1024, 0, s>>>(w.block_sums, B, w.block_offsets, nullptr, n_slots, w.total);
   NGP_LAUNCH_CHECK("ngp_render_emit/scan");
   march_emit_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, p, n_slots, w.n_samples, w.block_offsets, w.scratch,
-                                             capacity, rays_a, xyzs, dirs, deltas, ts, alive_out);
+                                             capacity, rays_a, xyzs, dirs, deltas, ts, alive_out, kScratch);
   NGP_LAUNCH_CHECK("ngp_render_emit/emit");
   cudaMemcpyAsync(counters + 1, w.total, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);   // low word of the int64 total
   return 0;

@@ -127,7 +127,7 @@ def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwarg
     while n_alive > 0:
         n_next = min(4 << rnd, 128, max_samples - samples) if samples < max_samples else 0
         rnd += 1; samples += n_next
-        ws = torch.empty(int(lib.ngp_raymarching_train_workspace_bytes(n_alive)), dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(lib.ngp_render_workspace_bytes(n_alive)), dtype=torch.uint8, device=dev)
         alive_out = torch.empty(n_alive, dtype=torch.int64, device=dev)
         pr = prev if prev is not None else (None,) * 5
         check(lib.ngp_render_advance(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(pr[0]), ptr(pr[1]),
