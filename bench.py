@@ -352,14 +352,20 @@ def gpu_arm(args):
         if tr_["kernel"] == dom:
             roof["traffic"] = tr_["dram_bytes_per_sample"] * int(xyzs.shape[0])
             roof["traffic_source"] = tr_["source"]
+            if "red_sectors_per_sample" in tr_:      # what actually bounds the kernel: L2 reduction requests per second
+                rate = tr_["red_sectors_per_sample"] * int(xyzs.shape[0]) / sec / 1e9
+                roof["limiter"] = {"resource": "L2 reduction sector requests", "achieved_G_per_s": rate,
+                                   "peak_G_per_s": tr_.get("red_peak_G_per_s", 220.0), "frac": rate / tr_.get("red_peak_G_per_s", 220.0),
+                                   "peak_source": "tools/probes/l2_red_probe.cu on B200 (random sectors of a 43 MB L2-resident table)",
+                                   "sectors_per_sample": tr_["red_sectors_per_sample"]}
     except Exception:
         pass
     table_mb = model.xyz_encoder.params.numel() * 4 / 2 ** 20
     if table_mb < 100:
         roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the %.0f MB fp32 "
                         "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 - the kernel is bound by L2 "
-                        "reduction sector requests (~220 G/s, tools/probes/l2_red_probe.cu; ncu lts__throughput 77 %%), see "
-                        "profiles/r01b_ncu_hashgrid_bw_params_kernel.txt" % table_mb)
+                        "reduction sector requests (~220 G/s, tools/probes/l2_red_probe.cu; ncu lts__throughput 80 %%), see "
+                        "profiles/r01d_ncu_hashgrid_bw_params_kernel.txt" % table_mb)
     else:
         roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time; the %.0f MB fp32 table exceeds the 126 MB L2, "
                         "random 8-byte entries of 32-byte sectors: DRAM traffic is up to 4x the algorithmic table bytes" % table_mb)
