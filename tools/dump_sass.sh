@@ -1,23 +1,22 @@
 #!/bin/bash
 # Regenerates profiles/sass/*.sass (cuobjdump -sass of the hot kernels in libngp_b200.so) — the instantiations the
-# headline step launches: density net fw<5 slots>/bw<4>, colour net fw<8>/bw<4>, hash grid F=2 fp32, marcher, compositors.
+# headline step launches: density net (feature tiles) fw<6 slots>/bw<5>, colour net fw<8>/bw<4>, hash grid F=2 fp32, marcher, compositors.
 set -e
 cd "$(dirname "$0")/../profiles/sass"
 SO="../../instant-ngp-pp_b200/libngp_b200.so"
 cuobjdump -sass $SO | grep "Function :" | sed 's/.*Function : //' > /tmp/fn_list.txt
-rm -f mlp_fw_kernel.sass mlp_bw_kernel.sass
+rm -f mlp_*.sass hashgrid_*.sass
 dump() {  # pattern outname
   fn=$(grep -E "$1" /tmp/fn_list.txt | head -1)
   [ -z "$fn" ] && { echo "no function matches $1"; return; }
   cuobjdump -sass -fun "$fn" $SO 2>/dev/null | sed 's#/\*[0-9a-f]\{4\}\*/##; s#/\* 0x[0-9a-f]* \*/##' | grep -v "^\s*$" > "$2.sass"
 }
-dump 'mlp_fw_kernelILi5ENS_11StaticShapeILi1E' mlp_fw_sigma_slots5
+dump 'mlp_fw_kernelILi6ENS_11StaticShapeILi1ELi2E' mlp_fw_sigma_tiles_slots6
 dump 'mlp_fw_kernelILi8ENS_11StaticShapeILi2E' mlp_fw_rgb_slots8
-dump 'mlp_bw_kernelILi4ENS_11StaticShapeILi1E' mlp_bw_sigma_slots4
+dump 'mlp_bw_kernelILi5ENS_11StaticShapeILi1ELi2E' mlp_bw_sigma_tiles_slots5
 dump 'mlp_bw_kernelILi4ENS_11StaticShapeILi2E' mlp_bw_rgb_slots4
-dump 'hashgrid_fw_kernelILi2EfE' hashgrid_fw_kernelILi2EfE
-dump 'hashgrid_bw_params_kernelILi2ELi4E' hashgrid_bw_params_kernelILi2ELi4E
-rm -f hashgrid_bw_params_kernelILi2E.sass
+dump 'hashgrid_fw_kernelILi2EfLb1E' hashgrid_fw_tiles_F2
+dump 'hashgrid_bw_params_kernelILi2ELi2ELb1E' hashgrid_bw_params_tiles_F2
 dump 'march_count_kernelILb1E' march_count_kernelILb1E
 dump 'composite_train_fw_kernelILi16E' composite_train_fw_kernelILi16E
 dump 'composite_train_bw_kernelILi16E' composite_train_bw_kernelILi16E
