@@ -18,6 +18,6 @@ dump 'mlp_bw_kernelILi4ENS_11StaticShapeILi2E' mlp_bw_rgb_slots4
 dump 'hashgrid_fw_kernelILi2EfLb1E' hashgrid_fw_tiles_F2
 dump 'hashgrid_bw_params_kernelILi2ELi2ELb1E' hashgrid_bw_params_tiles_F2
 dump 'march_count_kernelILb1E' march_count_kernelILb1E
-dump 'composite_train_fw_kernelILi16E' composite_train_fw_kernelILi16E
-dump 'composite_train_bw_kernelILi16E' composite_train_bw_kernelILi16E
+dump 'composite_train_fw_kernelILi32E' composite_train_fw_kernelILi32E
+dump 'composite_train_bw_kernelILi32E' composite_train_bw_kernelILi32E
 grep -c "UTCHMMA" mlp_*.sass; grep -c "UBLKCP" mlp_*.sass; grep -c "LDTM\|STTM" mlp_*.sass
