@@ -37,7 +37,19 @@ struct GridMeta {
   int affine;              // 0 none, 1 (x - lo) / range, 2 (x - lo) * (1/range) with power-of-two ranges (exact)
   float lo[3], range[3], inv_range[3];
   int k0p;                 // L*F rounded up to 16: operand-tile width of the feature-tile / gradient-tile layouts
+  // Block order (block_coords below).  0 = level chunk FASTEST: the n_chunks CTAs that touch the same rows of x / y run
+  // back to back, so the rows are served from L2 instead of being swept from HBM once per chunk — right while the whole
+  // table is L2 resident (44 MB at T=2^19 F=2).  1 = level chunk SLOWEST: all sample blocks of chunk 0, then chunk 1, ...
+  // so that only the 1-4 levels of one chunk (32 MB each at T=2^22 F=2) are live in the 126 MB L2 at any time — for
+  // tables beyond the L2, where a random entry otherwise costs a DRAM sector fetch (gather) or a fetch + write-back
+  // (reduction); the price is re-reading x (12 B) per chunk and, for the scatter, a dL/dy sector shared by two chunks.
+  int chunk_major;
+  uint32_t n_sblocks;      // sample blocks of this launch (chunk_major only)
 };
+__device__ __forceinline__ void block_coords(const GridMeta& m, int n_chunks, uint32_t& sblock, int& chunk) {
+  if (m.chunk_major) { chunk = (int)(blockIdx.x / m.n_sblocks); sblock = blockIdx.x % m.n_sblocks; }
+  else { sblock = blockIdx.x / n_chunks; chunk = (int)(blockIdx.x % n_chunks); }
+}
 __device__ __forceinline__ void to_unit(const GridMeta& m, float& x, float& y, float& z) {
   if (m.affine == 2) {            // every range is a power of two: the multiplication by 1/range is exact, same bits as the division
     x = __fmul_rn(__fsub_rn(x, m.lo[0]), m.inv_range[0]);
@@ -146,12 +158,12 @@ template <int F, typename TP, bool TILES>
 __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
                                                           GridMeta m, int64_t n, float* __restrict__ y) {
   constexpr int LC = levels_per_thread<F>();
-  // level chunk is the FASTEST block coordinate: the n_chunks CTAs that touch the same rows of x / y run back to
-  // back, so the rows are served from L2 instead of being swept from HBM once per chunk
   const int n_chunks = TILES ? m.k0p / 8 : (m.n_levels + LC - 1) / LC;
-  const int64_t i = (int64_t)(blockIdx.x / n_chunks) * (blockDim.x >> 1) + (threadIdx.x >> 1);   // 128 samples per CTA
+  uint32_t sblock; int chunk;
+  block_coords(m, n_chunks, sblock, chunk);                                                        // GridMeta::chunk_major
+  const int64_t i = (int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1);                      // 128 samples per CTA
   const uint32_t xh = threadIdx.x & 1u;                                                            // which x-neighbour
-  const int l0 = (blockIdx.x % n_chunks) * LC;
+  const int l0 = chunk * LC;
   const bool in_range = i < n;
   const int64_t ii = in_range ? i : n - 1;          // out-of-range lanes still take part in the pair shuffles
   float xx = __ldg(x + 3 * ii), xy = __ldg(x + 3 * ii + 1), xz = __ldg(x + 3 * ii + 2);
@@ -251,11 +263,13 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, uint32_t xh, flo
 template <int F, int LC, bool DYT>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
-  const int n_chunks = (m.n_levels + LC - 1) / LC;          // level chunk fastest (see hashgrid_fw_kernel)
-  const int64_t s0 = ((int64_t)(blockIdx.x / n_chunks) * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
+  const int n_chunks = (m.n_levels + LC - 1) / LC;
+  uint32_t sblock; int chunk;
+  block_coords(m, n_chunks, sblock, chunk);                 // GridMeta::chunk_major
+  const int64_t s0 = ((int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
   const uint32_t xh = threadIdx.x & 1u;
   if (s0 >= n) return;
-  const int l0 = (blockIdx.x % n_chunks) * LC;
+  const int l0 = chunk * LC;
   const int LF = m.n_levels * F;
   CellAcc<F> acc[LC];
 #pragma unroll
@@ -439,7 +453,17 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
     off += (uint32_t)sz;
   }
   m.offset[n_levels] = off;
+  m.chunk_major = 0; m.n_sblocks = 1;
   return 0;
+}
+
+// Block order of the gather / scatter launches (GridMeta::chunk_major): chunk-major once the table no longer fits the
+// L2 with room for the streamed rows.  NGP_HASH_ORDER=0|1 overrides (tools/hash_order_probe.py).
+constexpr size_t kL2ResidentTableBytes = 72u << 20;
+static void set_block_order(GridMeta& m, size_t entry_bytes, int64_t n_sblocks) {
+  const char* e = getenv("NGP_HASH_ORDER");
+  m.chunk_major = e ? atoi(e) != 0 : (size_t)m.offset[m.n_levels] * entry_bytes > kL2ResidentTableBytes;
+  m.n_sblocks = (uint32_t)n_sblocks;
 }
 
 }  // namespace ngp
@@ -492,6 +516,7 @@ NGP_API int ngp_hashgrid_fw(const float* x, const float* aabb, const void* table
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = levels_per_thread<F>();
     const unsigned grid = (unsigned)(ceil_div(n, 128) * ceil_div(n_levels, LC));     // lane pair per (sample, level chunk)
+    set_block_order(m, (size_t)F * (table_dtype == 0 ? 4 : 2), ceil_div(n, 128));
     if (table_dtype == 0) hashgrid_fw_kernel<F, float, false><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, y);
     else hashgrid_fw_kernel<F, __half, false><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, y);
   });
@@ -512,6 +537,7 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     const char* e = getenv("NGP_HASH_SPT");
     const int spt = e ? atoi(e) : kSPT;
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC));
+    set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, spt), 64));
     hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
@@ -573,6 +599,7 @@ NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void*
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
     const unsigned grid = (unsigned)(ceil_div(n, 128) * (m.k0p / 8));      // one lane pair per (sample, 16-byte chunk), padded width
+    set_block_order(m, (size_t)F * (table_dtype == 0 ? 4 : 2), ceil_div(n, 128));
     if (table_dtype == 0) hashgrid_fw_kernel<F, float, true><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, (float*)y_tiles);
     else hashgrid_fw_kernel<F, __half, true><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, (float*)y_tiles);
   });
@@ -590,6 +617,7 @@ NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, cons
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = scatter_levels_per_thread<F>();
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
+    set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
     hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");
