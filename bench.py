@@ -35,6 +35,14 @@ WORKLOADS = {
     "street": dict(scene="street", scale=8.0, log2_T=22, esf=1.0 / 256, lr=2e-3, views=128,
                    name="street-shaped (KITTI-360-1538 shape) 1408x376x128 views, scale 8 (5 cascades), exp_step 1/256, "
                         "hashgrid L16 F2 T2^22 + 64-wide MLPs, distortion loss, 2^18 rays/GPU/step"),
+    # --workload playground: BASELINE.json configs[2] shape: the reference's LITERAL field (networks.py:13-163: two F=8 grids
+    # T=2^19 / 2^21 = 174 + 588 MiB, Softplus density net with autograd normals, rgb / normal / semantic heads), scale 8,
+    # appearance embedding 8, 7 classes, normal + semantic compositing, Ref-NeRF + semantic + distortion losses,
+    # 2^18 rays over 8 GPUs = 2^15 rays per GPU
+    "playground": dict(scene="street", scale=8.0, esf=1.0 / 256, lr=2e-3, views=128, field="ngp", rays=1 << 15, classes=7, embed_a_len=8,
+                       name="playground-shaped (TanksAndTemples-BG shape: unbounded, scale 8, 5 cascades, exp_step 1/256), reference-literal "
+                            "NGP field (2 hash grids L16 F8 T2^19/T2^21, density net + autograd normals, rgb/normal/semantic heads), "
+                            "appearance embedding 8, 7 classes, normal+semantic compositing, RefLoss+CE+distortion, 2^15 rays/GPU/step"),
 }
 
 
@@ -119,6 +127,37 @@ def time_kernel(fn, iters=10):
         fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / iters * 1e-3
+
+
+def kernel_breakdown_ngp(model, xyzs, dirs):
+    """Per-kernel times for the reference-literal field (tcnn-API kernels: fp32 (N, L*F) feature / gradient matrices)."""
+    from ngp_b200 import tcnn
+    S = xyzs.shape[0]
+    aabb = model.aabb()
+    xw = xyzs.contiguous()
+    out = {}
+    for tag, enc in (("xyz", model.xyz_encoder), ("rgb", model.rgb_encoder)):
+        g, table = enc.grid, enc.params.detach()
+        LF = g.n_levels * g.n_features
+        dy = torch.randn(S, LF, device=xw.device)
+        dtab = torch.zeros_like(table)
+        out[f"hashgrid_fw_{tag}"] = (time_kernel(lambda: tcnn.grid_forward(xw, table, g, aabb), 3), S * (12 + 8 * LF * 4 + LF * 4), "B")
+        out[f"hashgrid_bw_params_{tag}"] = (time_kernel(lambda: tcnn.grid_backward_params(xw, dy, g, out=dtab, aabb=aabb), 3), S * (12 + LF * 4 + 16 * LF * 4), "B")
+        if tag == "xyz":
+            out["hashgrid_bw_input_xyz"] = (time_kernel(lambda: tcnn.grid_backward_input(xw, dy, table, g, aabb), 3), S * (12 + 8 * LF * 4 + LF * 4 + 12), "B")
+        del dy, dtab
+    feat = tcnn.grid_forward(xw, model.rgb_encoder.params.detach(), model.rgb_encoder.grid, aabb)
+    m2, p2 = model.rgb_net.mlp, model.rgb_net.params.detach()
+    emb = torch.randn(S, model.rgb_net.n_input_dims - 16 - feat.shape[1], device=xw.device)
+    segs = [(dirs, 16, 1), (feat, feat.shape[1], 0)] + ([(emb, emb.shape[1], 0)] if emb.shape[1] else [])
+    k0 = model.rgb_net.n_input_dims
+    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
+    rgb = tcnn.mlp_forward(segs, p2, m2)
+    out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, p2, m2), 3), S * flops(m2, k0), "F")
+    drgb = torch.randn_like(rgb)
+    out["mlp_rgb_bw"] = (time_kernel(lambda: tcnn.mlp_backward(segs, p2, m2, drgb, [False, True] + [True] * (len(segs) - 2), saved_out=rgb), 3),
+                         S * flops(m2, k0) * 3, "F")
+    return out
 
 
 def kernel_breakdown(model, xyzs, dirs):
@@ -209,7 +248,7 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
 def gpu_arm(args):
     import torch.distributed as dist
     from ngp_b200 import _lib, vren
-    from ngp_b200.networks import NGPCompact
+    from ngp_b200.networks import NGP, NGPCompact
     from ngp_b200.synthetic import BoxScene, scene_density_grid
     from ngp_b200.trainer import Trainer, psnr
     from ngp_b200.rendering import render
@@ -233,33 +272,50 @@ def gpu_arm(args):
     wl = WORKLOADS[args.workload]
     scene = BoxScene(wl["scene"], device=dev)
     poses = scene.poses(wl["views"])
-    model = NGPCompact(scale=wl["scale"], log2_T=wl["log2_T"]).to(dev)
+    full = wl.get("field") == "ngp"                                  # the reference-literal field with normal / semantic heads
+    if full:
+        model = NGP(scale=wl["scale"], embed_a=True, embed_a_len=wl["embed_a_len"], classes=wl["classes"]).to(dev)
+        emb = torch.nn.Embedding(wl["views"], wl["embed_a_len"]).to(dev)              # train.py:117-119
+        rkw = dict(exp_step_factor=wl["esf"], num_classes=wl["classes"], normal_ref=True, semantic=True)
+    else:
+        model = NGPCompact(scale=wl["scale"], log2_T=wl["log2_T"]).to(dev)
+        emb = None
+        rkw = dict(exp_step_factor=wl["esf"], num_classes=0)
     model.density_grid.copy_(scene_density_grid(scene))             # converged-occupancy proxy; maintained by update_density_grid afterwards
     vren.packbits(model.density_grid, 0.5, model.density_bitfield)
-    rkw = dict(exp_step_factor=wl["esf"], num_classes=0)
-    tr = Trainer(model, lr=wl["lr"], render_kwargs=rkw, world_size=world)
+    tr = Trainer(model, lr=wl["lr"], render_kwargs=rkw, world_size=world, max_grad_norm=50.0 if full else None,
+                 extra_params=emb.parameters() if full else ())
 
-    R = R_PER_GPU
+    R = wl.get("rays", R_PER_GPU)
     n_batches = 8
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)       # each rank draws its own shard of the global batch
-    pool_o, pool_d, pool_c = [], [], []
+    W_, H_ = scene.img_wh
+    pool = []                                                        # (rays_o, rays_d, rgb, image index, semantic label)
     for _ in range(n_batches):
-        ro, rd = scene.sample_rays(R, poses, gen)
-        c, *_ = scene.shade(ro, rd)
-        pool_o.append(ro); pool_d.append(rd); pool_c.append(c)
-    host = [(o.cpu().pin_memory(), d.cpu().pin_memory(), c.cpu().pin_memory()) for o, d, c in zip(pool_o, pool_d, pool_c)]
-    h2d_bytes = sum(t.numel() * 4 for t in host[0])
+        img = torch.randint(poses.shape[0], (R,), device=dev, generator=gen)
+        u = torch.randint(W_, (R,), device=dev, generator=gen).float()
+        v = torch.randint(H_, (R,), device=dev, generator=gen).float()
+        ro, rd = scene.rays_from_pixels(poses, img, u, v)
+        c, _, _, lab = scene.shade(ro, rd)
+        pool.append((ro, rd, c, img, lab))
+    pool_o, pool_d = [b[0] for b in pool], [b[1] for b in pool]
+    host = [tuple(t.cpu().pin_memory() for t in (b if full else b[:3])) for b in pool]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 
     sample_log = []
 
+    def step(o, d, c, img=None, lab=None):
+        if full:
+            return tr.train_step(o, d, c, target={"label": lab}, embedding_a=emb(img))
+        return tr.train_step(o, d, c)
+
     def step_resident(i):
-        out = tr.train_step(pool_o[i % n_batches], pool_d[i % n_batches], pool_c[i % n_batches])
+        out = step(*(pool[i % n_batches] if full else pool[i % n_batches][:3]))
         sample_log.append(tr.last_samples)
         return out
 
     def step_e2e(i):
-        o, d, c = (t.to(dev, non_blocking=True) for t in host[i % n_batches])
-        loss, _ = tr.train_step(o, d, c)
+        loss, _ = step(*(t.to(dev, non_blocking=True) for t in host[i % n_batches]))
         return float(loss)                                           # device -> host read of the step's result
 
     # pre-train so that the occupancy grid / sample count are at their steady state
@@ -309,14 +365,17 @@ def gpu_arm(args):
 
     # steady-state quality + sample statistics (outside the timed regions)
     with torch.no_grad():
-        ro, rd = scene.sample_rays(1 << 16, poses, gen)
+        img = torch.randint(poses.shape[0], (1 << 15,), device=dev, generator=gen)
+        u = torch.randint(W_, (1 << 15,), device=dev, generator=gen).float()
+        v = torch.randint(H_, (1 << 15,), device=dev, generator=gen).float()
+        ro, rd = scene.rays_from_pixels(poses, img, u, v)
         gt, *_ = scene.shade(ro, rd)
-        out = render(model, ro, rd, **rkw)
+        out = render(model, ro, rd, **rkw, **({"embedding_a": emb(img)} if full else {}))
         q = float(psnr(out["rgb"], gt))
         spr = float(out["total_samples"]) / ro.shape[0]
         rays_a, xyzs, dirs = out["rays_a"], out["xyzs"], None
     rend = None
-    if not args.no_render:
+    if not args.no_render and not full:
         rend = render_bench(model, scene, poses, rank=rank, world=world, esf=wl["esf"])
         if args.render_4k:
             rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world, esf=wl["esf"])
@@ -332,7 +391,7 @@ def gpu_arm(args):
         _, hits_t, _ = vren.ray_aabb_intersect(pool_o[0], pool_d[0], model.center, model.half_size, 1)
         ra, xyzs, dirs, deltas, ts, tot = RayMarcher.apply(pool_o[0], pool_d[0], hits_t[:, 0].contiguous(), model.density_bitfield,
                                                            model.cascades, model.scale, wl["esf"], model.grid_size, MAX_SAMPLES)
-        kb = kernel_breakdown(model, xyzs, dirs)
+        kb = (kernel_breakdown_ngp if full else kernel_breakdown)(model, xyzs, dirs)
     pk, pk_src = peaks()
     kern = {}
     for k, (sec, work, unit) in kb.items():

@@ -43,6 +43,9 @@ struct GridMeta {
   // so that only the 1-4 levels of one chunk (32 MB each at T=2^22 F=2) are live in the 126 MB L2 at any time — for
   // tables beyond the L2, where a random entry otherwise costs a DRAM sector fetch (gather) or a fetch + write-back
   // (reduction); the price is re-reading x (12 B) per chunk and, for the scatter, a dL/dy sector shared by two chunks.
+  // Measured on the street shape (114 M samples, 363 MB table, tools/hash_order_probe.py): scatter 71.7 -> 39.3 ms,
+  // gather 19.7 -> 19.0 ms (its chunk is 4 levels = 128 MB live).  Tried and dropped: one level per lane pair in the
+  // scatter (51 ms: twice the row loads), evict-first (ld.global.cs) row loads (41 ms).
   int chunk_major;
   uint32_t n_sblocks;      // sample blocks of this launch (chunk_major only)
 };

@@ -19,10 +19,13 @@ from .rendering import render
 
 class Trainer:
     def __init__(self, model, lr=1e-2, eps=1e-15, update_interval=16, warmup_steps=256, density_threshold=0.01 * 1024 / 3 ** 0.5,
-                 lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1, max_grad_norm=None):
+                 lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1, max_grad_norm=None,
+                 extra_params=()):
         self.model = model
         self.loss_fn = NeRFLoss(lambda_opa=lambda_opa, lambda_distortion=lambda_distortion)
-        params = [p for p in model.parameters() if p.numel() > 0]
+        # extra_params: parameters outside the field that the step also trains (the appearance embedding, train.py:117-119)
+        self.extra_params = [p for p in extra_params if p.numel() > 0]
+        params = [p for p in model.parameters() if p.numel() > 0] + self.extra_params
         on_gpu = len(params) > 0 and params[0].is_cuda
         # train.py:244-251,435: Adam + global-norm clip, fused (device-resident clip coefficient, 1/world averaging)
         self.opt = (FusedAdam(params, lr=lr, eps=eps, max_grad_norm=max_grad_norm, grad_scale=1.0 / world_size) if on_gpu
@@ -39,7 +42,7 @@ class Trainer:
         if self.world_size <= 1:
             return
         # largest tensors first: the hash tables are > 99 % of the bytes
-        ps = sorted((p for p in self.model.parameters() if p.grad is not None), key=lambda p: -p.numel())
+        ps = sorted((p for p in list(self.model.parameters()) + self.extra_params if p.grad is not None), key=lambda p: -p.numel())
         works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
         for w in works:
             w.wait()
@@ -47,13 +50,16 @@ class Trainer:
             for p in ps:
                 p.grad.div_(self.world_size)
 
-    def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True):
-        """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count."""
+    def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True, target=None, **step_kwargs):
+        """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count.
+        target: further ground-truth tensors of the batch ('label', 'normal', 'depth': train.py:275-283);
+        step_kwargs: per-step render arguments (embedding_a = the batch's appearance embeddings, train.py:285-288)."""
         m = self.model
         if update_grid and self.step % self.update_interval == 0:
             m.update_density_grid(self.density_threshold, warmup=self.step < self.warmup_steps)
-        results = render(m, rays_o, rays_d, **self.render_kwargs)
-        losses = self.loss_fn(results, {"rgb": rgb_gt}, **self.render_kwargs)
+        kw = {**self.render_kwargs, **step_kwargs} if step_kwargs else self.render_kwargs
+        results = render(m, rays_o, rays_d, **kw)
+        losses = self.loss_fn(results, {"rgb": rgb_gt, **(target or {})}, **kw)
         loss = sum(v.mean() for v in losses.values())
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
