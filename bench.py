@@ -419,15 +419,16 @@ def gpu_arm(args):
                                    "sectors_per_sample": tr_["red_sectors_per_sample"]}
     except Exception:
         pass
-    table_mb = model.xyz_encoder.params.numel() * 4 / 2 ** 20
+    table_mb = (model.rgb_encoder if (full and dom.endswith("_rgb")) else model.xyz_encoder).params.numel() * 4 / 2 ** 20
     if table_mb < 100:
         roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the %.0f MB fp32 "
                         "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 - the kernel is bound by L2 "
                         "reduction sector requests (~220 G/s, tools/probes/l2_red_probe.cu; ncu lts__throughput 80 %%), see "
                         "profiles/r01d_ncu_hashgrid_bw_params_kernel.txt" % table_mb)
     else:
-        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time; the %.0f MB fp32 table exceeds the 126 MB L2, "
-                        "random 8-byte entries of 32-byte sectors: DRAM traffic is up to 4x the algorithmic table bytes" % table_mb)
+        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time; the %.0f MB fp32 table exceeds the 126 MB L2: the "
+                        "launch walks level chunks slowest (GridMeta::chunk_major, hashgrid.cu) so that only one chunk's levels are "
+                        "live in L2 at a time; block-order probe in profiles/r01e_hash_block_order_probe.txt" % table_mb)
         roof["traffic"] = None
     cpu, _ = cpu_arm(steps=4, warmup=1)
     value = world * R * args.steps / t_res
