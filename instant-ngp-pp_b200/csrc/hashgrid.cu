@@ -157,9 +157,15 @@ __host__ __device__ __forceinline__ uint32_t feat_tile_bytes(int k0p) { return (
 // only in their low bits for hashed ones, i.e. the same line 15 times out of 16 — are fetched by the two lanes of a
 // lane PAIR in the same instruction: ~4.3 line lookups per (sample, level) instead of 6 (4 when x is even and the pair
 // could go out as one 16-byte load, 8 when it is odd).  The pair's partial sums meet through one shuffle per feature.
-template <int F, typename TP, bool TILES>
+//
+// H2 (double backward of the input gradient, see ngp_hashgrid_bwbw_input): the same gather with the trilinear weight of a
+// corner replaced by the coefficient of that corner in g2 . dy/dx,
+//     coef = scale_l * (g2_x * s_x * w_y * w_z + g2_y * s_y * w_x * w_z + g2_z * s_z * w_x * w_y),   s_d = +1 / -1 for the far / near corner,
+// so that y = d(g2 . dL/dx)/d(dL/dy).
+template <int F, typename TP, bool TILES, bool H2 = false>
 __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restrict__ x, const TP* __restrict__ table,
-                                                          GridMeta m, int64_t n, float* __restrict__ y) {
+                                                          GridMeta m, int64_t n, float* __restrict__ y,
+                                                          const float* __restrict__ g2 = nullptr) {
   constexpr int LC = levels_per_thread<F>();
   const int n_chunks = TILES ? m.k0p / 8 : (m.n_levels + LC - 1) / LC;
   uint32_t sblock; int chunk;
@@ -171,6 +177,8 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
   const int64_t ii = in_range ? i : n - 1;          // out-of-range lanes still take part in the pair shuffles
   float xx = __ldg(x + 3 * ii), xy = __ldg(x + 3 * ii + 1), xz = __ldg(x + 3 * ii + 2);
   to_unit(m, xx, xy, xz);
+  float hx = 0.f, hy = 0.f, hz = 0.f;
+  if (H2) { hx = __ldg(g2 + 3 * ii); hy = __ldg(g2 + 3 * ii + 1); hz = __ldg(g2 + 3 * ii + 2); }
   float out[LC * F];
 #pragma unroll
   for (int k = 0; k < LC * F; k++) out[k] = 0.f;
@@ -190,7 +198,10 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
       for (int p = 0; p < 4; p++) Vec<F, TP>::ld(base + (size_t)idx[p] * F, v[p]);
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        const float w = wxs * ((p & 1) ? c.wy : 1.f - c.wy) * (((p >> 1) & 1) ? c.wz : 1.f - c.wz);
+        const float wy = (p & 1) ? c.wy : 1.f - c.wy, wz = ((p >> 1) & 1) ? c.wz : 1.f - c.wz;
+        float w;
+        if (H2) w = m.scale[l] * (hx * (xh ? 1.f : -1.f) * wy * wz + hy * ((p & 1) ? 1.f : -1.f) * wxs * wz + hz * (((p >> 1) & 1) ? 1.f : -1.f) * wxs * wy);
+        else w = wxs * wy * wz;
 #pragma unroll
         for (int f = 0; f < F; f++) out[li * F + f] = fmaf(w, v[p][f], out[li * F + f]);
       }
@@ -263,9 +274,12 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, uint32_t xh, flo
 //     float(tile, r, c) at tile*(128*k0p) + (c/8)*(128*8) + r*8 + (c%8)
 // i.e. the 8 columns of a level chunk are one 32-byte sector per sample and consecutive samples are contiguous —
 // exactly what a (run of samples, level chunk) lane pair reads, and what a row-per-thread MLP epilogue writes coalesced.
-template <int F, int LC, bool DYT>
+// H2: the table gradient of the double backward (dtable += d(g2 . dL/dx)/dtable): the same run-merged scatter with the
+// corner weight replaced by the coefficient `coef` of hashgrid_fw_kernel<.., H2>; dy is then the FIRST-order upstream.
+template <int F, int LC, bool DYT, bool H2 = false>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                 GridMeta m, int64_t n, float* __restrict__ dtable, int spt) {
+                                                                 GridMeta m, int64_t n, float* __restrict__ dtable, int spt,
+                                                                 const float* __restrict__ g2 = nullptr) {
   const int n_chunks = (m.n_levels + LC - 1) / LC;
   uint32_t sblock; int chunk;
   block_coords(m, n_chunks, sblock, chunk);                 // GridMeta::chunk_major
@@ -284,6 +298,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
     if (i >= n) break;
     float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
     to_unit(m, xx, xy, xz);
+    float hx = 0.f, hy = 0.f, hz = 0.f;
+    if (H2) { hx = __ldg(g2 + 3 * i); hy = __ldg(g2 + 3 * i + 1); hz = __ldg(g2 + 3 * i + 2); }
     const float* src = DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
                            : dy + i * LF + (int64_t)l0 * F;
     float g[LC * F];
@@ -303,6 +319,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
       bool any = false;
 #pragma unroll
       for (int f = 0; f < F; f++) any |= g[li * F + f] != 0.f;
+      if (H2) any = any && (hx != 0.f || hy != 0.f || hz != 0.f);
       if (l < m.n_levels && any) {
         const Cell c = locate(xx, xy, xz, m.scale[l]);
         CellAcc<F>& A = acc[li];
@@ -317,7 +334,10 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
         const float wxs = xh ? c.wx : 1.f - c.wx;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const float w = wxs * ((k & 1) ? c.wy : 1.f - c.wy) * (((k >> 1) & 1) ? c.wz : 1.f - c.wz);
+          const float wy = (k & 1) ? c.wy : 1.f - c.wy, wz = ((k >> 1) & 1) ? c.wz : 1.f - c.wz;
+          float w;
+          if (H2) w = m.scale[l] * (hx * (xh ? 1.f : -1.f) * wy * wz + hy * ((k & 1) ? 1.f : -1.f) * wxs * wz + hz * (((k >> 1) & 1) ? 1.f : -1.f) * wxs * wy);
+          else w = wxs * wy * wz;
 #pragma unroll
           for (int f = 0; f < F; f++) A.a[k][f] = fmaf(w, g[li * F + f], A.a[k][f]);
         }
@@ -375,58 +395,13 @@ __global__ void __launch_bounds__(256) hashgrid_bw_input_kernel(const float* __r
 
 // ----------------------------------------------------------------------------------- double bw
 // Given g2 = dL/d(dL/dx) (N,3) and the first-order upstream gy = dL/dy (N, L*F):
-//   dL/dtable[corner c] += gy * scale * sum_d g2_d * sign_d(c) * prod_{d' != d} w_{d'}(c)
-//   dL/d(gy)_{l,f}       = sum_d g2_d * dy_{l,f}/dx_d
-// (second derivatives of the trilinear kernel w.r.t. x itself are not propagated: x is a leaf
-// produced by the marcher under no_grad in the reference, models/rendering.py:207-212).
-template <int F, typename TP>
-__global__ void __launch_bounds__(256) hashgrid_bwbw_kernel(const float* __restrict__ x, const float* __restrict__ g2,
-                                                            const float* __restrict__ gy_in, const TP* __restrict__ table,
-                                                            GridMeta m, int64_t n, float* __restrict__ dtable,
-                                                            float* __restrict__ dgy) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int l = blockIdx.y;
-  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
-  to_unit(m, xx, xy, xz);
-  const float hx = __ldg(g2 + 3 * i), hy = __ldg(g2 + 3 * i + 1), hz = __ldg(g2 + 3 * i + 2);
-  const int LF = m.n_levels * F;
-  const Cell c = locate(xx, xy, xz, m.scale[l]);
-  const uint32_t res = m.res[l], size = m.size[l];
-  const bool dense = m.dense[l];
-  const float s = m.scale[l];
-  float g[F];
-#pragma unroll
-  for (int f = 0; f < F; f++) g[f] = gy_in ? __ldg(gy_in + i * LF + l * F + f) : 0.f;
-  float acc[F];
-#pragma unroll
-  for (int f = 0; f < F; f++) acc[f] = 0.f;
-  const bool zero_h = (hx == 0.f && hy == 0.f && hz == 0.f);
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
-    const float wx = bx ? c.wx : 1.f - c.wx, wy = by ? c.wy : 1.f - c.wy, wz = bz ? c.wz : 1.f - c.wz;
-    // coefficient of v[k] in sum_d g2_d * dy/dx_d
-    const float coef = s * (hx * (bx ? 1.f : -1.f) * wy * wz + hy * (by ? 1.f : -1.f) * wx * wz + hz * (bz ? 1.f : -1.f) * wx * wy);
-    const uint32_t idx = grid_index(c.px + bx, c.py + by, c.pz + bz, res, size, dense);
-    if (dgy) {
-      float v[F];
-      Vec<F, TP>::ld(table + ((size_t)m.offset[l] + idx) * F, v);
-#pragma unroll
-      for (int f = 0; f < F; f++) acc[f] = fmaf(coef, v[f], acc[f]);
-    }
-    if (dtable && !zero_h) {
-      float v[F];
-#pragma unroll
-      for (int f = 0; f < F; f++) v[f] = coef * g[f];
-      red_add<F>(dtable + ((size_t)m.offset[l] + idx) * F, v);
-    }
-  }
-  if (dgy) {
-#pragma unroll
-    for (int f = 0; f < F; f++) dgy[i * LF + l * F + f] = acc[f];
-  }
-}
+//   dL/dtable[corner c] += gy * scale * sum_d g2_d * sign_d(c) * prod_{d' != d} w_{d'}(c)     -> hashgrid_bw_params_kernel<.., H2>
+//   dL/d(gy)_{l,f}       = sum_d g2_d * dy_{l,f}/dx_d                                           -> hashgrid_fw_kernel<.., H2>
+// (second derivatives of the trilinear kernel w.r.t. x itself are not propagated: x is a leaf produced by the marcher
+// under no_grad in the reference, models/rendering.py:207-212).  The first version was one thread per (sample, level)
+// issuing its 8 corner reductions unmerged: 119 ms for 14 M samples of the street shape (F=8), 35 % of the step of the
+// reference-literal field — consecutive samples of a ray sit in the same coarse cell, i.e. 32-way same-address
+// reductions; the run-merged lane-pair kernels do the same work in the time of an ordinary gather + scatter.
 
 static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res, float per_level_scale, const float* aabb = nullptr) {
   if (n_levels < 1 || n_levels > kMaxLevels) return -1;
@@ -578,9 +553,19 @@ NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const flo
     return set_error_msg("ngp_hashgrid_bwbw_input: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
-    const dim3 grid((unsigned)ceil_div(n, 256), (unsigned)n_levels);
-    if (table_dtype == 0) hashgrid_bwbw_kernel<F, float><<<grid, 256, 0, st>>>(x, g2, dL_dy, (const float*)table, m, n, dtable, d_dL_dy);
-    else hashgrid_bwbw_kernel<F, __half><<<grid, 256, 0, st>>>(x, g2, dL_dy, (const __half*)table, m, n, dtable, d_dL_dy);
+    if (d_dL_dy) {
+      constexpr int LC = levels_per_thread<F>();
+      const unsigned grid = (unsigned)(ceil_div(n, 128) * ceil_div(n_levels, LC));
+      set_block_order(m, (size_t)F * (table_dtype == 0 ? 4 : 2), ceil_div(n, 128));
+      if (table_dtype == 0) hashgrid_fw_kernel<F, float, false, true><<<grid, 256, 0, st>>>(x, (const float*)table, m, n, d_dL_dy, g2);
+      else hashgrid_fw_kernel<F, __half, false, true><<<grid, 256, 0, st>>>(x, (const __half*)table, m, n, d_dL_dy, g2);
+    }
+    if (dtable && dL_dy) {
+      constexpr int LC = scatter_levels_per_thread<F>();
+      const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
+      set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
+      hashgrid_bw_params_kernel<F, LC, false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
+    }
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bwbw_input");
   return 0;

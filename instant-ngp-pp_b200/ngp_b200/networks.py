@@ -143,8 +143,15 @@ class _OccupancyMixin:
 
 class NGP(nn.Module, _OccupancyMixin):
     def __init__(self, scale, rgb_act="Sigmoid", use_skybox=False, embed_a=False, embed_a_len=12, classes=7,
-                 grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16):
+                 grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16, density_net_tf32=True):
         super().__init__()
+        # The density net is the one part of the field the reference keeps in torch (nn.Linear 128 -> 128 -> 1 with
+        # Softplus, double-differentiated for the normals, networks.py:54-59): its fp32 matmuls run on the SIMT pipe by
+        # default (76 ms of a 340 ms step at 14 M samples, tools/step_profile_ngp.py).  TF32 puts them on the tensor
+        # cores — the precision class SURVEY.md a12 states for this net; every other head already rounds to bf16.
+        # Process-wide torch switch, set here once; pass density_net_tf32=False to leave torch's default alone.
+        if density_net_tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.rgb_act = rgb_act
         self.use_skybox = use_skybox
         self.embed_a = embed_a
