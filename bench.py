@@ -290,16 +290,19 @@ def gpu_arm(args):
     n_batches = 8
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)       # each rank draws its own shard of the global batch
     W_, H_ = scene.img_wh
-    pool = []                                                        # (rays_o, rays_d, rgb, image index, semantic label)
+    from ngp_b200 import ray_utils
+    K_ = [[scene.focal, 0.0, W_ / 2], [0.0, scene.focal, H_ / 2], [0.0, 0.0, 1.0]]
+    directions = ray_utils.get_ray_directions(H_, W_, K_, device=dev)       # train.py:103 self.directions (device buffer)
+    pool, host = [], []
     for _ in range(n_batches):
         img = torch.randint(poses.shape[0], (R,), device=dev, generator=gen)
-        u = torch.randint(W_, (R,), device=dev, generator=gen).float()
-        v = torch.randint(H_, (R,), device=dev, generator=gen).float()
-        ro, rd = scene.rays_from_pixels(poses, img, u, v)
+        pix = torch.randint(W_ * H_, (R,), device=dev, generator=gen)
+        ro, rd = ray_utils.get_rays_indexed(directions, poses, img, pix)
         c, _, _, lab = scene.shade(ro, rd)
-        pool.append((ro, rd, c, img, lab))
+        pool.append((ro, rd, c, img, lab))                           # resident batch: rays already generated
+        # what the reference's loader hands a step (datasets/*: img_idxs, pix_idxs, rgb [, label]) in pinned host memory
+        host.append(tuple(t.cpu().pin_memory() for t in ((img, pix, c, lab) if full else (img, pix, c))))
     pool_o, pool_d = [b[0] for b in pool], [b[1] for b in pool]
-    host = [tuple(t.cpu().pin_memory() for t in (b if full else b[:3])) for b in pool]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
 
     sample_log = []
@@ -314,8 +317,30 @@ def gpu_arm(args):
         sample_log.append(tr.last_samples)
         return out
 
+    # end to end: every step's (img_idxs, pix_idxs, rgb[, label]) travel host -> device inside the timed region, on a copy
+    # stream one step ahead of the compute stream (double buffering); rays are generated on the device from the indices
+    # (train.py:136-156), and the step's loss is read back to the host.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = []
+
+    def prefetch(i):
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            bufs = tuple(t.to(dev, non_blocking=True) for t in host[i % n_batches])
+            for t in bufs:
+                t.record_stream(main)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        pending.append((bufs, ev))
+
     def step_e2e(i):
-        loss, _ = step(*(t.to(dev, non_blocking=True) for t in host[i % n_batches]))
+        if not pending:
+            prefetch(i)
+        bufs, ev = pending.pop(0)
+        torch.cuda.current_stream().wait_event(ev)
+        prefetch(i + 1)                                              # next step's inputs fly while this step computes
+        img, pix, c = bufs[:3]
+        o, d = ray_utils.get_rays_indexed(directions, poses, img, pix)
+        loss, _ = step(o, d, c, img, bufs[3]) if full else step(o, d, c)
         return float(loss)                                           # device -> host read of the step's result
 
     # pre-train so that the occupancy grid / sample count are at their steady state
@@ -366,9 +391,7 @@ def gpu_arm(args):
     # steady-state quality + sample statistics (outside the timed regions)
     with torch.no_grad():
         img = torch.randint(poses.shape[0], (1 << 15,), device=dev, generator=gen)
-        u = torch.randint(W_, (1 << 15,), device=dev, generator=gen).float()
-        v = torch.randint(H_, (1 << 15,), device=dev, generator=gen).float()
-        ro, rd = scene.rays_from_pixels(poses, img, u, v)
+        ro, rd = ray_utils.get_rays_indexed(directions, poses, img, torch.randint(W_ * H_, (1 << 15,), device=dev, generator=gen))
         gt, *_ = scene.shade(ro, rd)
         out = render(model, ro, rd, **rkw, **({"embedding_a": emb(img)} if full else {}))
         q = float(psnr(out["rgb"], gt))
@@ -441,7 +464,9 @@ def gpu_arm(args):
                    "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of table+MLP gradients" if world > 1 else "single GPU",
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
         "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": t_e2e / args.steps * 1e3},
+                "ms_per_step": t_e2e / args.steps * 1e3,
+                "path": "pinned host (img_idxs i64, pix_idxs i64, rgb f32[, label]) -> H2D on a copy stream one step ahead -> ngp_get_rays -> "
+                        "Trainer.train_step -> float(loss) on the host, every step"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "render": rend,
     }
     print(json.dumps(line))

@@ -34,6 +34,12 @@ int ngp_ray_sphere_intersect(const float* rays_o, const float* rays_d, const flo
                              int64_t n_rays, int64_t n_spheres, int max_hits, int32_t* hit_cnt, float* hits_t,
                              int64_t* hits_sphere_idx, void* stream);
 
+/* ray generation: get_rays  datasets/ray_utils.py:49-72 with the gathers of train.py:136-137 fused:
+ * rays_d = poses[img_idx][:, :3] . directions[pix_idx], rays_o = poses[img_idx][:, 3].  directions (P,3), poses (V,3,4);
+ * img_idx NULL = poses[0] for every ray, pix_idx NULL = directions[i]. */
+int ngp_get_rays(const float* directions, const float* poses, const int64_t* img_idx, const int64_t* pix_idx,
+                 int64_t n_rays, float* rays_o, float* rays_d, void* stream);
+
 /* ------------------------------------------------------------------ a9: occupancy grid
  * vren.morton3D          binding.cpp:46-50 -> raymarching.cu:72-88    coords (N,3) i32 -> (N) i32
  * vren.morton3D_invert   binding.cpp:53-57 -> raymarching.cu:103-119

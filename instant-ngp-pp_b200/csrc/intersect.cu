@@ -108,9 +108,42 @@ static inline int ray_grid(int64_t n) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Ray generation: rays_d = R(c2w) . direction, rays_o = t(c2w)  (datasets/ray_utils.py:49-72 get_rays, with the two
+// gathers self.poses[img_idxs] / self.directions[pix_idxs] of train.py:136-137 fused in).  Thread per ray; the pose is
+// 48 bytes that all rays of an image share (L1), the direction row is a random 12-byte read for a training batch and
+// a streamed one for a full frame; six coalesced floats out.  The matrix-vector product is spelled as two FMAs onto
+// one product per component (x*R0 first), left to right like a row-by-column dot product.
+__global__ void __launch_bounds__(256) get_rays_kernel(const float* __restrict__ directions, const float* __restrict__ poses,
+                                                       const int64_t* __restrict__ img_idx, const int64_t* __restrict__ pix_idx,
+                                                       int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* P = poses + (img_idx ? __ldg(img_idx + i) : 0) * 12;       // (3,4) row-major camera-to-world
+  const float* d = directions + (pix_idx ? __ldg(pix_idx + i) : i) * 3;
+  const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    rays_d[3 * i + r] = fmaf(dz, __ldg(P + 4 * r + 2), fmaf(dy, __ldg(P + 4 * r + 1), dx * __ldg(P + 4 * r)));
+    rays_o[3 * i + r] = __ldg(P + 4 * r + 3);
+  }
+}
+
 }  // namespace ngp
 
 using namespace ngp;
+
+// rays_o, rays_d (R,3) = get_rays(directions[pix_idx], poses[img_idx])  — datasets/ray_utils.py:49-72 as called from
+// train.py:136-156.  directions (P,3) camera-space (un-normalised, ray_utils.py:39-40), poses (V,3,4) camera-to-world.
+// img_idx == NULL: every ray uses poses[0] (the test-time call with one (3,4) pose); pix_idx == NULL: ray i uses
+// directions[i] (a full frame).  Indices are i64 (torch's index dtype) and are NOT range-checked, like torch's gather
+// in release builds.
+NGP_API int ngp_get_rays(const float* directions, const float* poses, const int64_t* img_idx, const int64_t* pix_idx,
+                         int64_t n_rays, float* rays_o, float* rays_d, void* stream) {
+  if (n_rays <= 0) return 0;
+  get_rays_kernel<<<ray_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(directions, poses, img_idx, pix_idx, n_rays, rays_o, rays_d);
+  NGP_LAUNCH_CHECK("ngp_get_rays");
+  return 0;
+}
 
 // Replaces vren.ray_aabb_intersect (binding.cpp:4-16 -> intersection.cu:59-100).
 // Outputs: hit_cnt (R) i32, hits_t (R,max_hits,2) f32 [-1 = empty slot], hits_voxel_idx (R,max_hits) i64.

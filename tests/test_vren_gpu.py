@@ -350,3 +350,31 @@ def test_against_committed_goldens(vren):
                 assert same.mean() > 0.995
                 close(N(op)[same], g[f"fw_{tag}_opacity"][same]); close(N(rgb)[same], g[f"fw_{tag}_rgb"][same])
                 close(N(sem)[same], g[f"fw_{tag}_sem"][same]); close(N(dep)[same], g[f"fw_{tag}_depth"][same])
+
+
+def test_get_rays_matches_the_reference_formula():
+    """datasets/ray_utils.py:49-72 (+ the gathers of train.py:136-137): rays_d = directions @ R^T, rays_o = t.
+    fp32 tolerance 1e-6 relative: torch evaluates the 3-term dot products in cuBLAS' order, the kernel as two FMAs."""
+    from ngp_b200 import ray_utils
+    g = torch.Generator(device="cuda").manual_seed(11)
+    H, W, V = 60, 80, 7
+    K = [[70.0, 0, W / 2], [0, 65.0, H / 2], [0, 0, 1]]
+    dirs = ray_utils.get_ray_directions(H, W, K, device="cuda")
+    assert dirs.shape == (H * W, 3) and float(dirs[0, 2]) == 1.0
+    assert abs(float(dirs[0, 0]) - (0 - W / 2 + 0.5) / 70.0) < 1e-7 and abs(float(dirs[-1, 1]) - (H - 1 - H / 2 + 0.5) / 65.0) < 1e-7
+    poses = torch.randn(V, 3, 4, device="cuda", generator=g)
+    n = 5000
+    img = torch.randint(V, (n,), device="cuda", generator=g)
+    pix = torch.randint(H * W, (n,), device="cuda", generator=g)
+    ro, rd = ray_utils.get_rays_indexed(dirs, poses, img, pix)
+    c2w, d = poses[img].double(), dirs[pix].double()
+    rd_ref = torch.einsum("nij,nj->ni", c2w[..., :3], d)
+    assert torch.equal(ro, poses[img][..., 3])
+    assert torch.allclose(rd.double(), rd_ref, rtol=1e-6, atol=1e-6)
+    # the reference's two call forms: one (3,4) pose for a whole frame, one pose per ray
+    ro1, rd1 = ray_utils.get_rays(dirs, poses[2])
+    assert torch.equal(ro1, poses[2, :, 3].expand(H * W, 3)) and torch.allclose(rd1.double(), dirs.double() @ poses[2, :, :3].double().T, rtol=1e-6, atol=1e-6)
+    ro2, rd2 = ray_utils.get_rays(dirs[pix], poses[img])
+    assert torch.equal(ro2, ro) and torch.equal(rd2, rd)
+    ro0, rd0 = ray_utils.get_rays_indexed(dirs, poses, img[:0], pix[:0])          # empty batch
+    assert ro0.shape == (0, 3) and rd0.shape == (0, 3)
