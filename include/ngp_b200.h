@@ -200,6 +200,18 @@ int ngp_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream)
 int ngp_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ a12/a13: density net with analytic normals
+ * The elementwise stages of the reference's torch density net  models/networks.py:54-59 (xyz_net = Linear -> Softplus ->
+ * Linear(.,1), sigma_act Softplus) together with d sigma / d(encoding) of networks.py:186-196 and the backward of both
+ * (what torch.autograd.grad(create_graph=True) + loss.backward() evaluate there).  The GEMMs with W1 stay with the caller.
+ *   fw: z1 (N,W) = e W1^T + b1, w2 (W), b2 (1)  ->  sigma (N), s2 (N) = sigmoid(z2), t (N,W) = s2*sigmoid(z1)*w2  (g_e = t W1)
+ *   bw: v (N,W) = dL/dg_e W1^T | NULL, dsigma (N) | NULL  ->  dz1 (N,W), dz2 (N); dw2 (W), db1 (W) accumulated (+=).
+ * W in {128, 256, 384, 512}. */
+int ngp_density_head_fw(const float* z1, const float* w2, const float* b2, int64_t n, int width, float* sigma,
+                        float* s2, float* t, void* stream);
+int ngp_density_head_bw(const float* z1, const float* v, const float* s2, const float* dsigma, const float* w2,
+                        int64_t n, int width, float* dz1, float* dz2, float* dw2, float* db1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,50 @@ class _OccupancyMixin:
         vren.packbits_dthr(self.density_grid, thr, self.density_bitfield)
 
 
+class _DensityNormalsFn(torch.autograd.Function):
+    """(sigma (N), g_e (N,D) = d sigma / d e) of the reference's torch density net
+        sigma = Softplus(Linear(W,1)(Softplus(Linear(D,W)(e))))                       (networks.py:54-59,172-181)
+    as ONE autograd node whose backward covers both outputs — what the reference obtains from
+    torch.autograd.grad(sigmas, x, create_graph=True) + loss.backward() (networks.py:186-196) through ~30 elementwise
+    torch kernels on (N,W) tensors.  Here: one fused elementwise kernel per direction (csrc/density_head.cu, formulas
+    there) between the GEMMs with W1, which stay on cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, e, W1, b1, W2, b2):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        e = e.contiguous()
+        n, W = e.shape[0], W1.shape[0]
+        z1 = torch.addmm(b1, e, W1.t())
+        sigma = torch.empty(n, device=e.device); s2 = torch.empty(n, device=e.device)
+        t = torch.empty(n, W, device=e.device)
+        w2 = W2.reshape(-1).contiguous()
+        check(lib.ngp_density_head_fw(ptr(z1), ptr(w2), ptr(b2.contiguous()), n, W, ptr(sigma), ptr(s2), ptr(t), stream()),
+              "density_head_fw")
+        g_e = t @ W1
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(e, W1, w2, z1, s2, t)
+        return sigma, g_e
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dsigma, dg):
+        from ._lib import lib, ptr, check, stream
+        e, W1, w2, z1, s2, t = ctx.saved_tensors
+        n, W = z1.shape
+        v = (dg.contiguous() @ W1.t()) if dg is not None else None
+        dz1 = torch.empty_like(z1); dz2 = torch.empty(n, device=z1.device)
+        dw2 = torch.zeros(W, device=z1.device); db1 = torch.zeros(W, device=z1.device)
+        check(lib.ngp_density_head_bw(ptr(z1), ptr(v), ptr(s2), ptr(dsigma.contiguous() if dsigma is not None else None), ptr(w2), n, W,
+                                      ptr(dz1), ptr(dz2), ptr(dw2), ptr(db1), stream()), "density_head_bw")
+        de = dz1 @ W1 if ctx.needs_input_grad[0] else None
+        dW1 = dz1.t() @ e
+        if dg is not None:
+            dW1.addmm_(t.t(), dg)
+        return de, dW1, db1, dw2[None], dz2.sum()[None]
+
+
 class NGP(nn.Module, _OccupancyMixin):
     def __init__(self, scale, rgb_act="Sigmoid", use_skybox=False, embed_a=False, embed_a_len=12, classes=7,
                  grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16, density_net_tf32=True):
@@ -186,6 +230,8 @@ class NGP(nn.Module, _OccupancyMixin):
                 setattr(self, f"tonemapper_net_{i}", head(1, 1, 64, "Sigmoid"))
 
     # ------------------------------------------------------------------ density / normals
+    fused_density_head = True     # sigma and d sigma / d(encoding) through _DensityNormalsFn (csrc/density_head.cu)
+
     def _normalise(self, x):
         return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
 
@@ -206,8 +252,12 @@ class NGP(nn.Module, _OccupancyMixin):
         (networks.py:186-196)."""
         x, ab = x.detach().contiguous(), self.aabb()
         enc = self.xyz_encoder(x, ab)
-        sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
-        (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)
+        l0, l2 = self.xyz_net[0], self.xyz_net[2]
+        if self.fused_density_head and enc.is_cuda and enc.dtype == torch.float32 and l0.out_features % 128 == 0 and l0.out_features <= 512:
+            sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias)
+        else:       # any other density net: generic autograd double backward, as the reference does it
+            sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
+            (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)
         # input gradient of the grid as a differentiable op of (g_enc, table): its backward is the
         # double-backward kernel
         g_xn, _ = _GridBwFn.apply(g_enc.contiguous(), x, self.xyz_encoder.params, self.xyz_encoder.grid,

@@ -203,3 +203,39 @@ def test_street_shaped_scene_cascades_semantics_normals_embedding():
         out = render(m, ro[:2048], rd[:2048], embedding_a=emb(img[:1]), exp_step_factor=1.0 / 256, num_classes=10,
                      test_time=True, T_threshold=1e-2)
     assert torch.isfinite(out["rgb"]).all() and out["semantic"].max() < 10
+
+
+@pytest.mark.parametrize("width", [128, 256])
+def test_density_head_matches_autograd_double_backward(width):
+    """_DensityNormalsFn (csrc/density_head.cu) against the reference's formulation — torch.autograd.grad with
+    create_graph=True through Linear -> Softplus -> Linear -> Softplus (networks.py:54-59,186-196) — evaluated in
+    fp64: both outputs and all five gradients of a scalar that uses both.  fp32 kernels + fp32 (non-TF32) GEMMs:
+    relative error 1e-4 of each tensor's norm."""
+    from ngp_b200.networks import _DensityNormalsFn
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device="cuda").manual_seed(7)
+        n, D = 4099, 96
+        rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+        e, W1, b1, W2, b2 = rnd(n, D), rnd(width, D) * 0.2, rnd(width), rnd(1, width) * 0.3, rnd(1)
+        e[0] = 40.0                                   # drives pre-activations past softplus' linear threshold (20)
+        ds, dg = rnd(n), rnd(n, D)
+        ps = [t.clone().requires_grad_(True) for t in (e, W1, b1, W2, b2)]
+        sig, ge = _DensityNormalsFn.apply(*ps)
+        grads = torch.autograd.grad((sig * ds).sum() + (ge * dg).sum(), ps)
+        po = [t.double().clone().requires_grad_(True) for t in (e, W1, b1, W2, b2)]
+        o_sig = F.softplus(F.linear(F.softplus(F.linear(po[0], po[1], po[2])), po[3], po[4]))[:, 0]
+        (o_ge,) = torch.autograd.grad(o_sig, po[0], torch.ones_like(o_sig), create_graph=True)
+        o_grads = torch.autograd.grad((o_sig * ds.double()).sum() + (o_ge * dg.double()).sum(), po)
+        rel = lambda a, b: float((a.double() - b).norm() / (b.norm() + 1e-30))
+        assert rel(sig, o_sig) < 1e-5 and rel(ge, o_ge) < 1e-4, (rel(sig, o_sig), rel(ge, o_ge))
+        for name, a, b in zip(("e", "W1", "b1", "W2", "b2"), grads, o_grads):
+            assert a.shape == b.shape and rel(a, b) < 1e-4, (name, rel(a, b))
+        # sigma-only upstream (density evaluation without normals) and normals-only upstream
+        sig, ge = _DensityNormalsFn.apply(*ps)
+        (g_w1,) = torch.autograd.grad((sig * ds).sum(), ps[1])
+        (o_w1,) = torch.autograd.grad((F.softplus(F.linear(F.softplus(F.linear(po[0], po[1], po[2])), po[3], po[4]))[:, 0] * ds.double()).sum(), po[1])
+        assert rel(g_w1, o_w1) < 1e-4
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
