@@ -102,3 +102,31 @@ def mlp_forward(x, params, n_in, width, n_hidden, n_out, activation="ReLU", outp
         z = rnd(h) @ rnd(W).t()
         h = _ACT[activation](z) if li < len(shapes) - 1 else _ACT[output_activation](z[:, :n_out])
     return h
+
+
+# ------------------------------------------------------------------------------------------ density net + normals
+def density_head_reference(e, W1, b1, W2, b2):
+    """The reference's formulation (models/networks.py:54-59,172-181,186-196): xyz_net = Linear -> Softplus -> Linear(.,1),
+    sigma_act = Softplus, and d sigma / d e by autograd with create_graph=True.  -> (sigma (N), g_e (N,D))."""
+    import torch.nn.functional as F
+    sig = F.softplus(F.linear(F.softplus(F.linear(e, W1, b1)), W2, b2))[:, 0]
+    (g,) = torch.autograd.grad(sig, e, torch.ones_like(sig), create_graph=True)
+    return sig, g
+
+
+def density_head_closed_form(e, W1, b1, W2, b2, dsigma, dg):
+    """Closed forms that csrc/density_head.cu evaluates (its header comment), in plain torch ops:
+    -> (sigma, g_e, (de, dW1, db1, dW2, db2)) for upstream gradients (dsigma (N), dg (N,D)) of the two outputs."""
+    import torch.nn.functional as F
+    z1 = torch.addmm(b1, e, W1.t())
+    s1, a1, w2 = torch.sigmoid(z1), F.softplus(z1), W2[0]
+    z2 = a1 @ w2 + b2
+    sigma, s2 = F.softplus(z2), torch.sigmoid(z2)
+    t = s2[:, None] * s1 * w2
+    g_e = t @ W1
+    v = dg @ W1.t()
+    uv = s1 * v
+    dz2 = (uv @ w2) * s2 * (1 - s2) + dsigma * s2
+    dz1 = w2 * (uv * s2[:, None] * (1 - s1) + dz2[:, None] * s1)
+    return sigma, g_e, (dz1 @ W1, t.t() @ dg + dz1.t() @ e, dz1.sum(0), (s2[:, None] * uv + dz2[:, None] * a1).sum(0)[None],
+                        dz2.sum()[None])

@@ -244,3 +244,26 @@ def test_mlp_oracle_layout():
     y = tcnn_oracle.mlp_forward(x, p, 4, 8, 1, 3)
     W0 = p[:32].reshape(8, 4); W1 = p[32:].reshape(16, 8)
     assert torch.allclose(y, (torch.relu(x @ W0.t()) @ W1.t())[:, :3])
+
+
+def test_density_head_closed_forms_match_autograd_double_backward():
+    """The formulas csrc/density_head.cu implements (oracle/tcnn_oracle.density_head_closed_form) against the reference's
+    own formulation — autograd.grad(create_graph=True) through Linear/Softplus/Linear/Softplus, networks.py:54-59,186-196 —
+    in fp64 on CPU: outputs and all five gradients to 1e-8 — the one row driven past softplus' linear threshold (20)
+    differs by 1 - sigmoid(z) ~ 2e-9 in fp64 (torch switches to the identity there); in fp32 both round to 1."""
+    import torch
+    from oracle import tcnn_oracle
+    torch.manual_seed(3)
+    n, D, W = 200, 24, 16
+    mk = lambda *s: torch.randn(*s, dtype=torch.double)
+    e, W1, b1, W2, b2 = mk(n, D), mk(W, D) * 0.5, mk(W), mk(1, W), mk(1)
+    e[0] = 30.0                                            # past softplus' linear threshold
+    ds, dg = mk(n), mk(n, D)
+    ps = [t.clone().requires_grad_(True) for t in (e, W1, b1, W2, b2)]
+    sig, g = tcnn_oracle.density_head_reference(*ps)
+    ref = torch.autograd.grad((sig * ds).sum() + (g * dg).sum(), ps)
+    sigma, g_e, grads = tcnn_oracle.density_head_closed_form(e, W1, b1, W2, b2, ds, dg)
+    assert float((sigma - sig).abs().max()) < 1e-12 and float((g_e - g).abs().max()) < 1e-8
+    assert float((g_e[1:] - g[1:]).abs().max()) < 1e-12          # rows below the threshold: exact
+    for a, b in zip(grads, ref):
+        assert a.shape == b.shape and float((a - b).abs().max()) < 1e-8 * max(1.0, float(b.abs().max()))
