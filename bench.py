@@ -307,10 +307,10 @@ def gpu_arm(args):
 
     sample_log = []
 
-    def step(o, d, c, img=None, lab=None):
+    def step(o, d, c, img=None, lab=None, host_loss=False):
         if full:
-            return tr.train_step(o, d, c, target={"label": lab}, embedding_a=emb(img))
-        return tr.train_step(o, d, c)
+            return tr.train_step(o, d, c, target={"label": lab}, embedding_a=emb(img), host_loss=host_loss)
+        return tr.train_step(o, d, c, host_loss=host_loss)
 
     def step_resident(i):
         out = step(*(pool[i % n_batches] if full else pool[i % n_batches][:3]))
@@ -340,8 +340,8 @@ def gpu_arm(args):
         prefetch(i + 1)                                              # next step's inputs fly while this step computes
         img, pix, c = bufs[:3]
         o, d = ray_utils.get_rays_indexed(directions, poses, img, pix)
-        loss, _ = step(o, d, c, img, bufs[3]) if full else step(o, d, c)
-        return float(loss)                                           # device -> host read of the step's result
+        loss, _ = step(o, d, c, img, bufs[3], host_loss=True) if full else step(o, d, c, host_loss=True)
+        return loss                                                  # python float: this step's loss, read back on the host (Trainer.train_step)
 
     # pre-train so that the occupancy grid / sample count are at their steady state
     for i in range(args.pretrain):
@@ -466,7 +466,7 @@ def gpu_arm(args):
         "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / args.steps * 1e3,
                 "path": "pinned host (img_idxs i64, pix_idxs i64, rgb f32[, label]) -> H2D on a copy stream one step ahead -> ngp_get_rays -> "
-                        "Trainer.train_step -> float(loss) on the host, every step"},
+                        "Trainer.train_step(host_loss=True): loss -> pinned host right after the forward pass, waited for after the step is enqueued; every step"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "render": rend,
     }
     print(json.dumps(line))

@@ -291,6 +291,27 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
   CellAcc<F> acc[LC];
 #pragma unroll
   for (int li = 0; li < LC; li++) acc[li].has = false;
+  auto dy_row = [&](int64_t i) -> const float* {
+    return DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
+               : dy + i * LF + (int64_t)l0 * F;
+  };
+  if (m.chunk_major) {
+    // In chunk-major order the run's x and dL/dy rows come from DRAM on every chunk sweep, one dependent miss per
+    // sample of the serial loop below (ncu r01e, street shape: long-scoreboard 15 of 18 stall cycles per issue, DRAM
+    // 21 %, L2 46 % busy: latency, not bandwidth).  Ask the L2 for the whole run up front: lane 0 of the pair for the
+    // x rows (12 B per sample, contiguous), lane 1 for the dL/dy rows.
+    const int64_t s1 = s0 + spt < n ? s0 + spt : n;
+    if (xh == 0) {
+      const char* p = reinterpret_cast<const char*>(x + 3 * s0);
+      const char* e = reinterpret_cast<const char*>(x + 3 * s1);
+      for (; p < e; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    } else {
+      constexpr int kStep = DYT ? 4 : 1;      // gradient tiles: consecutive samples are 32 B apart (4 per line); matrix rows: a line or more each
+      for (int64_t i = s0; i < s1; i += kStep) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy_row(i)));
+      if (H2) for (const char* p = reinterpret_cast<const char*>(g2 + 3 * s0); p < reinterpret_cast<const char*>(g2 + 3 * s1); p += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
 
 #pragma unroll 1
   for (int j = 0; j < spt; j++) {
@@ -300,8 +321,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
     to_unit(m, xx, xy, xz);
     float hx = 0.f, hy = 0.f, hz = 0.f;
     if (H2) { hx = __ldg(g2 + 3 * i); hy = __ldg(g2 + 3 * i + 1); hz = __ldg(g2 + 3 * i + 2); }
-    const float* src = DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
-                           : dy + i * LF + (int64_t)l0 * F;
+    const float* src = dy_row(i);
     float g[LC * F];
     if (l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0) {
 #pragma unroll

@@ -37,6 +37,7 @@ class Trainer:
         self.world_size = world_size
         self.step = 0
         self.last_samples = None
+        self._loss_host = self._loss_event = None
 
     def allreduce_grads(self):
         if self.world_size <= 1:
@@ -50,10 +51,13 @@ class Trainer:
             for p in ps:
                 p.grad.div_(self.world_size)
 
-    def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True, target=None, **step_kwargs):
+    def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True, target=None, host_loss=False, **step_kwargs):
         """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count.
         target: further ground-truth tensors of the batch ('label', 'normal', 'depth': train.py:275-283);
-        step_kwargs: per-step render arguments (embedding_a = the batch's appearance embeddings, train.py:285-288)."""
+        step_kwargs: per-step render arguments (embedding_a = the batch's appearance embeddings, train.py:285-288).
+        host_loss=True returns the loss as a python float (what the reference's progress bar / logger reads every step,
+        train.py:337-343): the value is copied to pinned host memory as soon as the forward pass has produced it and
+        waited for only after backward + optimiser have been enqueued, so the read-back never drains the GPU."""
         m = self.model
         if update_grid and self.step % self.update_interval == 0:
             m.update_density_grid(self.density_threshold, warmup=self.step < self.warmup_steps)
@@ -61,12 +65,21 @@ class Trainer:
         results = render(m, rays_o, rays_d, **kw)
         losses = self.loss_fn(results, {"rgb": rgb_gt, **(target or {})}, **kw)
         loss = sum(v.mean() for v in losses.values())
+        if host_loss:
+            if self._loss_host is None:
+                self._loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+                self._loss_event = torch.cuda.Event()
+            self._loss_host.copy_(loss.detach(), non_blocking=True)
+            self._loss_event.record()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.allreduce_grads()
         self.opt.step()
         self.step += 1
         self.last_samples = results["total_samples"]
+        if host_loss:
+            self._loss_event.synchronize()
+            return float(self._loss_host), results
         return loss.detach(), results
 
 
