@@ -321,27 +321,35 @@ def gpu_arm(args):
     # stream one step ahead of the compute stream (double buffering); rays are generated on the device from the indices
     # (train.py:136-156), and the step's loss is read back to the host.
     copy_stream = torch.cuda.Stream(device=dev)
-    pending = []
+    dev_bufs = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host[0]) for _ in range(2)]   # double buffer, allocated once
+    free_ev = [None, None]               # recorded on the compute stream when the step that read buffer b is fully enqueued
+    pending, seq = [], [0]
 
-    def prefetch(i):
-        main = torch.cuda.current_stream()
+    def prefetch():
+        b = seq[0] % 2
         with torch.cuda.stream(copy_stream):
-            bufs = tuple(t.to(dev, non_blocking=True) for t in host[i % n_batches])
-            for t in bufs:
-                t.record_stream(main)
+            if free_ev[b] is not None:
+                copy_stream.wait_event(free_ev[b])
+            for dst, src in zip(dev_bufs[b], host[seq[0] % n_batches]):
+                dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(copy_stream)
-        pending.append((bufs, ev))
+        pending.append((b, ev))
+        seq[0] += 1
 
     def step_e2e(i):
         if not pending:
-            prefetch(i)
-        bufs, ev = pending.pop(0)
-        torch.cuda.current_stream().wait_event(ev)
-        prefetch(i + 1)                                              # next step's inputs fly while this step computes
+            prefetch()
+        b, ev = pending.pop(0)
+        main = torch.cuda.current_stream()
+        main.wait_event(ev)
+        prefetch()                                                   # next step's inputs fly while this step computes
+        bufs = dev_bufs[b]
         img, pix, c = bufs[:3]
         o, d = ray_utils.get_rays_indexed(directions, poses, img, pix)
-        loss, _ = step(o, d, c, img, bufs[3], host_loss=True) if full else step(o, d, c, host_loss=True)
-        return loss                                                  # python float: this step's loss, read back on the host (Trainer.train_step)
+        hl = os.environ.get("NGP_BENCH_BLOCKING_LOSS", "0") != "1"     # 1: float(loss) after the step (drains the GPU every step)
+        loss, _ = step(o, d, c, img, bufs[3], host_loss=hl) if full else step(o, d, c, host_loss=hl)
+        free_ev[b] = torch.cuda.Event(); free_ev[b].record(main)
+        return float(loss)                                                  # python float: this step's loss, read back on the host (Trainer.train_step)
 
     # pre-train so that the occupancy grid / sample count are at their steady state
     for i in range(args.pretrain):

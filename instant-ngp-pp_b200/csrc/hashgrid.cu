@@ -45,7 +45,9 @@ struct GridMeta {
   // (reduction); the price is re-reading x (12 B) per chunk and, for the scatter, a dL/dy sector shared by two chunks.
   // Measured on the street shape (114 M samples, 363 MB table, tools/hash_order_probe.py): scatter 71.7 -> 39.3 ms,
   // gather 19.7 -> 19.0 ms (its chunk is 4 levels = 128 MB live).  Tried and dropped: one level per lane pair in the
-  // scatter (51 ms: twice the row loads), evict-first (ld.global.cs) row loads (41 ms).
+  // scatter (51 ms: twice the row loads), evict-first (ld.global.cs) row loads (41 ms), prefetch.global.L2 of a run's x /
+  // dL/dy rows ahead of its serial loop (40.8 ms: no change, although ncu shows long-scoreboard stalls with DRAM at 21 %
+  // and L2 at 46 % — the misses that matter are the reductions' own sector fetches, L2 hit rate 54 %).
   int chunk_major;
   uint32_t n_sblocks;      // sample blocks of this launch (chunk_major only)
 };
@@ -295,24 +297,6 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
     return DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
                : dy + i * LF + (int64_t)l0 * F;
   };
-  if (m.chunk_major) {
-    // In chunk-major order the run's x and dL/dy rows come from DRAM on every chunk sweep, one dependent miss per
-    // sample of the serial loop below (ncu r01e, street shape: long-scoreboard 15 of 18 stall cycles per issue, DRAM
-    // 21 %, L2 46 % busy: latency, not bandwidth).  Ask the L2 for the whole run up front: lane 0 of the pair for the
-    // x rows (12 B per sample, contiguous), lane 1 for the dL/dy rows.
-    const int64_t s1 = s0 + spt < n ? s0 + spt : n;
-    if (xh == 0) {
-      const char* p = reinterpret_cast<const char*>(x + 3 * s0);
-      const char* e = reinterpret_cast<const char*>(x + 3 * s1);
-      for (; p < e; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    } else {
-      constexpr int kStep = DYT ? 4 : 1;      // gradient tiles: consecutive samples are 32 B apart (4 per line); matrix rows: a line or more each
-      for (int64_t i = s0; i < s1; i += kStep) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy_row(i)));
-      if (H2) for (const char* p = reinterpret_cast<const char*>(g2 + 3 * s0); p < reinterpret_cast<const char*>(g2 + 3 * s1); p += 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-  }
-
 #pragma unroll 1
   for (int j = 0; j < spt; j++) {
     const int64_t i = s0 + j;
