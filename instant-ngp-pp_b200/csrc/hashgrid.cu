@@ -356,6 +356,73 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
   }
 }
 
+// F = 8 (the reference's grids, networks.py:40-52,67-76): an entry is 32 bytes = one whole sector, so the x-neighbours of
+// a corner pair can never share a sector and every corner costs TWO 16-byte reductions = two L2 sector requests in the
+// kernel above.  Here the lanes of a pair split the FEATURES instead: lane h owns features 4h..4h+3 of all eight
+// corners, the pair's two float4 reductions to one entry are the same instruction and the same sector = ONE request:
+// 8 requests per (cell, level) instead of 16.  Same run merging, same zero-row skip, same H2 weights.
+template <bool DYT, bool H2>
+__global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                    GridMeta m, int64_t n, float* __restrict__ dtable, int spt,
+                                                                    const float* __restrict__ g2 = nullptr) {
+  constexpr int F = 8;
+  uint32_t sblock; int l;
+  block_coords(m, m.n_levels, sblock, l);                   // one level per lane pair
+  const int64_t s0 = ((int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
+  const uint32_t fh = (threadIdx.x & 1u) * 4u;              // this lane's feature half
+  if (s0 >= n) return;
+  const int LF = m.n_levels * F;
+  const float scale = m.scale[l];
+  const uint32_t res = m.res[l], size = m.size[l];
+  const bool dense = m.dense[l];
+  float* base = dtable + (size_t)m.offset[l] * F + fh;
+  uint32_t cx = 0, cy = 0, cz = 0;
+  bool has = false;
+  float a[8][4];                                            // corner (x bit 2, z bit 1, y bit 0) x feature of this half
+  auto flush = [&]() {
+#pragma unroll
+    for (int xb = 0; xb < 2; xb++) {
+      uint32_t idx[4];
+      corner4(cx + xb, cy, cz, res, size, dense, idx);
+#pragma unroll
+      for (int p = 0; p < 4; p++) red_add<4>(base + (size_t)idx[p] * F, a[xb * 4 + p]);
+    }
+  };
+#pragma unroll 1
+  for (int j = 0; j < spt; j++) {
+    const int64_t i = s0 + j;
+    if (i >= n) break;
+    float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+    to_unit(m, xx, xy, xz);
+    float hx = 0.f, hy = 0.f, hz = 0.f;
+    if (H2) { hx = __ldg(g2 + 3 * i); hy = __ldg(g2 + 3 * i + 1); hz = __ldg(g2 + 3 * i + 2); }
+    const float* src = DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)l * (128 * 8) + (i & 127) * 8 + fh
+                           : dy + i * LF + (int64_t)l * F + fh;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(src));
+    bool any = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
+    if (H2) any = any && (hx != 0.f || hy != 0.f || hz != 0.f);
+    if (!any) continue;
+    const Cell c = locate(xx, xy, xz, scale);
+    if (!has || cx != c.px || cy != c.py || cz != c.pz) {
+      if (has) flush();
+      cx = c.px; cy = c.py; cz = c.pz; has = true;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { a[k][0] = 0.f; a[k][1] = 0.f; a[k][2] = 0.f; a[k][3] = 0.f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int xb = k >> 2, yb = k & 1, zb = (k >> 1) & 1;
+      const float wx = xb ? c.wx : 1.f - c.wx, wy = yb ? c.wy : 1.f - c.wy, wz = zb ? c.wz : 1.f - c.wz;
+      float w;
+      if (H2) w = scale * (hx * (xb ? 1.f : -1.f) * wy * wz + hy * (yb ? 1.f : -1.f) * wx * wz + hz * (zb ? 1.f : -1.f) * wx * wy);
+      else w = wx * wy * wz;
+      a[k][0] = fmaf(w, g.x, a[k][0]); a[k][1] = fmaf(w, g.y, a[k][1]);
+      a[k][2] = fmaf(w, g.z, a[k][2]); a[k][3] = fmaf(w, g.w, a[k][3]);
+    }
+  }
+  if (has) flush();
+}
+
 // ----------------------------------------------------------------------------------- bw (input)
 // dL/dx_d = sum_l scale_l * sum_f dL/dy_{l,f} * sum_{corners of the other two dims} w_other * (v[d=1]-v[d=0])
 template <int F, typename TP>
@@ -520,7 +587,8 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     const int spt = e ? atoi(e) : kSPT;
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, spt), 64));
-    hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    if (F == 8 && (n_levels * F) % 4 == 0) hashgrid_bw_params_f8_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    else hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
   return 0;
@@ -568,7 +636,8 @@ NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const flo
       constexpr int LC = scatter_levels_per_thread<F>();
       const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
       set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
-      hashgrid_bw_params_kernel<F, LC, false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
+      if (F == 8) hashgrid_bw_params_f8_kernel<false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
+      else hashgrid_bw_params_kernel<F, LC, false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
     }
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bwbw_input");
@@ -610,7 +679,8 @@ NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, cons
     constexpr int LC = scatter_levels_per_thread<F>();
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
-    hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
+    if (F == 8) hashgrid_bw_params_f8_kernel<true, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
+    else hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");
   return 0;

@@ -72,12 +72,14 @@ def test_hashgrid_forward_and_first_order(cfg):
     assert float((e[8:] > 2e-2).float().mean()) < 1e-2, float((e[8:] > 2e-2).float().mean())
 
 
-def test_hashgrid_double_backward():
+@pytest.mark.parametrize("F", [4, 8, 2])
+def test_hashgrid_double_backward(F):
     """Normals-style second order: loss = |d softplus(y.W)/dx|^2 + sum; gradient w.r.t. the table goes
-    through the double-backward kernel.  Low resolutions keep the fp32 problem well conditioned."""
+    through the double-backward kernels (the H2 variants of the gather / scatter; F = 8 takes the feature-split
+    scatter).  Low resolutions keep the fp32 problem well conditioned."""
     from ngp_b200 import tcnn
     from ngp_b200.tcnn import _GridFn
-    L, F, T, base, b = 6, 4, 11, 4, 1.45
+    L, T, base, b = 6, 11, 4, 1.45
     enc = tcnn.Encoding(3, {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": T,
                             "base_resolution": base, "per_level_scale": b}).cuda()
     assert enc.grid.dense[0] and not enc.grid.dense[-1]
@@ -291,3 +293,30 @@ def test_mlp_backward_from_saved_output_equals_recompute(shape):
     dp1, dx1 = tcnn.mlp_backward([(x, n_in, 0)], p, net.mlp, dy, [True], d_aux=da, saved_out=y)
     assert torch.equal(dx0[0], dx1[0])
     assert rel(dp1, dp0) < 1e-5
+
+
+@pytest.mark.parametrize("F", [2, 8])
+def test_hashgrid_block_order_does_not_change_results(F, monkeypatch):
+    """GridMeta::chunk_major (hashgrid.cu): tables beyond the L2 walk level chunks slowest.  The order only permutes
+    CTAs: the gather is bit-identical, the scatter (fp32 atomics, already order-dependent) agrees to 1e-5 relative."""
+    from ngp_b200 import tcnn
+    enc, _ = _grid(16, F, 15, 16, 0.5)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 20011
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    dy = torch.randn(n, 16 * F, device="cuda", generator=g)
+    table = enc.params.detach()
+    out = {}
+    for order in ("0", "1"):
+        monkeypatch.setenv("NGP_HASH_ORDER", order)
+        y = tcnn.grid_forward(x, table, enc.grid)
+        dt = tcnn.grid_backward_params(x, dy, enc.grid)
+        tiles = tcnn.grid_forward_tiles(x, table, enc.grid) if F == 2 else None
+        torch.cuda.synchronize()
+        out[order] = (y, dt, tiles)
+    assert torch.equal(out["0"][0], out["1"][0])
+    assert rel(out["1"][1], out["0"][1]) < 1e-5
+    if F == 2:
+        k0p = 32
+        v = lambda t: t.view(-1, k0p // 8, 128 * 16 + 64)[:, :, :128 * 16]
+        assert torch.equal(v(out["0"][2]), v(out["1"][2]))
