@@ -16,12 +16,27 @@
 //     dz1  = w2 * (uv * s2 * (1 - s1) + dz2 * s1)
 //     dw2  = sum_rows (s2 * uv + dz2 * a1)   db1 = sum_rows dz1    (db2 = sum dz2, dW1 = t^T dg_e + dz1^T e, de = dz1 W1: caller)
 // torch's softplus is linear above threshold 20; sigmoid(z > 20) rounds to 1 in fp32, so the derivatives agree.
+// (sigma at z2 > 20: z2 + log(1+e^-z2) = z2 in fp32, the same value.)
 #include "common.cuh"
 
 namespace ngp {
 
-__device__ __forceinline__ float softplus1(float z) { return z > 20.f ? z : log1pf(expf(z)); }
-__device__ __forceinline__ float sigmoid1(float z) { return 1.f / (1.f + expf(-z)); }
+// softplus and sigmoid of the same z from ONE exponential: e = exp(-|z|) in (0, 1],
+//     sigmoid(z) = z >= 0 ? 1/(1+e) : e/(1+e) ;  softplus(z) = max(z, 0) + log(1 + e)
+// (no overflow for any z; above torch's linear threshold 20 the log term is < 2.1e-9 and vanishes in fp32 exactly as
+// torch's switch to the identity does).  MUFU.EX2 + MUFU.RCP + MUFU.LG2: with expf / log1pf / an IEEE division per
+// element the kernels were ALU bound at 42 % (fw) / 56 % (bw) of the HBM rate (profiles/r01e_step_profile_playground_after.txt).
+struct SpSg { float sp, sg; };
+__device__ __forceinline__ SpSg softplus_sigmoid(float z) {
+  const float e = __expf(-fabsf(z));
+  const float r = __frcp_rn(1.f + e);
+  SpSg o;
+  o.sg = z >= 0.f ? r : e * r;
+  o.sp = fmaxf(z, 0.f) + __logf(1.f + e);
+  return o;
+}
+__device__ __forceinline__ float softplus1(float z) { return softplus_sigmoid(z).sp; }
+__device__ __forceinline__ float sigmoid1(float z) { return softplus_sigmoid(z).sg; }
 
 constexpr int kHeadMaxK = 4;   // W <= 512
 
@@ -43,12 +58,13 @@ __global__ void __launch_bounds__(256) density_head_fw_kernel(const float* __res
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const float4 z = __ldcs(reinterpret_cast<const float4*>(z1 + r * W) + k * 32 + lane);
-      dot += softplus1(z.x) * w[k].x + softplus1(z.y) * w[k].y + softplus1(z.z) * w[k].z + softplus1(z.w) * w[k].w;
-      s[k] = make_float4(sigmoid1(z.x), sigmoid1(z.y), sigmoid1(z.z), sigmoid1(z.w));
+      const SpSg a = softplus_sigmoid(z.x), b = softplus_sigmoid(z.y), c = softplus_sigmoid(z.z), d = softplus_sigmoid(z.w);
+      dot += a.sp * w[k].x + b.sp * w[k].y + c.sp * w[k].z + d.sp * w[k].w;
+      s[k] = make_float4(a.sg, b.sg, c.sg, d.sg);
     }
-    const float z2 = warp_sum(dot) + bias;
-    const float sg = sigmoid1(z2);
-    if (lane == 0) { sigma[r] = softplus1(z2); s2_out[r] = sg; }
+    const SpSg h = softplus_sigmoid(warp_sum(dot) + bias);
+    const float sg = h.sg;
+    if (lane == 0) { sigma[r] = h.sp; s2_out[r] = sg; }
 #pragma unroll
     for (int k = 0; k < K; k++)
       __stcs(reinterpret_cast<float4*>(t + r * W) + k * 32 + lane,
@@ -80,8 +96,9 @@ __global__ void __launch_bounds__(256) density_head_bw_kernel(const float* __res
     for (int k = 0; k < K; k++) {
       const float4 z = __ldcs(reinterpret_cast<const float4*>(z1 + r * W) + k * 32 + lane);
       const float4 vv = v ? __ldcs(reinterpret_cast<const float4*>(v + r * W) + k * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s[k] = make_float4(sigmoid1(z.x), sigmoid1(z.y), sigmoid1(z.z), sigmoid1(z.w));
-      a[k] = make_float4(softplus1(z.x), softplus1(z.y), softplus1(z.z), softplus1(z.w));
+      const SpSg p0 = softplus_sigmoid(z.x), p1 = softplus_sigmoid(z.y), p2 = softplus_sigmoid(z.z), p3 = softplus_sigmoid(z.w);
+      s[k] = make_float4(p0.sg, p1.sg, p2.sg, p3.sg);
+      a[k] = make_float4(p0.sp, p1.sp, p2.sp, p3.sp);
       uv[k] = make_float4(s[k].x * vv.x, s[k].y * vv.y, s[k].z * vv.z, s[k].w * vv.w);
       dot += uv[k].x * w[k].x + uv[k].y * w[k].y + uv[k].z * w[k].z + uv[k].w * w[k].w;
     }
