@@ -141,6 +141,22 @@ class _OccupancyMixin:
         vren.packbits_dthr(self.density_grid, thr, self.density_bitfield)
 
 
+class _tf32_matmul:
+    """`with _tf32_matmul(on):` — fp32 GEMMs of the enclosed torch calls run on the tensor cores as TF32; the process-wide
+    torch switch is restored on exit, so nothing outside the density net changes precision."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 class _DensityNormalsFn(torch.autograd.Function):
     """(sigma (N), g_e (N,D) = d sigma / d e) of the reference's torch density net
         sigma = Softplus(Linear(W,1)(Softplus(Linear(D,W)(e))))                       (networks.py:54-59,172-181)
@@ -150,19 +166,22 @@ class _DensityNormalsFn(torch.autograd.Function):
     there) between the GEMMs with W1, which stay on cuBLAS."""
 
     @staticmethod
-    def forward(ctx, e, W1, b1, W2, b2):
+    def forward(ctx, e, W1, b1, W2, b2, tf32=True):
         from . import _lib
         from ._lib import lib, ptr, check, stream
         _lib.require_device()
         e = e.contiguous()
         n, W = e.shape[0], W1.shape[0]
-        z1 = torch.addmm(b1, e, W1.t())
+        ctx.tf32 = tf32
+        with _tf32_matmul(tf32):
+            z1 = torch.addmm(b1, e, W1.t())
         sigma = torch.empty(n, device=e.device); s2 = torch.empty(n, device=e.device)
         t = torch.empty(n, W, device=e.device)
         w2 = W2.reshape(-1).contiguous()
         check(lib.ngp_density_head_fw(ptr(z1), ptr(w2), ptr(b2.contiguous()), n, W, ptr(sigma), ptr(s2), ptr(t), stream()),
               "density_head_fw")
-        g_e = t @ W1
+        with _tf32_matmul(tf32):
+            g_e = t @ W1
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(e, W1, w2, z1, s2, t)
         return sigma, g_e
@@ -173,16 +192,18 @@ class _DensityNormalsFn(torch.autograd.Function):
         from ._lib import lib, ptr, check, stream
         e, W1, w2, z1, s2, t = ctx.saved_tensors
         n, W = z1.shape
-        v = (dg.contiguous() @ W1.t()) if dg is not None else None
+        with _tf32_matmul(ctx.tf32):
+            v = (dg.contiguous() @ W1.t()) if dg is not None else None
         dz1 = torch.empty_like(z1); dz2 = torch.empty(n, device=z1.device)
         dw2 = torch.zeros(W, device=z1.device); db1 = torch.zeros(W, device=z1.device)
         check(lib.ngp_density_head_bw(ptr(z1), ptr(v), ptr(s2), ptr(dsigma.contiguous() if dsigma is not None else None), ptr(w2), n, W,
                                       ptr(dz1), ptr(dz2), ptr(dw2), ptr(db1), stream()), "density_head_bw")
-        de = dz1 @ W1 if ctx.needs_input_grad[0] else None
-        dW1 = dz1.t() @ e
-        if dg is not None:
-            dW1.addmm_(t.t(), dg)
-        return de, dW1, db1, dw2[None], dz2.sum()[None]
+        with _tf32_matmul(ctx.tf32):
+            de = dz1 @ W1 if ctx.needs_input_grad[0] else None
+            dW1 = dz1.t() @ e
+            if dg is not None:
+                dW1.addmm_(t.t(), dg)
+        return de, dW1, db1, dw2[None], dz2.sum()[None], None
 
 
 class NGP(nn.Module, _OccupancyMixin):
@@ -193,9 +214,8 @@ class NGP(nn.Module, _OccupancyMixin):
         # Softplus, double-differentiated for the normals, networks.py:54-59): its fp32 matmuls run on the SIMT pipe by
         # default (76 ms of a 340 ms step at 14 M samples, tools/step_profile_ngp.py).  TF32 puts them on the tensor
         # cores — the precision class SURVEY.md a12 states for this net; every other head already rounds to bf16.
-        # Process-wide torch switch, set here once; pass density_net_tf32=False to leave torch's default alone.
-        if density_net_tf32:
-            torch.backends.cuda.matmul.allow_tf32 = True
+        # torch's switch is process-wide, so it is flipped only around this net's own GEMMs (_tf32_matmul) and restored.
+        self.density_net_tf32 = density_net_tf32
         self.rgb_act = rgb_act
         self.use_skybox = use_skybox
         self.embed_a = embed_a
@@ -238,7 +258,7 @@ class NGP(nn.Module, _OccupancyMixin):
     def density(self, x, return_feat=False, grad=True, grad_feat=True):
         """sigmas (N) [, feat_rgb (N, L*F)] for x (N,3) in [-scale, scale]  (networks.py:165-184)."""
         x, ab = x.contiguous(), self.aabb()              # (x - xyz_min) / (xyz_max - xyz_min) happens inside the grid kernels
-        with torch.set_grad_enabled(grad and torch.is_grad_enabled()):
+        with torch.set_grad_enabled(grad and torch.is_grad_enabled()), _tf32_matmul(self.density_net_tf32):
             sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(x, ab))[:, 0])
         if not return_feat:
             return sigmas
@@ -254,7 +274,7 @@ class NGP(nn.Module, _OccupancyMixin):
         enc = self.xyz_encoder(x, ab)
         l0, l2 = self.xyz_net[0], self.xyz_net[2]
         if self.fused_density_head and enc.is_cuda and enc.dtype == torch.float32 and l0.out_features % 128 == 0 and l0.out_features <= 512:
-            sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias)
+            sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias, self.density_net_tf32)
         else:       # any other density net: generic autograd double backward, as the reference does it
             sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
             (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)

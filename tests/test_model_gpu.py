@@ -42,7 +42,7 @@ def _oracle_field(m, x, d, embed=None):
 
 @pytest.mark.parametrize("embed_a", [False, True])
 def test_ngp_field_matches_torch_restatement(embed_a):
-    m = _small_ngp(embed_a=embed_a, embed_a_len=8, classes=7)
+    m = _small_ngp(embed_a=embed_a, embed_a_len=8, classes=7, density_net_tf32=False)     # fp32 density GEMMs on both sides
     g = torch.Generator(device="cuda").manual_seed(1)
     n = 3000
     x = (torch.rand(n, 3, device="cuda", generator=g) - 0.5) * 0.98
@@ -222,7 +222,7 @@ def test_density_head_matches_autograd_double_backward(width):
         e[0] = 40.0                                   # drives pre-activations past softplus' linear threshold (20)
         ds, dg = rnd(n), rnd(n, D)
         ps = [t.clone().requires_grad_(True) for t in (e, W1, b1, W2, b2)]
-        sig, ge = _DensityNormalsFn.apply(*ps)
+        sig, ge = _DensityNormalsFn.apply(*ps, False)          # fp32 GEMMs
         grads = torch.autograd.grad((sig * ds).sum() + (ge * dg).sum(), ps)
         po = [t.double().clone().requires_grad_(True) for t in (e, W1, b1, W2, b2)]
         o_sig = F.softplus(F.linear(F.softplus(F.linear(po[0], po[1], po[2])), po[3], po[4]))[:, 0]
@@ -233,9 +233,17 @@ def test_density_head_matches_autograd_double_backward(width):
         for name, a, b in zip(("e", "W1", "b1", "W2", "b2"), grads, o_grads):
             assert a.shape == b.shape and rel(a, b) < 1e-4, (name, rel(a, b))
         # sigma-only upstream (density evaluation without normals) and normals-only upstream
-        sig, ge = _DensityNormalsFn.apply(*ps)
+        sig, ge = _DensityNormalsFn.apply(*ps, False)
         (g_w1,) = torch.autograd.grad((sig * ds).sum(), ps[1])
         (o_w1,) = torch.autograd.grad((F.softplus(F.linear(F.softplus(F.linear(po[0], po[1], po[2])), po[3], po[4]))[:, 0] * ds.double()).sum(), po[1])
         assert rel(g_w1, o_w1) < 1e-4
+        # the default: the net's own GEMMs as TF32 (10-bit mantissa operands) — 3e-3 of each tensor's norm — and the
+        # process-wide switch is back to what it was afterwards
+        sig, ge = _DensityNormalsFn.apply(*ps)
+        grads = torch.autograd.grad((sig * ds).sum() + (ge * dg).sum(), ps)
+        assert torch.backends.cuda.matmul.allow_tf32 is False
+        assert rel(sig, o_sig) < 3e-3 and rel(ge, o_ge) < 3e-3
+        for name, a, b in zip(("e", "W1", "b1", "W2", "b2"), grads, o_grads):
+            assert rel(a, b) < 3e-3, (name, rel(a, b))
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
