@@ -278,7 +278,10 @@ __device__ __forceinline__ void flush_cell(const CellAcc<F>& c, uint32_t xh, flo
 // exactly what a (run of samples, level chunk) lane pair reads, and what a row-per-thread MLP epilogue writes coalesced.
 // H2: the table gradient of the double backward (dtable += d(g2 . dL/dx)/dtable): the same run-merged scatter with the
 // corner weight replaced by the coefficient `coef` of hashgrid_fw_kernel<.., H2>; dy is then the FIRST-order upstream.
-template <int F, int LC, bool DYT, bool H2 = false>
+// PF: software pipelining of the run loop — the rows (x, dL/dy[, g2]) of sample j+1 are requested before sample j is
+// processed.  In chunk-major order they come from DRAM on every chunk sweep and 69 % of the stall samples sat on their
+// first use (ncu r01e, street shape, profiles/r01e_ncu_street_scatter_order1.txt + per-line profile); costs 7 registers.
+template <int F, int LC, bool DYT, bool H2 = false, bool PF = false>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt,
                                                                  const float* __restrict__ g2 = nullptr) {
@@ -297,26 +300,37 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
     return DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)((l0 * F) >> 3) * (128 * 8) + (i & 127) * 8 + ((l0 * F) & 7)
                : dy + i * LF + (int64_t)l0 * F;
   };
+  struct Row { float x, y, z, hx, hy, hz, g[LC * F]; };
+  const bool vec4 = l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0;
+  auto load_row = [&](int64_t i, Row& r) {
+    r.x = __ldg(x + 3 * i); r.y = __ldg(x + 3 * i + 1); r.z = __ldg(x + 3 * i + 2);
+    r.hx = r.hy = r.hz = 0.f;
+    if (H2) { r.hx = __ldg(g2 + 3 * i); r.hy = __ldg(g2 + 3 * i + 1); r.hz = __ldg(g2 + 3 * i + 2); }
+    const float* src = dy_row(i);
+    if (vec4) {
+#pragma unroll
+      for (int k = 0; k < LC * F; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+        r.g[k] = v.x; r.g[k + 1] = v.y; r.g[k + 2] = v.z; r.g[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < LC * F; k++) r.g[k] = (l0 * F + k < LF) ? __ldg(src + k) : 0.f;
+    }
+  };
+  Row nxt;
+  if (PF) load_row(s0, nxt);
 #pragma unroll 1
   for (int j = 0; j < spt; j++) {
     const int64_t i = s0 + j;
     if (i >= n) break;
-    float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+    Row cur;
+    if (PF) { cur = nxt; if (j + 1 < spt && i + 1 < n) load_row(i + 1, nxt); }
+    else load_row(i, cur);
+    float xx = cur.x, xy = cur.y, xz = cur.z;
     to_unit(m, xx, xy, xz);
-    float hx = 0.f, hy = 0.f, hz = 0.f;
-    if (H2) { hx = __ldg(g2 + 3 * i); hy = __ldg(g2 + 3 * i + 1); hz = __ldg(g2 + 3 * i + 2); }
-    const float* src = dy_row(i);
-    float g[LC * F];
-    if (l0 + LC <= m.n_levels && (LF & 3) == 0 && ((l0 * F) & 3) == 0) {
-#pragma unroll
-      for (int k = 0; k < LC * F; k += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
-        g[k] = v.x; g[k + 1] = v.y; g[k + 2] = v.z; g[k + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < LC * F; k++) g[k] = (l0 * F + k < LF) ? __ldg(src + k) : 0.f;
-    }
+    const float hx = cur.hx, hy = cur.hy, hz = cur.hz;
+    const float* g = cur.g;
 #pragma unroll
     for (int li = 0; li < LC; li++) {
       const int l = l0 + li;
@@ -509,6 +523,11 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
 // Block order of the gather / scatter launches (GridMeta::chunk_major): chunk-major once the table no longer fits the
 // L2 with room for the streamed rows.  NGP_HASH_ORDER=0|1 overrides (tools/hash_order_probe.py).
 constexpr size_t kL2ResidentTableBytes = 72u << 20;
+// software-pipelined scatter (PF): where the rows come from DRAM, i.e. in chunk-major order; NGP_HASH_PF=0|1 overrides
+static bool use_pf(const GridMeta& m) {
+  const char* e = getenv("NGP_HASH_PF");
+  return e ? atoi(e) != 0 : m.chunk_major != 0;
+}
 static void set_block_order(GridMeta& m, size_t entry_bytes, int64_t n_sblocks) {
   const char* e = getenv("NGP_HASH_ORDER");
   m.chunk_major = e ? atoi(e) != 0 : (size_t)m.offset[m.n_levels] * entry_bytes > kL2ResidentTableBytes;
@@ -588,6 +607,7 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, spt), 64));
     if (F == 8 && (n_levels * F) % 4 == 0) hashgrid_bw_params_f8_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    else if (use_pf(m)) hashgrid_bw_params_kernel<F, LC, false, false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     else hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params");
@@ -680,6 +700,7 @@ NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, cons
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
     if (F == 8) hashgrid_bw_params_f8_kernel<true, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
+    else if (use_pf(m)) hashgrid_bw_params_kernel<F, LC, true, false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
     else hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");
