@@ -19,24 +19,29 @@ def _worker(rank, world, port, out):
     from ngp_b200.trainer import Trainer
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
-    tr = Trainer(model, lr=1e-2, world_size=world)
+    emb = torch.nn.Embedding(4, 6)                                # trained outside the field (appearance embedding, train.py:117-119)
+    tr = Trainer(model, lr=1e-2, world_size=world, extra_params=emb.parameters())
     g = torch.Generator().manual_seed(1)
     x = torch.randn(64, 6, generator=g); y = torch.randn(64, 3, generator=g)
+    img = torch.randint(4, (64,), generator=g)
     shard = slice(rank * 32, (rank + 1) * 32)                     # rays shard, parameters replicate
-    loss = ((model(x[shard]) - y[shard]) ** 2).mean()
+    loss = ((model(x[shard] + emb(img[shard])) - y[shard]) ** 2).mean()
     tr.opt.zero_grad(); loss.backward(); tr.allreduce_grads()
-    grads = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    every = list(model.parameters()) + list(emb.parameters())
+    grads = torch.cat([p.grad.reshape(-1) for p in every])
     tr.opt.step()
-    params = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    params = torch.cat([p.detach().reshape(-1) for p in every])
     if rank == 0:
         # union-batch reference on one process
         torch.manual_seed(0)
         ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
-        opt = torch.optim.Adam(ref.parameters(), lr=1e-2, eps=1e-15)
-        ((ref(x) - y) ** 2).mean().backward()
-        rg = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+        remb = torch.nn.Embedding(4, 6)
+        rall = list(ref.parameters()) + list(remb.parameters())
+        opt = torch.optim.Adam(rall, lr=1e-2, eps=1e-15)
+        ((ref(x + remb(img)) - y) ** 2).mean().backward()
+        rg = torch.cat([p.grad.reshape(-1) for p in rall])
         opt.step()
-        rp = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+        rp = torch.cat([p.detach().reshape(-1) for p in rall])
         torch.save(dict(g=grads, rg=rg, p=params, rp=rp), out)
     gathered = [torch.zeros_like(params) for _ in range(world)]
     dist.all_gather(gathered, params)
