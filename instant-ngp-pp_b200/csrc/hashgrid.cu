@@ -439,43 +439,64 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float*
 
 // ----------------------------------------------------------------------------------- bw (input)
 // dL/dx_d = sum_l scale_l * sum_f dL/dy_{l,f} * sum_{corners of the other two dims} w_other * (v[d=1]-v[d=0])
+// Lane pairs as in hashgrid_fw_kernel: lane xh fetches the four corners with x = px + xh (one L1 line lookup for the two
+// x-neighbours of a corner pair instead of two), forms d_p = dL/dy . v_p for them, and contributes
+//     gx += scale * s_x * sum_p w_y w_z d_p          (s_x = +1 for xh = 1, -1 for xh = 0)
+//     gy += scale * w_x * sum_z w_z (d[y=1] - d[y=0]) ,  gz likewise;
+// the two lanes' partial sums over ALL levels meet through three shuffles at the end.  The first version (thread per
+// sample, eight 32-byte gathers per level for F = 8) took 10.5 ms on 14 M samples against 6.3 ms for the forward gather.
 template <int F, typename TP>
 __global__ void __launch_bounds__(256) hashgrid_bw_input_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                 const TP* __restrict__ table, GridMeta m, int64_t n,
                                                                 float* __restrict__ dx) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float xx = __ldg(x + 3 * i), xy = __ldg(x + 3 * i + 1), xz = __ldg(x + 3 * i + 2);
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1);
+  const uint32_t xh = threadIdx.x & 1u;
+  const bool in_range = i < n;
+  const int64_t ii = in_range ? i : n - 1;          // out-of-range lanes still take part in the pair shuffles
+  float xx = __ldg(x + 3 * ii), xy = __ldg(x + 3 * ii + 1), xz = __ldg(x + 3 * ii + 2);
   to_unit(m, xx, xy, xz);
   const int LF = m.n_levels * F;
+  const float sx = xh ? 1.f : -1.f;
   float gx = 0.f, gy = 0.f, gz = 0.f;
   for (int l = 0; l < m.n_levels; l++) {
     const Cell c = locate(xx, xy, xz, m.scale[l]);
     const TP* base = table + (size_t)m.offset[l] * F;
-    const uint32_t res = m.res[l], size = m.size[l];
-    const bool dense = m.dense[l];
     float g[F];
+    const float* gp = dy + ii * LF + l * F;
+    if constexpr (F % 4 == 0) {
+      if ((LF & 3) == 0) {
 #pragma unroll
-    for (int f = 0; f < F; f++) g[f] = __ldg(dy + i * LF + l * F + f);
-    float d[8];  // d[k] = sum_f g_f * v[k][f]
+        for (int f = 0; f < F; f += 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(gp + f)); g[f] = v.x; g[f + 1] = v.y; g[f + 2] = v.z; g[f + 3] = v.w; }
+      } else {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const uint32_t idx = grid_index(c.px + (k & 1), c.py + ((k >> 1) & 1), c.pz + ((k >> 2) & 1), res, size, dense);
-      float v[F];
-      Vec<F, TP>::ld(base + (size_t)idx * F, v);
+        for (int f = 0; f < F; f++) g[f] = __ldg(gp + f);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; f++) g[f] = __ldg(gp + f);
+    }
+    uint32_t idx[4];
+    corner4(c.px + xh, c.py, c.pz, m.res[l], m.size[l], m.dense[l], idx);
+    float v[4][F], d[4];      // p: bit0 = y, bit1 = z
+#pragma unroll
+    for (int p = 0; p < 4; p++) Vec<F, TP>::ld(base + (size_t)idx[p] * F, v[p]);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
       float a = 0.f;
 #pragma unroll
-      for (int f = 0; f < F; f++) a = fmaf(g[f], v[f], a);
-      d[k] = a;
+      for (int f = 0; f < F; f++) a = fmaf(g[f], v[p][f], a);
+      d[p] = a;
     }
-    const float ax = 1.f - c.wx, ay = 1.f - c.wy, az = 1.f - c.wz;
+    const float ay = 1.f - c.wy, az = 1.f - c.wz, wxs = xh ? c.wx : 1.f - c.wx;
     const float s = m.scale[l];
-    // k bit0 = x, bit1 = y, bit2 = z
-    gx += s * (ay * az * (d[1] - d[0]) + c.wy * az * (d[3] - d[2]) + ay * c.wz * (d[5] - d[4]) + c.wy * c.wz * (d[7] - d[6]));
-    gy += s * (ax * az * (d[2] - d[0]) + c.wx * az * (d[3] - d[1]) + ax * c.wz * (d[6] - d[4]) + c.wx * c.wz * (d[7] - d[5]));
-    gz += s * (ax * ay * (d[4] - d[0]) + c.wx * ay * (d[5] - d[1]) + ax * c.wy * (d[6] - d[2]) + c.wx * c.wy * (d[7] - d[3]));
+    gx += s * sx * (ay * az * d[0] + c.wy * az * d[1] + ay * c.wz * d[2] + c.wy * c.wz * d[3]);
+    gy += s * wxs * (az * (d[1] - d[0]) + c.wz * (d[3] - d[2]));
+    gz += s * wxs * (ay * (d[2] - d[0]) + c.wy * (d[3] - d[1]));
   }
-  dx[3 * i] = gx; dx[3 * i + 1] = gy; dx[3 * i + 2] = gz;
+  gx += __shfl_xor_sync(0xffffffffu, gx, 1);
+  gy += __shfl_xor_sync(0xffffffffu, gy, 1);
+  gz += __shfl_xor_sync(0xffffffffu, gz, 1);
+  if (xh == 0 && in_range) { dx[3 * i] = gx; dx[3 * i + 1] = gy; dx[3 * i + 2] = gz; }
 }
 
 // ----------------------------------------------------------------------------------- double bw
@@ -624,7 +645,7 @@ NGP_API int ngp_hashgrid_bw_input(const float* x, const float* aabb, const float
     return set_error_msg("ngp_hashgrid_bw_input: bad grid config");
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
-    const unsigned grid = (unsigned)ceil_div(n, 256);
+    const unsigned grid = (unsigned)ceil_div(n, 128);        // lane pair per sample
     if (table_dtype == 0) hashgrid_bw_input_kernel<F, float><<<grid, 256, 0, st>>>(x, dL_dy, (const float*)table, m, n, dL_dx);
     else hashgrid_bw_input_kernel<F, __half><<<grid, 256, 0, st>>>(x, dL_dy, (const __half*)table, m, n, dL_dx);
   });
