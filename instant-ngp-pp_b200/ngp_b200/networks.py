@@ -206,6 +206,55 @@ class _DensityNormalsFn(torch.autograd.Function):
         return de, dW1, db1, dw2[None], dz2.sum()[None], None
 
 
+class _TwoHeadsFn(torch.autograd.Function):
+    """norm_pred_header(feat) and semantic_header(feat) (networks.py:101-123: two bias-free MLPs  D -> 32 -> 3  and
+    D -> 32 -> C  on the SAME feature matrix) evaluated as ONE block-structured MLP  D -> 64 -> (3 + C):
+        W1 = [W1_norm ; W1_sem]          Wout = [[Wout_norm, 0], [0, Wout_sem]]
+    — bit for bit the same products and sums per output (the zero blocks add exact zeros), one pass over the (S, D)
+    features instead of two in each direction, and ONE dL/dfeat instead of two matrices that autograd then adds.
+    The gradient of the merged parameter vector is sliced back into the two heads' own `.params` (the cross blocks'
+    gradients are discarded: those weights do not exist)."""
+
+    @staticmethod
+    def _merge(pn, ps, D, H, C):
+        nop = 16
+        W1 = torch.cat([pn[:H * D].view(H, D), ps[:H * D].view(H, D)], 0)
+        Wo = torch.zeros(nop, 2 * H, device=pn.device, dtype=pn.dtype)
+        Wo[:3, :H] = pn[H * D:].view(nop, H)[:3]
+        Wo[3:3 + C, H:] = ps[H * D:].view(nop, H)[:C]
+        return torch.cat([W1.reshape(-1), Wo.reshape(-1)])
+
+    @staticmethod
+    def forward(ctx, feat, pn, ps, m_norm, m_sem):
+        from . import _lib
+        _lib.require_device()
+        feat = feat.contiguous()
+        D, H, C = feat.shape[1], m_norm.width, m_sem.n_out
+        merged = _TwoHeadsFn._merge(pn.detach(), ps.detach(), D, H, C)
+        m = tcnn.MlpConfig(D, 3 + C, {"otype": "CutlassMLP", "activation": "ReLU", "output_activation": "None",
+                                      "n_neurons": 2 * H, "n_hidden_layers": 1})
+        out = tcnn.mlp_forward([(feat, D, 0)], merged, m)
+        ctx.m, ctx.dims = m, (D, H, C)
+        ctx.save_for_backward(feat, merged, out)
+        return out[:, :3], out[:, 3:]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dn, ds):
+        feat, merged, out = ctx.saved_tensors
+        D, H, C = ctx.dims
+        dout = torch.cat([dn if dn is not None else torch.zeros_like(out[:, :3]),
+                          ds if ds is not None else torch.zeros_like(out[:, 3:])], 1)
+        dmerged, dsegs = tcnn.mlp_backward([(feat, D, 0)], merged, ctx.m, dout, [ctx.needs_input_grad[0]], saved_out=out)
+        dW1 = dmerged[:2 * H * D].view(2 * H, D)
+        dWo = dmerged[2 * H * D:].view(16, 2 * H)
+        dpn = torch.zeros(H * D + 16 * H, device=feat.device); dps = torch.zeros_like(dpn)
+        dpn[:H * D] = dW1[:H].reshape(-1); dps[:H * D] = dW1[H:].reshape(-1)
+        dpn[H * D:].view(16, H)[:3] = dWo[:3, :H]
+        dps[H * D:].view(16, H)[:C] = dWo[3:3 + C, H:]
+        return dsegs[0], dpn, dps, None, None
+
+
 class NGP(nn.Module, _OccupancyMixin):
     def __init__(self, scale, rgb_act="Sigmoid", use_skybox=False, embed_a=False, embed_a_len=12, classes=7,
                  grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16, density_net_tf32=True):
@@ -299,6 +348,17 @@ class NGP(nn.Module, _OccupancyMixin):
             rgbs = TruncExp.apply(rgbs) if kwargs.get("output_radiance", False) else self.log_radiance_to_rgb(rgbs, **kwargs)
         return rgbs
 
+    fused_aux_heads = True        # normal + semantic heads as one block-structured MLP (_TwoHeadsFn)
+
+    def _aux_heads(self, feat_rgb):
+        """-> (norm_pred_header(feat), semantic_header(feat)) raw outputs."""
+        a, b = self.norm_pred_header, self.semantic_header
+        ma, mb = a.mlp, b.mlp
+        if (self.fused_aux_heads and feat_rgb.is_cuda and ma.width == mb.width and ma.n_hidden == mb.n_hidden == 1 and 2 * ma.width <= 128
+                and ma.act_h == mb.act_h == tcnn.ACT["ReLU"] and ma.act_o == mb.act_o == tcnn.ACT["None"] and 3 + mb.n_out <= 16):
+            return _TwoHeadsFn.apply(feat_rgb, a.params, b.params, ma, mb)
+        return a(feat_rgb), b(feat_rgb)
+
     def log_radiance_to_rgb(self, log_radiances, **kwargs):
         out = [getattr(self, f"tonemapper_net_{i}")(log_radiances[:, i:i + 1]) for i in range(3)]
         return torch.cat(out, 1)
@@ -307,8 +367,9 @@ class NGP(nn.Module, _OccupancyMixin):
         """-> sigmas (N), rgbs (N,3), normals_raw (N,3), normals_pred (N,3), semantic (N,C)  (networks.py:198-240)"""
         sigmas, feat_rgb, grads = self.grad(x)
         normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
-        normals_pred = -F.normalize(self.norm_pred_header(feat_rgb), p=2, dim=-1, eps=1e-6)
-        semantic = self.semantic_act(self.semantic_header(feat_rgb))
+        n_out, s_out = self._aux_heads(feat_rgb)
+        normals_pred = -F.normalize(n_out, p=2, dim=-1, eps=1e-6)
+        semantic = self.semantic_act(s_out)
         rgbs = self._rgb(d, feat_rgb, kwargs)
         return sigmas, rgbs, normals_raw, normals_pred, semantic
 
@@ -320,8 +381,9 @@ class NGP(nn.Module, _OccupancyMixin):
         sigmas, feat_rgb, grads = sigmas.detach(), feat_rgb.detach(), grads.detach()
         with torch.no_grad():
             normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
-            normals_pred = -F.normalize(self.norm_pred_header(feat_rgb), p=2, dim=-1, eps=1e-6)
-            semantic = self.semantic_act(self.semantic_header(feat_rgb))
+            n_out, s_out = self._aux_heads(feat_rgb)
+            normals_pred = -F.normalize(n_out, p=2, dim=-1, eps=1e-6)
+            semantic = self.semantic_act(s_out)
             rgbs = self._rgb(d, feat_rgb, kwargs)
         return sigmas, rgbs, normals_pred, normals_raw, semantic
 

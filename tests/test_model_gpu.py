@@ -247,3 +247,31 @@ def test_density_head_matches_autograd_double_backward(width):
             assert rel(a, b) < 3e-3, (name, rel(a, b))
     finally:
         torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_fused_aux_heads_equal_the_two_separate_heads():
+    """NGP._aux_heads: norm_pred_header + semantic_header as one block-structured MLP (_TwoHeadsFn) against the two
+    separate tcnn.Network calls the reference makes (networks.py:221-224): same outputs (the zero blocks add exact
+    zeros: 1e-6 absolute) and the same gradients for the features and for BOTH heads' own parameter vectors."""
+    m = _small_ngp(classes=7)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n = 5000
+    feat = (torch.randn(n, m.rgb_encoder.n_output_dims, device="cuda", generator=g) * 0.5).requires_grad_(True)
+    wn, ws = torch.randn(n, 3, device="cuda", generator=g), torch.randn(n, 7, device="cuda", generator=g)
+    ps = [feat, m.norm_pred_header.params, m.semantic_header.params]
+    m.fused_aux_heads = True
+    a1, b1 = m._aux_heads(feat)
+    g1 = torch.autograd.grad((a1 * wn).sum() + (b1 * ws).sum(), ps)
+    m.fused_aux_heads = False
+    a0, b0 = m._aux_heads(feat)
+    g0 = torch.autograd.grad((a0 * wn).sum() + (b0 * ws).sum(), ps)
+    assert a1.shape == (n, 3) and b1.shape == (n, 7)
+    assert float((a1 - a0).abs().max()) < 1e-6 and float((b1 - b0).abs().max()) < 1e-6
+    rel = lambda x, y: float((x - y).norm() / (y.norm() + 1e-20))
+    assert rel(g1[0], g0[0]) < 2e-3          # dL/dfeat: one bf16-operand backward instead of the sum of two
+    assert g1[1].shape == g0[1].shape and rel(g1[1], g0[1]) < 1e-4
+    assert g1[2].shape == g0[2].shape and rel(g1[2], g0[2]) < 1e-4
+    # only one head used downstream (the other upstream gradient is None)
+    a1, b1 = (setattr(m, "fused_aux_heads", True), m._aux_heads(feat))[1]
+    (gs,) = torch.autograd.grad((b1 * ws).sum(), m.semantic_header.params)
+    assert rel(gs, g0[2]) < 1e-4
