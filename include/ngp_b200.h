@@ -200,6 +200,13 @@ int ngp_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream)
 int ngp_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ a14: per-ray tensors repeated per sample
+ * torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)  models/rendering.py:217-219 (appearance embeddings) and its
+ * backward.  v (., W) f32, rays_a (R,3) i64 [ray_idx, start_idx, N_samples], out / dout (S,W); W <= 32;
+ * reduce accumulates (+=) into dv (caller zeroes). */
+int ngp_expand_per_ray(const float* v, const int64_t* rays_a, int64_t n_rays, int width, float* out, void* stream);
+int ngp_reduce_per_ray(const float* dout, const int64_t* rays_a, int64_t n_rays, int width, float* dv, void* stream);
+
 /* ------------------------------------------------------------------ a12/a13: density net with analytic normals
  * The elementwise stages of the reference's torch density net  models/networks.py:54-59 (xyz_net = Linear -> Softplus ->
  * Linear(.,1), sigma_act Softplus) together with d sigma / d(encoding) of networks.py:186-196 and the backward of both

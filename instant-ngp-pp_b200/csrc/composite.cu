@@ -350,3 +350,58 @@ NGP_API int ngp_composite_test_fw(const float* sigmas, const float* rgbs, const 
   NGP_LAUNCH_CHECK("ngp_composite_test_fw");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------- per-ray -> per-sample
+// Per-ray tensors (appearance embeddings, ...) repeated for every sample of their ray: models/rendering.py:217-219
+//     kwargs[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)
+// = an index, a repeats -> indices kernel and an index_select whose gather kernel runs one CTA per output row (3.6 ms
+// for 14 M rows of 8 floats, twice per step, profiles/r01e_step_profile_playground_after.txt); the backward is an
+// index_add.  Here: one warp per ray in both directions; a ray's rows are contiguous in the packed sample order, so
+// the stores / loads of a warp are contiguous runs.  W <= 32 floats per row.
+namespace ngp {
+__global__ void __launch_bounds__(256) expand_per_ray_kernel(const float* __restrict__ v, const int64_t* __restrict__ rays_a,
+                                                             int64_t n_rays, int W, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / W, c = lane - sub * W, per = 32 / W;      // `per` rows per warp pass; lanes >= per*W idle
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rays; r += n_warps) {
+    const int64_t ray = __ldg(rays_a + 3 * r), start = __ldg(rays_a + 3 * r + 1), N = __ldg(rays_a + 3 * r + 2);
+    if (sub >= per || N <= 0) continue;
+    const float val = __ldg(v + ray * W + c);
+    for (int64_t k = sub; k < N; k += per) out[(start + k) * W + c] = val;
+  }
+}
+__global__ void __launch_bounds__(256) reduce_per_ray_kernel(const float* __restrict__ dout, const int64_t* __restrict__ rays_a,
+                                                             int64_t n_rays, int W, float* __restrict__ dv) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / W, c = lane - sub * W, per = 32 / W;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rays; r += n_warps) {
+    const int64_t ray = __ldg(rays_a + 3 * r), start = __ldg(rays_a + 3 * r + 1), N = __ldg(rays_a + 3 * r + 2);
+    if (sub >= per || N <= 0) continue;
+    float acc = 0.f;
+    for (int64_t k = sub; k < N; k += per) acc += __ldg(dout + (start + k) * W + c);
+    atomicAdd(dv + ray * W + c, acc);          // <= 32/W partial sums per (ray, column); dv is zeroed by the caller
+  }
+}
+}  // namespace ngp
+
+// out (S,W)[start_r + k] = v (., W)[ray_r] for every ray r of rays_a (R,3) i64 [ray_idx, start_idx, N_samples] and k < N_r
+// (models/rendering.py:217-219).  W <= 32.
+NGP_API int ngp_expand_per_ray(const float* v, const int64_t* rays_a, int64_t n_rays, int width, float* out, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (width < 1 || width > 32) return set_error_msg("ngp_expand_per_ray: width must be in [1, 32]");
+  const int64_t blocks = ceil_div(n_rays, 8);
+  expand_per_ray_kernel<<<(unsigned)(blocks < (int64_t)kSMs * 16 ? blocks : (int64_t)kSMs * 16), 256, 0, (cudaStream_t)stream>>>(v, rays_a, n_rays, width, out);
+  NGP_LAUNCH_CHECK("ngp_expand_per_ray");
+  return 0;
+}
+// Backward of ngp_expand_per_ray: dv (., W)[ray_r] += sum_k dout (S,W)[start_r + k]; the caller zeroes dv.
+NGP_API int ngp_reduce_per_ray(const float* dout, const int64_t* rays_a, int64_t n_rays, int width, float* dv, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (width < 1 || width > 32) return set_error_msg("ngp_reduce_per_ray: width must be in [1, 32]");
+  const int64_t blocks = ceil_div(n_rays, 8);
+  reduce_per_ray_kernel<<<(unsigned)(blocks < (int64_t)kSMs * 16 ? blocks : (int64_t)kSMs * 16), 256, 0, (cudaStream_t)stream>>>(dout, rays_a, n_rays, width, dv);
+  NGP_LAUNCH_CHECK("ngp_reduce_per_ray");
+  return 0;
+}

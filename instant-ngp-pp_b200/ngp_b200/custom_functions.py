@@ -202,3 +202,31 @@ class ReLU(torch.autograd.Function):
     def backward(ctx, g):
         (mask,) = ctx.saved_tensors
         return torch.where(mask, g, torch.full_like(g, 1e-6))
+
+
+class ExpandPerRay(torch.autograd.Function):
+    """Per-ray rows repeated for every sample of their ray — `torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)`
+    of models/rendering.py:217-219 (the appearance embedding) — as one kernel per direction (ngp_expand_per_ray /
+    ngp_reduce_per_ray).  v (R_all, W <= 32) float32, rays_a (R,3) int64, n_samples = rays_a[:, 2].sum()."""
+
+    @staticmethod
+    def forward(ctx, v, rays_a, n_samples):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        v = v.contiguous()
+        out = torch.empty(n_samples, v.shape[1], dtype=torch.float32, device=v.device)
+        check(lib.ngp_expand_per_ray(ptr(v), ptr(rays_a), rays_a.shape[0], v.shape[1], ptr(out), stream()), "expand_per_ray")
+        ctx.save_for_backward(rays_a)
+        ctx.shape = v.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        from ._lib import lib, ptr, check, stream
+        (rays_a,) = ctx.saved_tensors
+        dv = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        check(lib.ngp_reduce_per_ray(ptr(dout.contiguous()), ptr(rays_a), rays_a.shape[0], ctx.shape[1], ptr(dv), stream()),
+              "reduce_per_ray")
+        return dv, None, None

@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from . import vren
-from .custom_functions import RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer, VolumeRendererLite
+from .custom_functions import ExpandPerRay, RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer, VolumeRendererLite
 
 MAX_SAMPLES = 1024      # models/rendering.py:9
 NEAR_DISTANCE = 0.01    # models/rendering.py:10
@@ -203,7 +203,10 @@ def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
     kw = dict(kwargs)
     for k, v in kwargs.items():          # per-ray tensors are repeated per sample (rendering.py:217-219)
         if isinstance(v, torch.Tensor):
-            kw[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0, output_size=xyzs.shape[0])
+            if v.is_cuda and v.dtype == torch.float32 and v.dim() == 2 and v.shape[1] <= 32 and rays_a.is_contiguous():
+                kw[k] = ExpandPerRay.apply(v, rays_a, xyzs.shape[0])
+            else:
+                kw[k] = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0, output_size=xyzs.shape[0])
     sigmas, rgbs, normals_raw, normals_pred, sems = model(xyzs, dirs, **kw)
     results["sigma"], results["xyzs"] = sigmas, xyzs
     lite = normals_pred is None          # field without normal / semantic heads (NGPCompact)

@@ -378,3 +378,28 @@ def test_get_rays_matches_the_reference_formula():
     assert torch.equal(ro2, ro) and torch.equal(rd2, rd)
     ro0, rd0 = ray_utils.get_rays_indexed(dirs, poses, img[:0], pix[:0])          # empty batch
     assert ro0.shape == (0, 3) and rd0.shape == (0, 3)
+
+
+@pytest.mark.parametrize("W", [8, 12, 1, 32])
+def test_expand_per_ray_matches_repeat_interleave(W):
+    """models/rendering.py:217-219: per-ray rows -> per-sample rows, and the backward (segment sums), against torch's
+    repeat_interleave / its autograd; rays with zero samples and a shuffled ray order included.  Forward is a copy
+    (exact); the backward sums a ray's rows in a different order than index_add: 1e-5 relative."""
+    from ngp_b200.custom_functions import ExpandPerRay
+    g = torch.Generator(device="cuda").manual_seed(W)
+    R = 3001
+    N = torch.randint(0, 40, (R,), device="cuda", generator=g)
+    N[::7] = 0
+    start = torch.cumsum(N, 0) - N
+    ray = torch.randperm(R, device="cuda", generator=g)
+    rays_a = torch.stack([ray, start, N], 1).contiguous()
+    S = int(N.sum())
+    v = torch.randn(R, W, device="cuda", generator=g, requires_grad=True)
+    out = ExpandPerRay.apply(v, rays_a, S)
+    ref = torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)
+    assert out.shape == ref.shape == (S, W) and torch.equal(out, ref)
+    w = torch.randn(S, W, device="cuda", generator=g)
+    (g1,) = torch.autograd.grad((out * w).sum(), v)
+    (g0,) = torch.autograd.grad((ref * w).sum(), v)
+    assert torch.allclose(g1, g0, rtol=1e-5, atol=1e-5)
+    assert float(g1[ray[N == 0]].abs().max()) == 0.0
