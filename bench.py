@@ -462,6 +462,8 @@ def gpu_arm(args):
                         "live in L2 at a time; block-order probe in profiles/r01e_hash_block_order_probe.txt" % table_mb)
         roof["traffic"] = None
     cpu, _ = cpu_arm(steps=4, warmup=1)
+    if args.workload != "lego":       # the CPU port implements the headline field only
+        cpu["sample"] = "HEADLINE workload (lego-shaped, ngp_pl-shaped field), not this one: " + cpu["sample"]
     value = world * R * args.steps / t_res
     line = {
         "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
