@@ -160,6 +160,11 @@ int ngp_hashgrid_bw_input(const float* x, const float* aabb, const float* dL_dy,
 int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const float* g2, const float* dL_dy, const void* table, int table_dtype,
                             int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
                             float per_level_scale, int64_t n, float* dtable, float* d_dL_dy, void* stream);
+/* both terms of the table gradient of a field used with its input gradient (density + normals, networks.py:186-196):
+ * dtable += scatter(w, dL_dy) + scatter(coef(g2), dL_dy_first) — one pass for F = 8.  g2 == NULL: first term only. */
+int ngp_hashgrid_bw_params_dual(const float* x, const float* aabb, const float* dL_dy, const float* g2,
+                                const float* dL_dy_first, int n_levels, int n_features, int log2_hashmap_size,
+                                int base_resolution, float per_level_scale, int64_t n, float* dtable, void* stream);
 /* Fused density path of the ngp_pl-shaped field (private layouts, no reference counterpart): the encoder writes bf16
  * features directly as 128-sample tcgen05 operand tiles (ngp_feature_tile_bytes each) which ngp_mlp_fw/bw load with one
  * bulk copy (segment kind 2), and ngp_mlp_bw returns dL/dy as fp32 "gradient tiles" (ceil(N/128)*128*k0p floats,

@@ -375,11 +375,16 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
 // kernel above.  Here the lanes of a pair split the FEATURES instead: lane h owns features 4h..4h+3 of all eight
 // corners, the pair's two float4 reductions to one entry are the same instruction and the same sector = ONE request:
 // 8 requests per (cell, level) instead of 16.  Same run merging, same zero-row skip, same H2 weights.
-template <bool DYT, bool H2>
+// MODE 0: dtable += sum w * dy.  MODE 1 (H2): dtable += sum coef(g2) * dy.  MODE 2 (dual): both terms of the table
+// gradient of a field whose output AND input gradient are used (density + normals, networks.py:186-196) in one pass:
+// dtable += sum w * dy + coef(g2) * dy2 — the two scatters hit the same corners, so the second one's reductions are free.
+template <bool DYT, int MODE>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                     GridMeta m, int64_t n, float* __restrict__ dtable, int spt,
-                                                                    const float* __restrict__ g2 = nullptr) {
+                                                                    const float* __restrict__ g2 = nullptr,
+                                                                    const float* __restrict__ dy2 = nullptr) {
   constexpr int F = 8;
+  constexpr bool H2 = MODE != 0;
   uint32_t sblock; int l;
   block_coords(m, m.n_levels, sblock, l);                   // one level per lane pair
   const int64_t s0 = ((int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
@@ -410,11 +415,15 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float*
     to_unit(m, xx, xy, xz);
     float hx = 0.f, hy = 0.f, hz = 0.f;
     if (H2) { hx = __ldg(g2 + 3 * i); hy = __ldg(g2 + 3 * i + 1); hz = __ldg(g2 + 3 * i + 2); }
-    const float* src = DYT ? dy + (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)l * (128 * 8) + (i & 127) * 8 + fh
-                           : dy + i * LF + (int64_t)l * F + fh;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(src));
-    bool any = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
-    if (H2) any = any && (hx != 0.f || hy != 0.f || hz != 0.f);
+    const int64_t off = DYT ? (i >> 7) * (int64_t)(128 * m.k0p) + (int64_t)l * (128 * 8) + (i & 127) * 8 + fh
+                            : i * LF + (int64_t)l * F + fh;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy + off));
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);            // MODE 2: the rows weighted by coef(g2)
+    if (MODE == 2) q = __ldg(reinterpret_cast<const float4*>(dy2 + off));
+    const bool hnz = hx != 0.f || hy != 0.f || hz != 0.f;
+    const bool gnz = g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f;
+    const bool qnz = q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 0.f;
+    const bool any = MODE == 0 ? gnz : MODE == 1 ? (gnz && hnz) : (gnz || (qnz && hnz));
     if (!any) continue;
     const Cell c = locate(xx, xy, xz, scale);
     if (!has || cx != c.px || cy != c.py || cz != c.pz) {
@@ -427,11 +436,17 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float*
     for (int k = 0; k < 8; k++) {
       const int xb = k >> 2, yb = k & 1, zb = (k >> 1) & 1;
       const float wx = xb ? c.wx : 1.f - c.wx, wy = yb ? c.wy : 1.f - c.wy, wz = zb ? c.wz : 1.f - c.wz;
-      float w;
-      if (H2) w = scale * (hx * (xb ? 1.f : -1.f) * wy * wz + hy * (yb ? 1.f : -1.f) * wx * wz + hz * (zb ? 1.f : -1.f) * wx * wy);
-      else w = wx * wy * wz;
-      a[k][0] = fmaf(w, g.x, a[k][0]); a[k][1] = fmaf(w, g.y, a[k][1]);
-      a[k][2] = fmaf(w, g.z, a[k][2]); a[k][3] = fmaf(w, g.w, a[k][3]);
+      const float w = wx * wy * wz;
+      float coef = 0.f;
+      if (H2) coef = scale * (hx * (xb ? 1.f : -1.f) * wy * wz + hy * (yb ? 1.f : -1.f) * wx * wz + hz * (zb ? 1.f : -1.f) * wx * wy);
+      if (MODE == 2) {
+        a[k][0] = fmaf(coef, q.x, fmaf(w, g.x, a[k][0])); a[k][1] = fmaf(coef, q.y, fmaf(w, g.y, a[k][1]));
+        a[k][2] = fmaf(coef, q.z, fmaf(w, g.z, a[k][2])); a[k][3] = fmaf(coef, q.w, fmaf(w, g.w, a[k][3]));
+      } else {
+        const float u = MODE == 1 ? coef : w;
+        a[k][0] = fmaf(u, g.x, a[k][0]); a[k][1] = fmaf(u, g.y, a[k][1]);
+        a[k][2] = fmaf(u, g.z, a[k][2]); a[k][3] = fmaf(u, g.w, a[k][3]);
+      }
     }
   }
   if (has) flush();
@@ -627,7 +642,7 @@ NGP_API int ngp_hashgrid_bw_params(const float* x, const float* aabb, const floa
     const int spt = e ? atoi(e) : kSPT;
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, spt), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, spt), 64));
-    if (F == 8 && (n_levels * F) % 4 == 0) hashgrid_bw_params_f8_kernel<false, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
+    if (F == 8 && (n_levels * F) % 4 == 0) hashgrid_bw_params_f8_kernel<false, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     else if (use_pf(m)) hashgrid_bw_params_kernel<F, LC, false, false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
     else hashgrid_bw_params_kernel<F, LC, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, spt);
   });
@@ -677,11 +692,36 @@ NGP_API int ngp_hashgrid_bwbw_input(const float* x, const float* aabb, const flo
       constexpr int LC = scatter_levels_per_thread<F>();
       const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
       set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
-      if (F == 8) hashgrid_bw_params_f8_kernel<false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
+      if (F == 8) hashgrid_bw_params_f8_kernel<false, 1><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
       else hashgrid_bw_params_kernel<F, LC, false, true><<<grid, 128, 0, st>>>(x, dL_dy, m, n, dtable, kSPT, g2);
     }
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_bwbw_input");
+  return 0;
+}
+
+// dtable += scatter(w, dL_dy) + scatter(coef(g2), dL_dy_first): BOTH terms of the table gradient of a field evaluated with
+// its input gradient (density + normals, models/networks.py:186-196), where dL_dy is the upstream of the encoding itself,
+// g2 (N,3) the upstream of the input gradient and dL_dy_first (N, L*F) the first-order upstream the input gradient was
+// taken with.  One pass for F = 8 (the two scatters hit the same corners); otherwise the two launches of
+// ngp_hashgrid_bw_params + ngp_hashgrid_bwbw_input back to back.  g2 == NULL: the first term only.
+NGP_API int ngp_hashgrid_bw_params_dual(const float* x, const float* aabb, const float* dL_dy, const float* g2,
+                                        const float* dL_dy_first, int n_levels, int n_features, int log2_hashmap_size,
+                                        int base_resolution, float per_level_scale, int64_t n, float* dtable, void* stream) {
+  if (n <= 0) return 0;
+  if (g2 == nullptr || dL_dy_first == nullptr || n_features != 8) {
+    int rc = ngp_hashgrid_bw_params(x, aabb, dL_dy, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, n, dtable, stream);
+    if (rc || g2 == nullptr || dL_dy_first == nullptr) return rc;
+    return ngp_hashgrid_bwbw_input(x, aabb, g2, dL_dy_first, nullptr, 0, n_levels, n_features, log2_hashmap_size, base_resolution,
+                                   per_level_scale, n, dtable, nullptr, stream);
+  }
+  GridMeta m;
+  if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
+    return set_error_msg("ngp_hashgrid_bw_params_dual: bad grid config");
+  const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * n_levels);
+  set_block_order(m, (size_t)8 * 4, ceil_div(ceil_div(n, kSPT), 64));
+  hashgrid_bw_params_f8_kernel<false, 2><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dL_dy, m, n, dtable, kSPT, g2, dL_dy_first);
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_dual");
   return 0;
 }
 
@@ -720,7 +760,7 @@ NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, cons
     constexpr int LC = scatter_levels_per_thread<F>();
     const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
-    if (F == 8) hashgrid_bw_params_f8_kernel<true, false><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
+    if (F == 8) hashgrid_bw_params_f8_kernel<true, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
     else if (use_pf(m)) hashgrid_bw_params_kernel<F, LC, true, false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
     else hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });

@@ -206,6 +206,71 @@ class _DensityNormalsFn(torch.autograd.Function):
         return de, dW1, db1, dw2[None], dz2.sum()[None], None
 
 
+class _DensityFieldNormalsFn(torch.autograd.Function):
+    """x (N,3) world -> (sigma (N), d sigma / d x_unit (N,3)): hash-grid encoding, density net and the analytic input
+    gradient (models/networks.py:186-196 `grad`: encode, xyz_net, sigma_act, autograd.grad(create_graph=True)) as ONE
+    autograd node.  Forward = gather, GEMM, density_head_fw, GEMM, input-gradient kernel.  Backward, given the upstream
+    of both outputs: double-backward gather (d/d g_e), density_head_bw between the W1 GEMMs, and ONE dual scatter for
+    both terms of the table gradient (ngp_hashgrid_bw_params_dual: the first- and second-order scatters hit the same
+    corners) instead of two.  The result is d sigma / d x in UNIT-CUBE coordinates, like _GridBwFn."""
+
+    @staticmethod
+    def forward(ctx, x, table, W1, b1, W2, b2, grid, aabb, tf32):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        x = x.contiguous()
+        n, W = x.shape[0], W1.shape[0]
+        tb = table.detach()
+        enc = tcnn.grid_forward(x, tb, grid, aabb)
+        with _tf32_matmul(tf32):
+            z1 = torch.addmm(b1, enc, W1.t())
+        sigma = torch.empty(n, device=x.device); s2 = torch.empty(n, device=x.device)
+        t = torch.empty(n, W, device=x.device)
+        w2 = W2.reshape(-1).contiguous()
+        check(lib.ngp_density_head_fw(ptr(z1), ptr(w2), ptr(b2.contiguous()), n, W, ptr(sigma), ptr(s2), ptr(t), stream()),
+              "density_head_fw")
+        with _tf32_matmul(tf32):
+            g_e = t @ W1
+        g_x = tcnn.grid_backward_input(x, g_e, tb, grid, aabb)
+        ctx.grid, ctx.aabb, ctx.tf32 = grid, aabb, tf32
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, table, W1, w2, enc, z1, s2, t, g_e)
+        return sigma, g_x
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dsigma, dgx):
+        from ._lib import lib, ptr, check, stream
+        x, table, W1, w2, enc, z1, s2, t, g_e = ctx.saved_tensors
+        g, aabb = ctx.grid, ctx.aabb
+        n, W = z1.shape
+        tdt = 0 if table.dtype == torch.float32 else 1
+        d_ge = v = None
+        if dgx is not None:
+            dgx = dgx.contiguous()
+            d_ge = torch.empty_like(enc)            # d(dgx . g_x)/d(g_e): the gather with the input-gradient coefficients
+            check(lib.ngp_hashgrid_bwbw_input(ptr(x), tcnn._aabb_arg(aabb), ptr(dgx), None, ptr(table.detach()), tdt, *g.args(), n,
+                                              None, ptr(d_ge), stream()), "hashgrid_bwbw_input")
+            with _tf32_matmul(ctx.tf32):
+                v = d_ge @ W1.t()
+        dz1 = torch.empty_like(z1); dz2 = torch.empty(n, device=z1.device)
+        dw2 = torch.zeros(W, device=z1.device); db1 = torch.zeros(W, device=z1.device)
+        check(lib.ngp_density_head_bw(ptr(z1), ptr(v), ptr(s2), ptr(dsigma.contiguous() if dsigma is not None else None), ptr(w2), n, W,
+                                      ptr(dz1), ptr(dz2), ptr(dw2), ptr(db1), stream()), "density_head_bw")
+        with _tf32_matmul(ctx.tf32):
+            de = dz1 @ W1
+            dW1 = dz1.t() @ enc
+            if d_ge is not None:
+                dW1.addmm_(t.t(), d_ge)
+        dtable = None
+        if ctx.needs_input_grad[1]:
+            dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device)
+            check(lib.ngp_hashgrid_bw_params_dual(ptr(x), tcnn._aabb_arg(aabb), ptr(de), ptr(dgx), ptr(g_e) if dgx is not None else None,
+                                                  *g.args(), n, ptr(dtable), stream()), "hashgrid_bw_params_dual")
+        return None, dtable, dW1, db1, dw2[None], dz2.sum()[None], None, None, None
+
+
 class _TwoHeadsFn(torch.autograd.Function):
     """norm_pred_header(feat) and semantic_header(feat) (networks.py:101-123: two bias-free MLPs  D -> 32 -> 3  and
     D -> 32 -> C  on the SAME feature matrix) evaluated as ONE block-structured MLP  D -> 64 -> (3 + C):
@@ -300,6 +365,7 @@ class NGP(nn.Module, _OccupancyMixin):
 
     # ------------------------------------------------------------------ density / normals
     fused_density_head = True     # sigma and d sigma / d(encoding) through _DensityNormalsFn (csrc/density_head.cu)
+    fused_density_field = True    # ... and the encoding around it in the same node (_DensityFieldNormalsFn): one dual scatter
 
     def _normalise(self, x):
         return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
@@ -320,8 +386,13 @@ class NGP(nn.Module, _OccupancyMixin):
         """sigmas, feat_rgb, d sigma / d x (N,3), differentiable w.r.t. the parameters
         (networks.py:186-196)."""
         x, ab = x.detach().contiguous(), self.aabb()
-        enc = self.xyz_encoder(x, ab)
         l0, l2 = self.xyz_net[0], self.xyz_net[2]
+        if (self.fused_density_field and self.fused_density_head and x.is_cuda and self.xyz_encoder.params.dtype == torch.float32
+                and l0.out_features % 128 == 0 and l0.out_features <= 512):
+            sigmas, g_xn = _DensityFieldNormalsFn.apply(x, self.xyz_encoder.params, l0.weight, l0.bias, l2.weight, l2.bias,
+                                                        self.xyz_encoder.grid, ab, self.density_net_tf32)
+            return sigmas, self.rgb_encoder(x, ab), g_xn / (self.xyz_max - self.xyz_min)
+        enc = self.xyz_encoder(x, ab)
         if self.fused_density_head and enc.is_cuda and enc.dtype == torch.float32 and l0.out_features % 128 == 0 and l0.out_features <= 512:
             sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias, self.density_net_tf32)
         else:       # any other density net: generic autograd double backward, as the reference does it

@@ -275,3 +275,28 @@ def test_fused_aux_heads_equal_the_two_separate_heads():
     a1, b1 = (setattr(m, "fused_aux_heads", True), m._aux_heads(feat))[1]
     (gs,) = torch.autograd.grad((b1 * ws).sum(), m.semantic_header.params)
     assert rel(gs, g0[2]) < 1e-4
+
+
+def test_density_field_single_node_equals_the_three_node_path():
+    """NGP.grad through _DensityFieldNormalsFn (gather + density net + input gradient as one autograd node, one dual
+    scatter in the backward) against the same quantities through _GridFn -> _DensityNormalsFn -> _GridBwFn (two scatters):
+    identical forward kernels (bit-equal outputs), and the table / density-net gradients of a scalar that uses sigma AND
+    the normals agree to 1e-4 of their norms (atomics order; the dual kernel adds both terms in registers)."""
+    m = _small_ngp(classes=7, density_net_tf32=False)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n = 6000
+    x = (torch.rand(n, 3, device="cuda", generator=g) - 0.5) * 0.98
+    ws, wg = torch.randn(n, device="cuda", generator=g), torch.randn(n, 3, device="cuda", generator=g)
+    ps = [m.xyz_encoder.params, m.xyz_net[0].weight, m.xyz_net[0].bias, m.xyz_net[2].weight, m.xyz_net[2].bias]
+    outs, grads = {}, {}
+    for fused in (True, False):
+        m.fused_density_field = fused
+        sig, feat, gr = m.grad(x)
+        outs[fused] = (sig, gr)
+        grads[fused] = torch.autograd.grad((sig * ws).sum() + (gr * wg).sum(), ps)
+        (grads[fused + 2],) = torch.autograd.grad((m.grad(x)[0] * ws).sum(), ps[0])      # sigma only: no normals upstream
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-20))
+    for a, b in zip(grads[True], grads[False]):
+        assert a.shape == b.shape and rel(a, b) < 1e-4, rel(a, b)
+    assert rel(grads[3], grads[2]) < 1e-4
