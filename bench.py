@@ -196,7 +196,7 @@ def kernel_breakdown(model, xyzs, dirs):
     return out
 
 
-def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1, esf=0.0):
+def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1, esf=0.0, num_classes=0, extra=None):
     """Test-time rendering (BASELINE.json configs[4]): full frames through raymarching_test +
     composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules.
     With world > 1 every frame's rays are split into `world` contiguous tiles, one per rank, no collective on
@@ -204,7 +204,9 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
     import torch.distributed as dist
     from ngp_b200.rendering import render
     out = {}
-    scheds = ("wavefront", "geometric", "reference") if world == 1 else ("wavefront",)
+    full = getattr(model, "has_normals", True)        # fields with normal / semantic heads render through the reference-style loop
+    extra = extra or {}
+    scheds = (("geometric", "reference") if full else ("wavefront", "geometric", "reference")) if world == 1 else (("geometric",) if full else ("wavefront",))
     with torch.no_grad():
         for sched in scheds:
             def frame(i):
@@ -217,13 +219,13 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
                 ro, rd = scene.rays_from_pixels(poses[i % poses.shape[0]][None], torch.zeros(a1 - a0, dtype=torch.long, device="cuda"), u, v)
                 tot = 0
                 for a in range(0, ro.shape[0], chunk):
-                    r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=esf, num_classes=0, test_time=True,
+                    r = render(model, ro[a:a + chunk], rd[a:a + chunk], exp_step_factor=esf, num_classes=num_classes, test_time=True,
                                T_threshold=1e-2, sample_schedule=sched if sched != "wavefront" else "geometric",
-                               renderer="wavefront" if sched == "wavefront" else "loop")
+                               renderer="wavefront" if sched == "wavefront" else "loop", **extra)
                     tot += int(r["total_samples"])
                 return tot, n
             frame(0); torch.cuda.synchronize()
-            nf = frames if sched == "wavefront" else 1
+            nf = frames if sched == scheds[0] and not full else 1
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -237,7 +239,7 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
             dt, tot = float(dt), float(tt)
             out[sched] = {"Mrays_per_s": nr / dt / 1e6, "ms_per_frame": dt * 1e3, "samples_per_ray": tot / nr}
-    return {"metric": "render Mrays/s", "frame": f"{wh[0]}x{wh[1]}", "value": out["wavefront"]["Mrays_per_s"], "unit": "Mrays/s",
+    return {"metric": "render Mrays/s", "frame": f"{wh[0]}x{wh[1]}", "value": out[scheds[0]]["Mrays_per_s"], "unit": "Mrays/s",
             "n_gpus": world, "sharding": "contiguous ray tiles per rank, no collective" if world > 1 else "single GPU",
             "legend": "wavefront = fused advance kernel per round; geometric / reference = reference-style loop over "
                       "raymarching_test + composite_test_fw with 4,8,16.. / the reference's own round sizes",
@@ -406,6 +408,11 @@ def gpu_arm(args):
         spr = float(out["total_samples"]) / ro.shape[0]
         rays_a, xyzs, dirs = out["rays_a"], out["xyzs"], None
     rend = None
+    if not args.no_render and full:      # reference-literal field: chunks of 131 072 rays as the reference renders (render.py:33-48), test embedding 0 (train.py:150-151)
+        with torch.no_grad():
+            e0 = emb(torch.zeros(1, dtype=torch.long, device=dev))
+        rend = render_bench(model, scene, poses, frames=1, chunk=1 << 17, rank=rank, world=world, esf=wl["esf"], num_classes=wl["classes"],
+                            extra={"embedding_a": e0})
     if not args.no_render and not full:
         rend = render_bench(model, scene, poses, rank=rank, world=world, esf=wl["esf"])
         if args.render_4k:
