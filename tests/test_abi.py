@@ -24,7 +24,8 @@ def test_header_has_no_torch_types_and_cites_reference():
     assert "torch" not in code.lower() and "Tensor" not in code
     assert 'extern "C"' in src
     for cite in ("binding.cpp:4-16", "binding.cpp:60-81", "binding.cpp:121-145", "binding.cpp:287-298",
-                 "networks.py:40-52", "networks.py:89-162"):
+                 "networks.py:40-52", "networks.py:89-162", "ray_utils.py:49-72", "rendering.py:217-219", "networks.py:54-59",
+                 "networks.py:186-196"):
         assert cite in src, cite
 
 
@@ -88,3 +89,23 @@ def test_grid_layout_matches_oracle_layout():
         assert g.offsets[:-1] == [l["offset"] for l in lv]
         assert g.resolutions == [l["res"] for l in lv]
         assert g.dense == [l["dense"] for l in lv]
+
+
+def test_ray_directions_follow_the_reference_formula():
+    """datasets/ray_utils.py:10-46: ((u - cx + .5)/fx, (v - cy + .5)/fy, 1), row-major over (v, u), un-normalised.
+    (get_rays itself is a kernel: tests/test_vren_gpu.py; without a GPU it must refuse, not fall back.)"""
+    import torch
+    from ngp_b200 import ray_utils
+    H, W = 3, 5
+    K = [[10.0, 0, 2.5], [0, 20.0, 1.5], [0, 0, 1]]
+    d = ray_utils.get_ray_directions(H, W, K)
+    assert d.shape == (H * W, 3) and d.dtype == torch.float32
+    for v in range(H):
+        for u in range(W):
+            row = d[v * W + u]
+            assert abs(float(row[0]) - (u - 2.5 + 0.5) / 10.0) < 1e-7 and abs(float(row[1]) - (v - 1.5 + 0.5) / 20.0) < 1e-7
+            assert float(row[2]) == 1.0
+    assert ray_utils.get_ray_directions(H, W, K, flatten=False).shape == (H, W, 3)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            ray_utils.get_rays(d, torch.eye(4)[:3])
