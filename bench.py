@@ -7,7 +7,11 @@ Workload (BASELINE.json configs[1]): Lego-shaped procedural scene (800x800, 100 
 ngp_pl-shaped field (16-level F2 hash grid T=2^19, 64-wide MLPs), 2^18 rays per GPU per step,
 fp32 tables / bf16 tensor-core operands with fp32 accumulation.  One step = occupancy update (every
 16th) + AABB + march + hash encode + MLPs + composite + losses + backward + (all-reduce) + Adam.
-Prints ONE JSON line (see README / DESIGN.md §measurement for every key).
+`value` times the step on device-resident batches; `e2e` times the same step fed as the reference's loader feeds it
+— (img_idxs, pix_idxs, rgb) from pinned host memory, copied one step ahead on a copy stream into a double buffer, rays
+generated on the device (ngp_get_rays), the step's loss read back on the host every step.
+--workload street | playground run the BASELINE.json configs[3] / configs[2] shapes (not the headline).
+Prints ONE JSON line (see README / DESIGN.md §6 for every key).
 """
 import argparse
 import json
