@@ -403,3 +403,42 @@ def test_expand_per_ray_matches_repeat_interleave(W):
     (g0,) = torch.autograd.grad((ref * w).sum(), v)
     assert torch.allclose(g1, g0, rtol=1e-5, atol=1e-5)
     assert float(g1[ray[N == 0]].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["boxes", "shell", "sparse", "empty", "one_cell", "lego"])
+def test_raymarching_train_culling_keeps_counts_bit_exact(vren, kind):
+    """Empty-ray culling of the single-cascade training march (march.cu coarse_occupancy_kernel: rays whose segment stays
+    4 cells clear of every occupied cell skip the stepping loop) only engages from 2048 rays on — more than the golden
+    cases carry — so: 20 000 rays (incl. axis-parallel / grazing / inside / missing ones) against the C oracle, bit for
+    bit, on bitfields where most rays are culled (boxes, shell, a Lego-shaped voxelisation), none is (4 % random
+    occupancy: the dilated lattice is full), all are (empty grid), and where a single occupied corner cell decides."""
+    n, scale = 20000, 0.5
+    if kind == "empty":
+        bf = np.zeros(128 ** 3 // 8, np.uint8)
+    elif kind == "one_cell":
+        bf = np.zeros(128 ** 3 // 8, np.uint8)
+        for (x, y, z) in ((127, 127, 127), (0, 64, 3), (60, 61, 67)):
+            code = int(cases.morton_enc(np.array([x]), np.array([y]), np.array([z]))[0])
+            bf[code >> 3] |= np.uint8(1 << (code & 7))
+    elif kind == "lego":
+        import torch as _t
+        from ngp_b200.synthetic import BoxScene, scene_density_grid, pack_bitfield_torch
+        bf = pack_bitfield_torch(scene_density_grid(BoxScene("lego")), 0.5).numpy()
+    else:
+        bf = cases.bitfield(kind, 1, seed=4)
+    o, d = cases.rays(n, scale, seed=21)
+    if kind == "one_cell":                         # aim a third of the rays straight at the occupied cells
+        tg = (np.array([[127, 127, 127], [0, 64, 3], [60, 61, 67]], np.float32) + 0.5) / 128 - 0.5
+        k = n // 3
+        d[:k] = (tg[np.arange(k) % 3] + np.random.RandomState(5).normal(size=(k, 3)).astype(np.float32) * 0.004 - o[:k])
+    cnt, ht, _ = oracle.ray_aabb_intersect(o, d, np.zeros((1, 3), np.float32), np.full((1, 3), scale, np.float32), 1)
+    h = cases.near_clamp(ht)
+    noise = np.random.RandomState(8).rand(n).astype(np.float32)
+    rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(T(o), T(d), T(h), T(bf), 1, scale, 0.0, T(noise), 128, 1024)
+    ra, rx, rd, rdl, rts, rcnt = oracle.raymarching_train(o, d, h, bf, 1, scale, 0.0, noise, 128, 1024)
+    assert (N(counter) == rcnt).all() and (N(rays_a) == ra).all()
+    assert (bits(N(ts)) == bits(rts)).all() and (bits(N(deltas)) == bits(rdl)).all() and (bits(N(xyzs)) == bits(rx)).all()
+    if kind == "empty":
+        assert int(rcnt[0]) == 0
+    else:
+        assert int(rcnt[0]) > 0 and (ra[:, 2] == 0).mean() > 0.02        # both kinds of rays present
