@@ -441,4 +441,4 @@ def test_raymarching_train_culling_keeps_counts_bit_exact(vren, kind):
     if kind == "empty":
         assert int(rcnt[0]) == 0
     else:
-        assert int(rcnt[0]) > 0 and (ra[:, 2] == 0).mean() > 0.02        # both kinds of rays present
+        assert int(rcnt[0]) > 0 and (ra[:, 2] == 0).any() and (ra[:, 2] > 0).any()        # both kinds of rays present
