@@ -62,7 +62,9 @@ def last_error() -> str:
     return lib.ngp_last_error().decode()
 
 
-_KERNELS_PER_CALL = {"raymarching_train/count": 3}     # count + block sums + block scan; every other entry point = 1 launch
+# count + block sums + block scan (+ coarse lattice + cull pre-pass when the single-cascade culling applies, march.cu);
+# every other entry point = 1 launch
+_KERNELS_PER_CALL = {"raymarching_train/count": 3, "raymarching_train/count+cull": 5}
 _launches = 0
 
 

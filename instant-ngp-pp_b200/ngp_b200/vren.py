@@ -117,7 +117,8 @@ def raymarching_train_count(rays_o, rays_d, hits_t, density_bitfield, cascades, 
                                           ptr(_f32(hits_t, "hits_t")), ptr(density_bitfield), int(cascades),
                                           float(scale), float(exp_step_factor), ptr(_f32(noise, "noise")),
                                           int(grid_size), int(max_samples), R, ptr(counter), ptr(ws), stream()),
-          "raymarching_train/count")
+          "raymarching_train/count+cull" if (int(cascades) == 1 and float(exp_step_factor) == 0.0 and int(grid_size) == 128
+                                             and R >= 2048) else "raymarching_train/count")
     return MarchPlan(ws, counter, R)
 
 
