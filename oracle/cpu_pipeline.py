@@ -123,4 +123,4 @@ class CPUPipeline:
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
-        return float(loss), res["total_samples"]
+        return float(loss.detach()), res["total_samples"]
