@@ -95,21 +95,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(steps, warmup, rays_per_step=4096):
-    """The reference-side CPU implementation of the same workload (oracle port): C restatement of the
-    reference's vren kernels + PyTorch restatement of the tcnn operators, all host threads."""
-    from oracle.cpu_pipeline import CPUPipeline
-    from ngp_b200.synthetic import BoxScene, scene_density_grid, pack_bitfield_torch
+CPU_WORKLOAD = ("BASELINE.json configs[0]: lego-shaped 800x800x100 views, scale 0.5, 8192 rays/batch through the noCUDA path "
+                "(rendering_noCUDA coarse 64 + fine 128 samples/ray, two networks_noCUDA fields), fw+bw+Adam on the host cores")
+
+
+def cpu_arm(steps, warmup, rays_per_step=512):
+    """The reference's CPU-shaped implementation of the path (BASELINE.json configs[0]: models/rendering_noCUDA.py +
+    models/networks_noCUDA.py), restated in oracle/nocuda_pipeline.py because the files themselves import tinycudann / vren
+    and call .cuda().  Each step is a BOUNDED SAMPLE of one 8192-ray batch (`rays_per_step` rays of it) so
+    that the run ends within minutes; rays/s does not depend on the sample size (cost is linear in rays).  Imports nothing
+    from the product package: no libngp_b200.so is mapped by this arm."""
+    from oracle.nocuda_pipeline import NoCUDAPipeline, aabb_hits
+    from synth_scenes import BoxScene
     sc = BoxScene("lego")
-    bf = pack_bitfield_torch(scene_density_grid(sc), 0.5).numpy()
-    pipe = CPUPipeline(bf, scale=0.5)
+    pipe = NoCUDAPipeline(scale=0.5)
     poses = sc.poses(100)
     gen = torch.Generator().manual_seed(20220806)
     batches = []
     for _ in range(2):
-        ro, rd = sc.sample_rays(rays_per_step, poses, gen)
+        ro, rd = sc.sample_rays(rays_per_step * 2, poses, gen)
+        _, hit = aabb_hits(ro, rd, 0.5)                      # the noCUDA sampler needs rays that hit the box (0/0 otherwise)
+        ro, rd = ro[hit][:rays_per_step].contiguous(), rd[hit][:rays_per_step].contiguous()
         rgb, *_ = sc.shade(ro, rd)
-        batches.append((ro.numpy(), rd.numpy(), rgb.numpy()))
+        batches.append((ro, rd, rgb))
+    n = batches[0][0].shape[0]
     for i in range(warmup):
         pipe.train_step(*batches[i % 2])
     t0 = time.perf_counter()
@@ -117,9 +126,10 @@ def cpu_arm(steps, warmup, rays_per_step=4096):
     for i in range(steps):
         _, s = pipe.train_step(*batches[i % 2]); samples += s
     dt = time.perf_counter() - t0
-    return {"value": rays_per_step * steps / dt, "unit": "rays/s", "cores": pipe.threads, "kind": "port",
-            "sample": f"{steps} steps x {rays_per_step} rays of the same workload (fw+bw+Adam), {samples / max(steps, 1) / rays_per_step:.1f} samples/ray, "
-                      f"C oracle single-thread + torch CPU ops on {pipe.threads} threads"}, dt / max(steps, 1)
+    return {"value": n * steps / dt, "unit": "rays/s", "cores": pipe.threads, "kind": "port",
+            "sample": f"{steps} steps x {n} rays (a {n}/8192 sample of one configs[0] batch per step), {samples // max(steps, 1) // n} samples/ray "
+                      f"(coarse 64 + fine 128), fw+bw+Adam, torch CPU ops on {pipe.threads} threads; restatement of rendering_noCUDA.py:103-214 + "
+                      "networks_noCUDA.py:49-369 (oracle/nocuda_pipeline.py)"}, dt / max(steps, 1)
 
 
 # ------------------------------------------------------------------------------------------ kernel timing
@@ -255,7 +265,7 @@ def gpu_arm(args):
     import torch.distributed as dist
     from ngp_b200 import _lib, vren
     from ngp_b200.networks import NGP, NGPCompact
-    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    from synth_scenes import BoxScene, scene_density_grid
     from ngp_b200.trainer import Trainer, psnr
     from ngp_b200.rendering import render
 
@@ -357,9 +367,21 @@ def gpu_arm(args):
         free_ev[b] = torch.cuda.Event(); free_ev[b].record(main)
         return float(loss)                                                  # python float: this step's loss, read back on the host (Trainer.train_step)
 
+    def eval_psnr():
+        """PSNR on 2^15 held-out rays (generator seed 4321: the same rays baseline/ref_train.py evaluates the reference on)."""
+        with torch.no_grad():
+            g2 = torch.Generator(device=dev).manual_seed(4321)
+            ro, rd = scene.sample_rays(1 << 15, poses, g2)
+            gt, *_ = scene.shade(ro, rd)
+            kw_e = {"embedding_a": emb(torch.zeros(1 << 15, dtype=torch.long, device=dev))} if full else {}
+            return float(psnr(render(model, ro, rd, **rkw, **kw_e)["rgb"], gt))
+
     # pre-train so that the occupancy grid / sample count are at their steady state
+    psnr_at_ref_steps = None
     for i in range(args.pretrain):
         step_resident(i)
+        if i + 1 == args.ref_steps:
+            psnr_at_ref_steps = eval_psnr()
     for i in range(args.warmup):
         step_resident(i)
 
@@ -472,10 +494,27 @@ def gpu_arm(args):
                         "launch walks level chunks slowest (GridMeta::chunk_major, hashgrid.cu) so that only one chunk's levels are "
                         "live in L2 at a time; block-order probe in profiles/r01e_hash_block_order_probe.txt" % table_mb)
         roof["traffic"] = None
-    cpu, _ = cpu_arm(steps=4, warmup=1)
-    if args.workload != "lego":       # the CPU port implements the headline field only
-        cpu["sample"] = "HEADLINE workload (lego-shaped, ngp_pl-shaped field), not this one: " + cpu["sample"]
+    cpu, _ = cpu_arm(steps=3, warmup=1)
     value = world * R * args.steps / t_res
+    # reference GPU path on the same box, same run: the reference's unmodified glue + its own CUDA kernels + a
+    # torch-op tinycudann stand-in, same scene / batch recipe / lr / Adam eps, trained args.ref_steps steps, last 10 timed
+    ref_gpu = None
+    if args.workload == "lego" and world == 1 and args.ref_steps > 0:
+        del tr, pool, pool_o, pool_d
+        torch.cuda.empty_cache()
+        try:
+            from baseline import ref_train
+            ref_gpu = ref_train.run_reference_gpu(scene_kind="lego", field="ngp_pl", rays=R, steps_total=args.ref_steps, timed_last=10,
+                                                  lr=wl["lr"], eps=1e-15, views=wl["views"], log2_T=wl["log2_T"])
+            ref_gpu["ours_psnr_after_same_steps"] = psnr_at_ref_steps
+            ref_gpu["ours_over_reference_gpu"] = value / ref_gpu["value"]
+            torch.cuda.empty_cache()
+            # the same reference glue with BOTH extension imports bound to libngp_b200.so (zero-edit drop-in)
+            drop = ref_train.run_reference_gpu(scene_kind="lego", field="ngp_pl", rays=R, steps_total=args.ref_steps, timed_last=10,
+                                               lr=wl["lr"], eps=1e-15, views=wl["views"], log2_T=wl["log2_T"], vren="ours", tcnn="ours")
+            ref_gpu["reference_glue_on_libngp_b200"] = {k: drop[k] for k in ("value", "unit", "ms_per_step", "psnr_after_steps", "samples_per_ray")}
+        except Exception as ex:            # baseline/_ref or vren_ref.so not present on this box
+            ref_gpu = {"unavailable": repr(ex)[:300]} if ref_gpu is None else ref_gpu
     line = {
         "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -488,7 +527,7 @@ def gpu_arm(args):
                 "ms_per_step": t_e2e / args.steps * 1e3,
                 "path": "pinned host (img_idxs i64, pix_idxs i64, rgb f32[, label]) -> H2D on a copy stream one step ahead -> ngp_get_rays -> "
                         "Trainer.train_step(host_loss=True): loss -> pinned host right after the forward pass, waited for after the step is enqueued; every step"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "render": rend,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "render": rend,
     }
     print(json.dumps(line))
     if world > 1:
@@ -501,6 +540,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pretrain", type=int, default=400)
+    ap.add_argument("--ref-steps", type=int, default=100, help="steps the reference-GPU arm trains (PSNR is compared after the same number of steps); 0 = skip")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lego", choices=sorted(WORKLOADS), help="lego = BASELINE.json configs[1] (the headline); street = configs[3] shape")
     ap.add_argument("--no-render", action="store_true", help="skip the test-time render sweep")
@@ -509,12 +549,11 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:
             return
-        steps = max(1, min(args.steps, 8))
-        cpu, per_step = cpu_arm(steps=steps, warmup=min(args.warmup, 1))
+        cpu, per_step = cpu_arm(steps=args.steps, warmup=args.warmup)
         print(json.dumps({
             "impl": "reference", "metric": "train rays/s (fw+bw)", "value": cpu["value"], "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": cpu["sample"]},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": {"workload": CPU_WORKLOAD, "sample": cpu["sample"]},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     gpu_arm(args)

@@ -10,7 +10,10 @@ namespace ngp {
 // 3 x int4 loads (48 B) -> 1 x int4 store, fully coalesced across the warp.
 __global__ void __launch_bounds__(256) morton3D_kernel(const int32_t* __restrict__ coords, int64_t n,
                                                        int32_t* __restrict__ indices) {
-  const int64_t n4 = n >> 2;
+  // 16-byte vector path only for 16-byte aligned views; an offset view (coords[1:]) takes the scalar loop like the
+  // reference's scalar accessors would (raymarching.cu:62-70)
+  const bool aligned = ((((uintptr_t)coords) | ((uintptr_t)indices)) & 15) == 0;
+  const int64_t n4 = aligned ? (n >> 2) : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
     const int4* src = reinterpret_cast<const int4*>(coords) + q * 3;
@@ -22,14 +25,15 @@ __global__ void __launch_bounds__(256) morton3D_kernel(const int32_t* __restrict
     o.w = (int32_t)morton3D(c.y, c.z, c.w);
     reinterpret_cast<int4*>(indices)[q] = o;
   }
-  // tail (n % 4 cells)
-  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) indices[t] = (int32_t)morton3D(coords[3 * t], coords[3 * t + 1], coords[3 * t + 2]);
+  // tail (n % 4 cells; everything when unaligned)
+  for (int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    indices[t] = (int32_t)morton3D(coords[3 * t], coords[3 * t + 1], coords[3 * t + 2]);
 }
 
 __global__ void __launch_bounds__(256) morton3D_invert_kernel(const int32_t* __restrict__ indices, int64_t n,
                                                               int32_t* __restrict__ coords) {
-  const int64_t n4 = n >> 2;
+  const bool aligned = ((((uintptr_t)coords) | ((uintptr_t)indices)) & 15) == 0;
+  const int64_t n4 = aligned ? (n >> 2) : 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
     const int4 i = __ldg(reinterpret_cast<const int4*>(indices) + q);
@@ -43,8 +47,7 @@ __global__ void __launch_bounds__(256) morton3D_invert_kernel(const int32_t* __r
     int4* dst = reinterpret_cast<int4*>(coords) + q * 3;
     dst[0] = a; dst[1] = b; dst[2] = c;
   }
-  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) {
+  for (int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     const int32_t ind = indices[t];
     coords[3 * t + 0] = morton3D_invert((uint32_t)(ind >> 0));
     coords[3 * t + 1] = morton3D_invert((uint32_t)(ind >> 1));

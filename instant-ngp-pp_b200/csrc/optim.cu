@@ -10,7 +10,7 @@ namespace ngp {
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out) {
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n4 = n >> 2;
+  const int64_t n4 = (((uintptr_t)g) & 15) == 0 ? (n >> 2) : 0;        // float4 path only for 16-byte aligned views
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float step_size, float inv_sqrt_bc2, const float* __restrict__ gscale) {
   const float gs = gscale ? __ldg(gscale) : 1.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n4 = n >> 2;
+  const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  const int64_t n4 = aligned ? (n >> 2) : 0;                             // parameter views at odd offsets take the scalar loop
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
     const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);

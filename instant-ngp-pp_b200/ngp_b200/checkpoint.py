@@ -7,9 +7,9 @@ state dict (missing keys keep their current values, exactly like the reference's
 
 Parameter layouts are the reference's: every tcnn-shaped module owns ONE flat fp32 `.params` — the hash grid
 level-major / entry / feature, the MLPs layer after layer, row-major (out, in), output rows
-padded to 16.  tiny-cuda-nn pads an MLP's INPUT width to its alignment as well (16 for FullyFusedMLP, 8 for CutlassMLP;
-the padded columns see the constant 1): `adapt_mlp_params` converts such a vector to this library's unpadded first
-layer.  tiny-cuda-nn itself is not available offline, so that converter is unverified against a real tcnn file.
+padded to 16 HERE.  tiny-cuda-nn pads output rows to 16 (FullyFusedMLP) or 8 (CutlassMLP, the reference's heads) and may pad
+the input width too: `adapt_mlp_params` converts such a vector (see its docstring for what is and is not supported).
+tiny-cuda-nn itself is not available offline, so that converter is unverified against a real tcnn file.
 """
 import torch
 
@@ -46,7 +46,7 @@ def load_ckpt(model, ckpt_path, model_name="model", prefixes_to_ignore=()):
             if mlp is None:
                 raise RuntimeError(f"{k}: checkpoint has {v.numel()} parameters, the module {model_dict[k].numel()} "
                                    "(different grid configuration: levels / features / log2_hashmap_size / scale)")
-            incoming[k] = adapt_mlp_params(v, mlp.n_in, mlp.width, mlp.n_hidden, mlp.n_out)
+            incoming[k] = adapt_mlp_params(v, mlp.n_in, mlp.width, mlp.n_hidden, mlp.n_out, getattr(mod, 'network_config', {}).get('otype'))
     model_dict.update(incoming)
     model.load_state_dict(model_dict)
 
@@ -64,21 +64,42 @@ def slim_ckpt(ckpt_path, save_poses=False):
     return sd
 
 
-def adapt_mlp_params(flat, n_in, width, n_hidden, n_out):
-    """A bias-free MLP vector whose FIRST layer was stored with a padded input width (width x n_in_padded, tcnn) ->
-    this library's (width x n_in | (n_hidden-1) x width x width | n_out_pad16 x width).  The padded input columns
-    multiply the constant 1 in tcnn — a bias this library's networks do not have — so they are only dropped when they
-    are all zero; otherwise the mismatch is reported instead of silently changing the function."""
-    nop = (n_out + 15) // 16 * 16
-    rest = (n_hidden - 1) * width * width + nop * width
-    first = flat.numel() - rest
-    if first <= 0 or first % width:
-        raise RuntimeError(f"MLP parameter vector of {flat.numel()} values does not fit {n_in}->{width}x{n_hidden}->{n_out}")
-    n_in_padded = first // width
-    if n_in_padded < n_in:
-        raise RuntimeError(f"MLP first layer has {n_in_padded} input columns, the module expects {n_in}")
-    W0 = flat[:first].reshape(width, n_in_padded)
-    if n_in_padded > n_in and float(W0[:, n_in:].abs().max()) != 0.0:
-        raise RuntimeError(f"MLP first layer carries {n_in_padded - n_in} non-zero padded input columns (a tcnn bias column); "
+def _pad(n, a):
+    return (n + a - 1) // a * a
+
+
+def adapt_mlp_params(flat, n_in, width, n_hidden, n_out, otype=None):
+    """A bias-free tcnn MLP vector -> this library's layout (width x n_in | (n_hidden-1) x width x width | 16-row-padded
+    n_out x width).
+
+    tiny-cuda-nn pads an MLP's OUTPUT rows to 16 (FullyFusedMLP) or to its tensor-core width 8 (CutlassMLP — the otype of
+    every head in models/networks.py:89-162) and may pad the INPUT width to the same alignment (the padded columns see the
+    constant 1, i.e. they act as a bias).  The source padding is taken from `otype` when it explains the vector's length,
+    otherwise every (input pad, output pad) in {none, 8, 16} x {8, 16} is tried; the output rows are zero-padded or
+    truncated to this library's 16 (rows >= n_out are never read).  Padded input columns are dropped only when they are all
+    zero: a trained tcnn head with padded inputs (skybox 9 -> 16, tonemapper 1 -> 8) carries a learnt bias there that this
+    library's bias-free networks cannot represent — such checkpoints are reported as unsupported instead of silently
+    changing the function.  tiny-cuda-nn is not available offline, so the padding rules are from memory of its source
+    (SURVEY.md Appendix B items marked with a dagger) and unverified against a real tcnn file."""
+    hidden = (n_hidden - 1) * width * width
+    pref = {"CutlassMLP": 8, "FullyFusedMLP": 16}.get(otype)
+    out_pads = [a for a in ((pref,) if pref else ()) + (16, 8) if a]
+    cands = []
+    for oa in dict.fromkeys(out_pads):
+        for ia in dict.fromkeys([1, oa, 8, 16]):
+            ni, no = _pad(n_in, ia), _pad(n_out, oa)
+            if width * ni + hidden + no * width == flat.numel():
+                cands.append((ni, no))
+    if not cands:
+        raise RuntimeError(f"MLP parameter vector of {flat.numel()} values does not fit {n_in}->{width}x{n_hidden}->{n_out} "
+                           f"under any tcnn padding (otype {otype})")
+    ni, no = cands[0]
+    W0 = flat[:width * ni].reshape(width, ni)
+    if ni > n_in and float(W0[:, n_in:].abs().max()) != 0.0:
+        raise RuntimeError(f"MLP first layer carries {ni - n_in} non-zero padded input columns (a tcnn bias column): unsupported — "
                            "this library's networks are bias-free at the padded inputs")
-    return torch.cat([W0[:, :n_in].reshape(-1), flat[first:]])
+    Wl = flat[width * ni + hidden:].reshape(no, width)
+    nop = _pad(n_out, 16)
+    Wl16 = torch.zeros(nop, width, dtype=flat.dtype)
+    Wl16[:min(no, nop)] = Wl[:min(no, nop)]
+    return torch.cat([W0[:, :n_in].reshape(-1), flat[width * ni:width * ni + hidden], Wl16.reshape(-1)])

@@ -118,8 +118,10 @@ class VolumeRendererLite(torch.autograd.Function):
         S, R = sigmas.shape[0], rays_a.shape[0]
         d_sig = torch.empty_like(sigmas)
         d_rgb = torch.empty_like(rgbs)
-        check(lib.ngp_composite_train_bw(ptr(g_opacity.contiguous()), ptr(g_depth.contiguous()), ptr(g_rgb.contiguous()), None,
-                                         None, ptr(g_ws.contiguous()), ptr(sigmas), ptr(rgbs), ptr(ws), ptr(deltas), ptr(ts),
+        # bound to locals: a temporary .contiguous() copy would be freed (and its block reused by the next copy) before the launch
+        g_opacity, g_depth, g_rgb, g_ws = g_opacity.contiguous(), g_depth.contiguous(), g_rgb.contiguous(), g_ws.contiguous()
+        check(lib.ngp_composite_train_bw(ptr(g_opacity), ptr(g_depth), ptr(g_rgb), None,
+                                         None, ptr(g_ws), ptr(sigmas), ptr(rgbs), ptr(ws), ptr(deltas), ptr(ts),
                                          ptr(rays_a), ptr(opacity), ptr(depth), ptr(rgb), float(ctx.T_threshold), 0, S, R,
                                          ptr(d_sig), ptr(d_rgb), None, None, stream()), "composite_train_bw")
         return d_sig, d_rgb, None, None, None, None

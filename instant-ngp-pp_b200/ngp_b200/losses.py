@@ -13,10 +13,16 @@ from torch import nn
 from .custom_functions import DistortionLoss  # noqa: F401  (re-exported: losses.py:32-58)
 
 
-def compute_scale_and_shift(prediction, target):
-    """Least-squares (scale, shift) aligning prediction to target (losses.py:7-30), sync-free."""
+def compute_scale_and_shift(prediction, target, weight=None):
+    """Least-squares (scale, shift) aligning prediction to target (losses.py:7-30), sync-free.
+    weight (0/1 per element, optional): the solve runs over the elements with weight 1 — what the reference obtains by
+    indexing `results['depth'][mask]`, `depth_2d[mask]` first (losses.py:128) — without a boolean-mask gather; a_11 is then
+    the number of VALID elements, not numel()."""
+    if weight is None:
+        a11 = torch.tensor(float(prediction.numel()), device=prediction.device)
+    else:
+        prediction, target, a11 = prediction * weight, target * weight, weight.sum()
     a00, a01 = (prediction * prediction).sum(), prediction.sum()
-    a11 = torch.tensor(float(prediction.numel()), device=prediction.device)
     b0, b1 = (prediction * target).sum(), target.sum()
     det = a00 * a11 - a01 * a01
     ok = det != 0
@@ -77,7 +83,7 @@ class NeRFLoss(nn.Module):
             depth_2d = target["depth"] / 25
             w = (depth_2d > 0).float()
             pred = results["depth"].detach()
-            scale, shift = compute_scale_and_shift(pred * w, depth_2d * w)
+            scale, shift = compute_scale_and_shift(pred, depth_2d, weight=w)
             d["depth_mono"] = w * self.lambda_depth_mono * torch.exp(-pred / kwargs.get("scale", 1)) * \
                 (scale * results["depth"] + shift - depth_2d) ** 2
         return d

@@ -42,7 +42,7 @@ def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pre
       'reference' — the reference's chunk sizes: max(min(N_rays//N_alive, 64), min_samples) per round,
                     i.e. ONE sample per ray per round while most rays are alive (dozens to hundreds of
                     rounds, each with several host syncs);
-      'geometric' (default) — 4, 8, 16, ... samples per round: <= 9 rounds to reach MAX_SAMPLES and one
+      'geometric' (default) — 4, 8, 16, 32, 64, then 128 samples per round: <= 13 rounds to reach MAX_SAMPLES and one
                     host read-back per round.  The marcher resumes every ray exactly where it stopped
                     and the compositor is a per-ray sequential recurrence, so the composited result
                     does not depend on the chunking (up to the association of per-round partial sums).

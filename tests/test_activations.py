@@ -1,0 +1,62 @@
+"""TruncExp / TruncTanh / ReLU (reference models/custom_functions.py:200-244) — forward and backward
+against the reference's own classes (baseline/_ref, unmodified) and against the closed forms, including the clamp
+boundaries (+-7, +-15) and the reference ReLU's constant 1e-6 zero-side gradient."""
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_REF = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")) or os.path.isdir("/root/reference")
+
+
+def _x(dev):
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.randn(500, 3, generator=g) * 6, torch.tensor([[-7.0, 7.0, 0.0], [-15.0, 15.0, -0.0], [20.0, -20.0, 7.0001], [-7.0001, 15.5, -16.0]])])
+    return x.to(dev).requires_grad_(True)
+
+
+def _check(dev, ref_cf=None):
+    from ngp_b200.custom_functions import TruncExp, TruncTanh, ReLU
+    up = torch.randn(504, 3, generator=torch.Generator().manual_seed(1)).to(dev)
+    closed = {
+        "TruncExp": (lambda x: torch.exp(x), lambda x, g: g * torch.exp(x.clamp(-7, 7))),
+        "TruncTanh": (lambda x: torch.tanh(x), lambda x, g: g * (1 - torch.tanh(x.clamp(-15, 15)) ** 2)),
+        "ReLU": (lambda x: torch.where(x > 0, x, torch.zeros_like(x)), lambda x, g: torch.where(x > 0, g, torch.full_like(g, 1e-6))),
+    }
+    for name, fn in (("TruncExp", TruncExp), ("TruncTanh", TruncTanh), ("ReLU", ReLU)):
+        x = _x(dev)
+        y = fn.apply(x)
+        (gx,) = torch.autograd.grad(y, x, up)
+        fw, bw = closed[name]
+        assert torch.equal(y.detach(), fw(x.detach())), name
+        assert torch.equal(gx, bw(x.detach(), up)), name
+        if ref_cf is not None:                      # the reference's own class on the same tensors (its ReLU needs CUDA tensors)
+            xr = _x(dev)
+            yr = getattr(ref_cf, name).apply(xr)
+            (gr,) = torch.autograd.grad(yr, xr, up)
+            assert torch.equal(y.detach(), yr.detach()) and torch.equal(gx, gr), name
+
+
+def test_activations_closed_forms_cpu():
+    _check("cpu")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not installed")
+def test_truncexp_trunctanh_match_reference_classes_cpu():
+    from baseline import ref_harness
+    cf = ref_harness.load(vren="ours", tcnn="standin").custom_functions
+    from ngp_b200.custom_functions import TruncExp, TruncTanh
+    up = torch.randn(504, 3, generator=torch.Generator().manual_seed(1))
+    for name, fn in (("TruncExp", TruncExp), ("TruncTanh", TruncTanh)):
+        x, xr = _x("cpu"), _x("cpu")
+        (g1,) = torch.autograd.grad(fn.apply(x), x, up)
+        (g2,) = torch.autograd.grad(getattr(cf, name).apply(xr), xr, up)
+        assert torch.equal(g1, g2), name
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not installed")
+def test_activations_match_reference_classes_gpu():
+    from baseline import ref_harness
+    _check("cuda", ref_harness.load(vren="ours", tcnn="standin").custom_functions)

@@ -77,7 +77,7 @@ def test_ngp_field_matches_torch_restatement(embed_a):
 def _scene_and_model(model_kind):
     from ngp_b200 import vren
     from ngp_b200.networks import NGPCompact
-    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    from synth_scenes import BoxScene, scene_density_grid
     scene = BoxScene("lego", device="cuda")
     if model_kind == "compact":
         torch.manual_seed(0)
@@ -167,7 +167,7 @@ def test_street_shaped_scene_cascades_semantics_normals_embedding():
     from ngp_b200 import vren
     from ngp_b200.networks import NGP
     from ngp_b200.rendering import render
-    from ngp_b200.synthetic import BoxScene, scene_density_grid
+    from synth_scenes import BoxScene, scene_density_grid
     from ngp_b200.trainer import Trainer
     scene = BoxScene("street", device="cuda")
     torch.manual_seed(0)

@@ -267,3 +267,34 @@ def test_density_head_closed_forms_match_autograd_double_backward():
     assert float((g_e[1:] - g[1:]).abs().max()) < 1e-12          # rows below the threshold: exact
     for a, b in zip(grads, ref):
         assert a.shape == b.shape and float((a - b).abs().max()) < 1e-8 * max(1.0, float(b.abs().max()))
+
+
+def test_nocuda_grid_encode_fast_equals_oracle_grid_encode():
+    """the one-gather grid encode of the configs[0] CPU baseline is the oracle's encode (values, dx, dtable)"""
+    import torch
+    from oracle import tcnn_oracle
+    from oracle.nocuda_pipeline import grid_encode_fast
+    cfg = (6, 2, 11, 4, 1.6)
+    g = torch.Generator().manual_seed(0)
+    tab = torch.rand(tcnn_oracle.grid_layout(*cfg)[1] * 2, generator=g, dtype=torch.float64).requires_grad_(True)
+    x = torch.rand(400, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    a, b = grid_encode_fast(x, tab, *cfg), tcnn_oracle.grid_encode(x, tab, *cfg)
+    assert torch.allclose(a, b, rtol=1e-12, atol=1e-14)
+    ga = torch.autograd.grad((a ** 2).sum(), [x, tab]); gb = torch.autograd.grad((b ** 2).sum(), [x, tab])
+    assert all(torch.allclose(u, v, rtol=1e-10, atol=1e-12) for u, v in zip(ga, gb))
+
+
+def test_nocuda_pipeline_trains_on_cpu():
+    import torch
+    from oracle.nocuda_pipeline import NoCUDAPipeline, aabb_hits
+    from synth_scenes import BoxScene
+    sc = BoxScene("lego")
+    ro, rd = sc.sample_rays(256, sc.poses(4), torch.Generator().manual_seed(0))
+    _, hit = aabb_hits(ro, rd, 0.5)
+    ro, rd = ro[hit][:64].contiguous(), rd[hit][:64].contiguous()
+    rgb, *_ = sc.shade(ro, rd)
+    pipe = NoCUDAPipeline(log2_T_xyz=12, log2_T_rgb=13, samples=(16, 32), threads=4)
+    l0, n = pipe.train_step(ro, rd, rgb)
+    for _ in range(5):
+        l1, _ = pipe.train_step(ro, rd, rgb)
+    assert n == 64 * 48 and l1 < l0

@@ -422,7 +422,7 @@ def test_raymarching_train_culling_keeps_counts_bit_exact(vren, kind):
             bf[code >> 3] |= np.uint8(1 << (code & 7))
     elif kind == "lego":
         import torch as _t
-        from ngp_b200.synthetic import BoxScene, scene_density_grid, pack_bitfield_torch
+        from synth_scenes import BoxScene, scene_density_grid, pack_bitfield_torch
         bf = pack_bitfield_torch(scene_density_grid(BoxScene("lego")), 0.5).numpy()
     else:
         bf = cases.bitfield(kind, 1, seed=4)

@@ -10,7 +10,7 @@ import torch
 from ngp_b200 import vren, tcnn
 from ngp_b200._lib import lib, ptr, check, stream
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.custom_functions import RayMarcher
 
 dev = torch.device("cuda", 0)

@@ -5,7 +5,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "instant-ngp-pp_b200")]
 import torch
 from ngp_b200 import vren, tcnn
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.custom_functions import RayMarcher
 dev = torch.device("cuda", 0)
 scene = BoxScene("lego", device=dev); poses = scene.poses(100)

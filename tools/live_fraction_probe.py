@@ -7,7 +7,7 @@ os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import torch
 from ngp_b200 import vren
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.trainer import Trainer
 dev = torch.device("cuda", 0)
 for kind, scale, T, esf, lr in (("lego", 0.5, 19, 0.0, 1e-2), ("street", 8.0, 22, 1 / 256, 2e-3)):

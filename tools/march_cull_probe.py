@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "instant-ngp-pp_b200")]
 import torch
 from ngp_b200 import vren
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 dev = torch.device("cuda", 0)
 scene = BoxScene("lego", device=dev); poses = scene.poses(100)
 grid = scene_density_grid(scene)

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "instant-ngp-pp_
 import torch
 from ngp_b200 import vren, tcnn
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.custom_functions import RayMarcher
 
 dev = torch.device("cuda", 0)

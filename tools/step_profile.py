@@ -6,7 +6,7 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 from ngp_b200 import vren
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.trainer import Trainer
 
 dev = torch.device("cuda", 0)

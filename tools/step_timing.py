@@ -4,7 +4,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "instant-ngp-pp_
 import torch
 from ngp_b200 import vren
 from ngp_b200.networks import NGPCompact
-from ngp_b200.synthetic import BoxScene, scene_density_grid
+from synth_scenes import BoxScene, scene_density_grid
 from ngp_b200.trainer import Trainer
 
 dev = torch.device("cuda", 0)
