@@ -165,7 +165,7 @@ def kernel_breakdown_ngp(model, xyzs, dirs):
     emb = torch.randn(S, model.rgb_net.n_input_dims - 16 - feat.shape[1], device=xw.device)
     segs = [(dirs, 16, 1), (feat, feat.shape[1], 0)] + ([(emb, emb.shape[1], 0)] if emb.shape[1] else [])
     k0 = model.rgb_net.n_input_dims
-    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
+    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * m.n_out)      # useful flops: real output columns only
     rgb = tcnn.mlp_forward(segs, p2, m2)
     out["mlp_rgb_fw"] = (time_kernel(lambda: tcnn.mlp_forward(segs, p2, m2), 3), S * flops(m2, k0), "F")
     drgb = torch.randn_like(rgb)
@@ -197,7 +197,7 @@ def kernel_breakdown(model, xyzs, dirs):
     m1, m2 = model.sigma_net.mlp, model.rgb_net.mlp
     p1, p2 = model.sigma_net.params.detach(), model.rgb_net.params.detach()
     h, _ = tcnn.mlp_forward([(tiles, LF, 2)], p1, m1, aux_exp=True, n=S)
-    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * ((m.n_out + 15) // 16 * 16))
+    flops = lambda m, k0: 2 * (k0 * m.width + (m.n_hidden - 1) * m.width ** 2 + m.width * m.n_out)      # useful flops: real output columns only
     out["mlp_sigma_fw"] = (time_kernel(lambda: tcnn.mlp_forward([(tiles, LF, 2)], p1, m1, aux_exp=True, n=S)), S * flops(m1, LF), "F")
     dh = torch.randn_like(h); ds = torch.randn(S, device=xw.device)
     out["mlp_sigma_bw"] = (time_kernel(lambda: tcnn.mlp_backward([(tiles, LF, 2)], p1, m1, dh, [True], d_aux=ds, n=S, dseg_numel=dy_tiles.numel(), saved_out=h)),
@@ -303,6 +303,8 @@ def gpu_arm(args):
                  extra_params=emb.parameters() if full else ())
 
     R = wl.get("rays", R_PER_GPU)
+    if args.scaling == "strong":      # total rays per step fixed at the 1-GPU batch, sharded over the ranks (configs[2]: 2^18 rays over 8 GPUs)
+        R = R_PER_GPU // world
     n_batches = 8
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)       # each rank draws its own shard of the global batch
     W_, H_ = scene.img_wh
@@ -465,36 +467,45 @@ def gpu_arm(args):
             kern[k] = {"ms": sec * 1e3, "achieved_TFLOPs": work / sec / 1e12, "frac_tensor": work / sec / 1e12 / pk["bf16_tflops_sustained"]}
     dom = max(kb, key=lambda k: kb[k][0])
     sec, work, unit = kb[dom]
-    roof = {"kernel": dom, "bound": "hbm" if unit == "B" else "tensor", "achieved": work / sec / (1e9 if unit == "B" else 1e12),
-            "peak": pk["hbm_gbs"] if unit == "B" else pk["bf16_tflops_sustained"], "unit": "GB/s" if unit == "B" else "TFLOP/s",
-            "peak_source": pk_src, "traffic": None, "samples_per_launch": int(xyzs.shape[0])}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    try:    # measured DRAM bytes per launch of that kernel: per-sample figure of the committed ncu capture x this launch's samples
-        import glob
-        tr_ = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))   # newest capture
-        if tr_["kernel"] == dom:
-            roof["traffic"] = tr_["dram_bytes_per_sample"] * int(xyzs.shape[0])
-            roof["traffic_source"] = tr_["source"]
-            if "red_sectors_per_sample" in tr_:      # what actually bounds the kernel: L2 reduction requests per second
-                rate = tr_["red_sectors_per_sample"] * int(xyzs.shape[0]) / sec / 1e9
-                roof["limiter"] = {"resource": "L2 reduction sector requests", "achieved_G_per_s": rate,
-                                   "peak_G_per_s": tr_.get("red_peak_G_per_s", 220.0), "frac": rate / tr_.get("red_peak_G_per_s", 220.0),
-                                   "peak_source": "tools/probes/l2_red_probe.cu on B200 (random sectors of a 43 MB L2-resident table)",
-                                   "sectors_per_sample": tr_["red_sectors_per_sample"]}
-    except Exception:
-        pass
-    table_mb = (model.rgb_encoder if (full and dom.endswith("_rgb")) else model.xyz_encoder).params.numel() * 4 / 2 ** 20
-    if table_mb < 100:
-        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d: 12 + L*F*4 + 2*8*L*F*4 per sample) / CUDA-event time; the %.0f MB fp32 "
-                        "table is L2 resident, so table traffic never reaches HBM and frac can exceed 1 - the kernel is bound by L2 "
-                        "reduction sector requests (~220 G/s, tools/probes/l2_red_probe.cu; ncu lts__throughput 80 %%), see "
-                        "profiles/r01d_ncu_hashgrid_bw_params_kernel.txt" % table_mb)
+    S_l = int(xyzs.shape[0])
+    if unit == "F":
+        roof = {"kernel": dom, "bound": "tensor", "achieved": work / sec / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "peak_source": pk_src, "traffic": None, "samples_per_launch": S_l}
+        roof["frac"] = roof["achieved"] / roof["peak"]
     else:
-        roof["note"] = ("achieved = algorithmic bytes (SURVEY 8d) / CUDA-event time; the %.0f MB fp32 table exceeds the 126 MB L2: the "
-                        "launch walks level chunks slowest (GridMeta::chunk_major, hashgrid.cu) so that only one chunk's levels are "
-                        "live in L2 at a time; block-order probe in profiles/r01e_hash_block_order_probe.txt" % table_mb)
-        roof["traffic"] = None
-    cpu, _ = cpu_arm(steps=3, warmup=1)
+        # HBM-bound class.  `achieved` is the kernel's MEASURED DRAM traffic per launch (dram__bytes_read+write of the committed
+        # ncu --set full capture of this kernel, per sample, x this launch's samples) over its live CUDA-event time: a physical
+        # fraction of the HBM peak.  The ALGORITHMIC bytes are reported beside it: for a table that lives in the
+        # 126 MB L2 they exceed what HBM could deliver, which is the point of keeping the table resident — the kernel is then
+        # bound by the L2's reduction request rate, whose peak is re-measured in this run (ngp_probe_l2_reduction).
+        roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_source": pk_src,
+                "frac": None, "traffic": None, "samples_per_launch": S_l,
+                "algorithmic": {"bytes_per_launch": work, "GBs": work / sec / 1e9, "over_hbm_peak": work / sec / 1e9 / pk["hbm_gbs"],
+                                "formula": "SURVEY 8d: scatter 12 + L*F*4 + 2*8*L*F*4, gather 12 + 8*L*F*4 + L*F*s_out bytes per sample"}}
+        try:
+            import glob
+            cands = [json.load(open(f)) for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))]
+            cands = [t for t in cands if t["kernel"] == dom and t.get("workload", "lego") == args.workload]
+            tr_ = cands[-1]                                                    # newest capture of this kernel on this workload
+            roof["traffic"] = tr_["dram_bytes_per_sample"] * S_l
+            roof["traffic_source"] = tr_["source"]
+            roof["achieved"] = roof["traffic"] / sec / 1e9
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            if "red_sectors_per_sample" in tr_:
+                from ngp_b200._lib import lib as _l, ptr as _p, stream as _s
+                table_b = (model.rgb_encoder if (full and dom.endswith("_rgb")) else model.xyz_encoder).params.numel() * 4
+                buf = torch.zeros(table_b // 4, device=dev)
+                probe = lambda: _l.ngp_probe_l2_reduction(_p(buf), table_b, 64, _s())
+                n_req = probe(); torch.cuda.synchronize()
+                peak_req = n_req / time_kernel(probe, 3) / 1e9
+                rate = tr_["red_sectors_per_sample"] * S_l / sec / 1e9
+                roof["limiter"] = {"resource": "L2 reduction sector requests (one per 32-byte sector per instruction)", "achieved_G_per_s": rate,
+                                   "peak_G_per_s": peak_req, "frac": rate / peak_req, "sectors_per_sample": tr_["red_sectors_per_sample"],
+                                   "peak_source": f"ngp_probe_l2_reduction timed in this run on a zeroed {table_b >> 20} MB buffer (the table's size)"}
+                del buf
+        except Exception as ex:
+            roof["traffic_note"] = "no committed ncu capture for this kernel / workload: " + repr(ex)[:120]
+    cpu = None if args.no_cpu else cpu_arm(steps=3, warmup=1)[0]
     value = world * R * args.steps / t_res
     # reference GPU path on the same box, same run: the reference's unmodified glue + its own CUDA kernels + a
     # torch-op tinycudann stand-in, same scene / batch recipe / lr / Adam eps, trained args.ref_steps steps, last 10 timed
@@ -515,19 +526,36 @@ def gpu_arm(args):
             ref_gpu["reference_glue_on_libngp_b200"] = {k: drop[k] for k in ("value", "unit", "ms_per_step", "psnr_after_steps", "samples_per_ray")}
         except Exception as ex:            # baseline/_ref or vren_ref.so not present on this box
             ref_gpu = {"unavailable": repr(ex)[:300]} if ref_gpu is None else ref_gpu
+    others = None
+    if args.workload == "lego" and world == 1 and args.other_configs:
+        # BASELINE.json configs[3] / configs[2] shapes, short runs of this same script (their own processes: fresh allocator, own
+        # model), so that the driver-run line carries them too; each is a full line of its own under --workload
+        others = {}
+        for wname in ("street", "playground"):
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wname, "--steps", "8", "--warmup", "3", "--pretrain", "40",
+                                      "--ref-steps", "0", "--no-cpu", "--no-render"], capture_output=True, text=True, timeout=600)
+                sub = json.loads(out.stdout.strip().splitlines()[-1])
+                others[wname] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "roofline")}
+                others[wname].update({"workload": sub["config"]["workload"], "samples_per_ray": sub["config"]["samples_per_ray"],
+                                      "rays_per_gpu": sub["config"]["rays_per_gpu"], "psnr_after_pretrain": sub["config"]["psnr_after_pretrain"],
+                                      "pretrain_steps": sub["config"]["pretrain_steps"], "e2e": sub["e2e"]})
+            except Exception as ex:
+                others[wname] = {"error": repr(ex)[:300]}
     line = {
         "metric": "train rays/s (fw+bw)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "fp32 (bf16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": wl["name"], "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr, "samples_per_ray_timed_steps": {"min": min(spr_timed), "max": max(spr_timed), "mean": sum(spr_timed) / len(spr_timed)},
                    "pretrain_steps": args.pretrain, "psnr_after_pretrain": q, "l2": "inputs_exceed_l2 (>250 MB of samples per step)",
-                   "parallelism": f"ray-sharded dp{world}, NCCL all-reduce of table+MLP gradients" if world > 1 else "single GPU",
+                   "parallelism": (f"ray-sharded dp{world} ({args.scaling} scaling), NCCL all-reduce of table+MLP gradients; table slices all-reduced "
+                                   "under the remaining scatter launches (tcnn.GradSink)") if world > 1 else "single GPU",
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
         "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / args.steps * 1e3,
                 "path": "pinned host (img_idxs i64, pix_idxs i64, rgb f32[, label]) -> H2D on a copy stream one step ahead -> ngp_get_rays -> "
                         "Trainer.train_step(host_loss=True): loss -> pinned host right after the forward pass, waited for after the step is enqueued; every step"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "render": rend,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "render": rend, "configs": others,
     }
     print(json.dumps(line))
     if world > 1:
@@ -537,14 +565,18 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--pretrain", type=int, default=400)
     ap.add_argument("--ref-steps", type=int, default=100, help="steps the reference-GPU arm trains (PSNR is compared after the same number of steps); 0 = skip")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lego", choices=sorted(WORKLOADS), help="lego = BASELINE.json configs[1] (the headline); street = configs[3] shape")
     ap.add_argument("--no-render", action="store_true", help="skip the test-time render sweep")
-    ap.add_argument("--render-4k", action="store_true", help="also render 3840x2160 frames (BASELINE.json configs[4])")
+    ap.add_argument("--no-render-4k", dest="render_4k", action="store_false", help="skip the 3840x2160 frames of the render sweep (BASELINE.json configs[4])")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 2^18 rays per GPU (default); strong: 2^18 rays per step in total, sharded over the ranks")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
+                    help="skip the short street (configs[3]) / playground (configs[2]) runs appended to the headline line as `configs`")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) != 0:

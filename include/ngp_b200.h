@@ -22,6 +22,10 @@ extern "C" {
 int ngp_abi_version(void);
 const char* ngp_last_error(void);
 int ngp_check_device(void); /* 0 iff the current device is compute capability 10.x */
+/* diagnostic (no reference counterpart): issues `iters` rounds of lane-pair red.global.add.v2.f32 into random 32-byte
+ * sectors of `table` (the hash-gradient scatter's access pattern); returns the number of L2 sector requests issued.
+ * bench.py times it to measure, in the same run, the L2 reduction request rate that bounds hashgrid_bw_params. */
+int64_t ngp_probe_l2_reduction(float* table, int64_t table_bytes, int iters, void* stream);
 
 /* ------------------------------------------------------------------ a1: intersections
  * vren.ray_aabb_intersect  binding.cpp:4-16  -> intersection.cu:59-100
@@ -176,6 +180,12 @@ int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void* table, 
 int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, const float* dy_tiles, int n_levels, int n_features,
                                  int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
                                  float* dtable, void* stream);
+/* the same scatter restricted to levels [level_begin, level_end) (level_begin a multiple of 4/F): a level range is one
+ * contiguous slice of the flat table gradient, so the caller can start the data-parallel all-reduce of a finished slice
+ * (Lightning DDP's bucketed all-reduce, train.py:431) while the next range is being scattered. */
+int ngp_hashgrid_bw_params_tiles_range(const float* x, const float* aabb, const float* dy_tiles, int n_levels, int n_features,
+                                       int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n,
+                                       float* dtable, int level_begin, int level_end, void* stream);
 
 /* ------------------------------------------------------------------ a11: SH direction encoding
  * tcnn.Encoding(3, {"otype":"SphericalHarmonics","degree":4|3})  models/networks.py:78-85,128-135 */

@@ -36,3 +36,29 @@ NGP_API int ngp_check_device(void) {
   }
   return 0;
 }
+
+// ---- diagnostics -------------------------------------------------------------------------------------------------
+// Measures the rate at which the L2 executes reduction SECTOR requests, the resource that bounds the hash-table gradient
+// scatter (hashgrid.cu): every lane pair issues one red.global.add.v2.f32 pair into the same random 32-byte sector of
+// `table` (= one request, the scatter's access pattern for x-neighbours).  bench.py times this launch in the same run to
+// obtain the denominator of `roofline.limiter`; returns the number of sector requests issued, or < 0 on error.
+namespace ngp {
+__device__ __forceinline__ uint32_t probe_mix(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void __launch_bounds__(256) l2_red_probe_kernel(float* __restrict__ table, uint32_t n_sectors, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  for (int it = 0; it < iters; it++) {
+    const uint32_t sec = probe_mix((tid >> 1) * 2654435761u + it * 40503u) % n_sectors;
+    atomicAdd(reinterpret_cast<float2*>(table + (size_t)sec * 8) + ((lane & 1) + (probe_mix(tid >> 1) & 2)), make_float2(0.f, 0.f));
+  }
+}
+}  // namespace ngp
+
+NGP_API int64_t ngp_probe_l2_reduction(float* table, int64_t table_bytes, int iters, void* stream) {
+  if (table_bytes < 32 || iters < 1) return ngp::set_error_msg("ngp_probe_l2_reduction: need table_bytes >= 32 and iters >= 1");
+  const int blocks = ngp::kSMs * 32, threads = 256;
+  ngp::l2_red_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(table, (uint32_t)(table_bytes / 32), iters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int64_t)ngp::set_error(e, "ngp_probe_l2_reduction");
+  return (int64_t)blocks * threads / 2 * iters;
+}

@@ -50,6 +50,7 @@ struct GridMeta {
   // and L2 at 46 % — the misses that matter are the reductions' own sector fetches, L2 hit rate 54 %).
   int chunk_major;
   uint32_t n_sblocks;      // sample blocks of this launch (chunk_major only)
+  int chunk0, level_end;   // scatter over a level RANGE [chunk0 * LC, level_end) (ngp_hashgrid_bw_params_tiles_range); default 0, n_levels
 };
 __device__ __forceinline__ void block_coords(const GridMeta& m, int n_chunks, uint32_t& sblock, int& chunk) {
   if (m.chunk_major) { chunk = (int)(blockIdx.x / m.n_sblocks); sblock = blockIdx.x % m.n_sblocks; }
@@ -285,13 +286,13 @@ template <int F, int LC, bool DYT, bool H2 = false, bool PF = false>
 __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                  GridMeta m, int64_t n, float* __restrict__ dtable, int spt,
                                                                  const float* __restrict__ g2 = nullptr) {
-  const int n_chunks = (m.n_levels + LC - 1) / LC;
+  const int n_chunks = (m.level_end + LC - 1) / LC - m.chunk0;
   uint32_t sblock; int chunk;
   block_coords(m, n_chunks, sblock, chunk);                 // GridMeta::chunk_major
   const int64_t s0 = ((int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
   const uint32_t xh = threadIdx.x & 1u;
   if (s0 >= n) return;
-  const int l0 = chunk * LC;
+  const int l0 = (chunk + m.chunk0) * LC;
   const int LF = m.n_levels * F;
   CellAcc<F> acc[LC];
 #pragma unroll
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
 #pragma unroll
       for (int f = 0; f < F; f++) any |= g[li * F + f] != 0.f;
       if (H2) any = any && (hx != 0.f || hy != 0.f || hz != 0.f);
-      if (l < m.n_levels && any) {
+      if (l < m.level_end && any) {
         const Cell c = locate(xx, xy, xz, m.scale[l]);
         CellAcc<F>& A = acc[li];
         if (!A.has || A.px != c.px || A.py != c.py || A.pz != c.pz) {
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_kernel(const float* __
 #pragma unroll
   for (int li = 0; li < LC; li++) {
     const int l = l0 + li;
-    if (l < m.n_levels && acc[li].has)
+    if (l < m.level_end && acc[li].has)
       flush_cell<F>(acc[li], xh, dtable + (size_t)m.offset[l] * F, m.res[l], m.size[l], m.dense[l]);
   }
 }
@@ -386,7 +387,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_params_f8_kernel(const float*
   constexpr int F = 8;
   constexpr bool H2 = MODE != 0;
   uint32_t sblock; int l;
-  block_coords(m, m.n_levels, sblock, l);                   // one level per lane pair
+  block_coords(m, m.level_end - m.chunk0, sblock, l);       // one level per lane pair
+  l += m.chunk0;
   const int64_t s0 = ((int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1)) * spt;
   const uint32_t fh = (threadIdx.x & 1u) * 4u;              // this lane's feature half
   if (s0 >= n) return;
@@ -552,7 +554,7 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
     off += (uint32_t)sz;
   }
   m.offset[n_levels] = off;
-  m.chunk_major = 0; m.n_sblocks = 1;
+  m.chunk_major = 0; m.n_sblocks = 1; m.chunk0 = 0; m.level_end = n_levels;
   return 0;
 }
 
@@ -748,22 +750,37 @@ NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void*
   NGP_LAUNCH_CHECK("ngp_hashgrid_fw_tiles");
   return 0;
 }
-// dtable += scatter(dL/dy) with dL/dy in gradient tiles (ceil(N/128) * 128 * k0p floats, see the kernel).
-NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, const float* dy_tiles, int n_levels,
-                                         int n_features, int log2_hashmap_size, int base_resolution,
-                                         float per_level_scale, int64_t n, float* dtable, void* stream) {
+// dtable += scatter(dL/dy) with dL/dy in gradient tiles (ceil(N/128) * 128 * k0p floats, see the kernel), levels
+// [level_begin, level_end) only.  Launching the scatter as a few level ranges lets the caller hand each finished slice of the
+// table gradient (levels are contiguous in the flat table) to the gradient all-reduce while the next range is still being
+// scattered (ngp_b200/trainer.py).  level_begin must be a multiple of the kernel's levels-per-lane-pair (4/F, 1 for F >= 4).
+NGP_API int ngp_hashgrid_bw_params_tiles_range(const float* x, const float* aabb, const float* dy_tiles, int n_levels,
+                                               int n_features, int log2_hashmap_size, int base_resolution,
+                                               float per_level_scale, int64_t n, float* dtable, int level_begin, int level_end,
+                                               void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
   if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_bw_params_tiles: bad grid config");
+  if (level_begin < 0 || level_end > n_levels || level_begin >= level_end)
+    return set_error_msg("ngp_hashgrid_bw_params_tiles_range: need 0 <= level_begin < level_end <= n_levels");
   NGP_F_DISPATCH(n_features, {
     constexpr int LC = scatter_levels_per_thread<F>();
-    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * ceil_div(n_levels, LC));
+    if (level_begin % LC) return set_error_msg("ngp_hashgrid_bw_params_tiles_range: level_begin must be a multiple of 4/F");
+    const int n_chunks = (int)ceil_div(level_end - level_begin, LC);
+    const unsigned grid = (unsigned)(ceil_div(ceil_div(n, kSPT), 64) * n_chunks);
     set_block_order(m, (size_t)F * 4, ceil_div(ceil_div(n, kSPT), 64));
+    m.chunk0 = level_begin / LC; m.level_end = level_end;
     if (F == 8) hashgrid_bw_params_f8_kernel<true, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
     else if (use_pf(m)) hashgrid_bw_params_kernel<F, LC, true, false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
     else hashgrid_bw_params_kernel<F, LC, true><<<grid, 128, 0, (cudaStream_t)stream>>>(x, dy_tiles, m, n, dtable, kSPT);
   });
-  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles");
+  NGP_LAUNCH_CHECK("ngp_hashgrid_bw_params_tiles_range");
   return 0;
+}
+NGP_API int ngp_hashgrid_bw_params_tiles(const float* x, const float* aabb, const float* dy_tiles, int n_levels,
+                                         int n_features, int log2_hashmap_size, int base_resolution,
+                                         float per_level_scale, int64_t n, float* dtable, void* stream) {
+  return ngp_hashgrid_bw_params_tiles_range(x, aabb, dy_tiles, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, n,
+                                            dtable, 0, n_levels, stream);
 }

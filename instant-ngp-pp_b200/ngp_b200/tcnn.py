@@ -296,6 +296,36 @@ def grid_forward_tiles(x, table, g: GridConfig, aabb=None):
     return tiles
 
 
+class GradSink:
+    """In-place destination of a hash table's gradient for data-parallel training (ngp_b200.trainer.Trainer): the scatter
+    writes straight into `buf` (which the trainer has installed as table.grad) one level range at a time, finest levels
+    first, and `on_ready(a, b)` is called as soon as the range's launch is enqueued with the flat slice [a, b) of `buf`
+    it completes — the trainer starts that slice's all-reduce there, so it runs under the next range's scatter.
+    Registered per table storage in GRAD_SINKS; without an entry the backward returns a fresh dense gradient as before."""
+
+    def __init__(self, buf, grid, on_ready, n_pieces=4):
+        self.buf, self.on_ready = buf, on_ready
+        F = grid.n_features
+        lc = 1 if F >= 4 else 4 // F                           # levels per lane pair of the scatter kernel
+        sizes, L = grid.sizes, grid.n_levels
+        target = sum(sizes) / max(n_pieces - 1, 1)
+        self.ranges, hi, acc = [], L, 0
+        for l in range(L - 1, -1, -1):                         # finest first: they take the most scatter time, the coarse rest is small
+            acc += sizes[l]
+            if acc >= target and l % lc == 0 and l > 0:
+                self.ranges.append((l, hi)); hi, acc = l, 0
+        if hi > 0:            # the remainder: split off the dense coarse levels (a few MB) so that the LAST, exposed all-reduce is the smallest
+            d = next((l for l in range(hi) if sizes[l] == max(sizes)), hi)
+            d -= d % lc
+            if 0 < d < hi:
+                self.ranges.append((d, hi)); hi = d
+            self.ranges.append((0, hi))
+        self.flat = [(grid.offsets[a] * F, grid.offsets[b] * F) for a, b in self.ranges]
+
+
+GRAD_SINKS = {}     # table.data_ptr() -> GradSink
+
+
 class _DensityFieldFn(torch.autograd.Function):
     """(h, sigma) = density_head(MLP(encode(x))) of the ngp_pl-shaped field as ONE autograd node over three kernels
     per direction: the encoder writes bf16 operand tiles, the MLP bulk-copies them (no fp32 feature matrix, no
@@ -324,7 +354,13 @@ class _DensityFieldFn(torch.autograd.Function):
         dparams, dsegs = mlp_backward([(tiles, g.n_levels * g.n_features, 2)], params, m, dh, [need_table], d_aux=dsigma, n=n,
                                       dseg_numel=(n + 127) // 128 * 128 * k0p, saved_out=h)
         dtable = None
-        if need_table:
+        sink = GRAD_SINKS.get(table.data_ptr()) if need_table else None
+        if sink is not None:            # data-parallel: scatter level ranges into table.grad itself, hand each finished slice to the all-reduce
+            for (la, lb), (fa, fb) in zip(sink.ranges, sink.flat):
+                check(lib.ngp_hashgrid_bw_params_tiles_range(ptr(x), _aabb_arg(ctx.aabb), ptr(dsegs[0]), *g.args(), n, ptr(sink.buf), la, lb,
+                                                             stream()), "hashgrid_bw_params_tiles")
+                sink.on_ready(fa, fb)
+        elif need_table:
             dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device)
             check(lib.ngp_hashgrid_bw_params_tiles(ptr(x), _aabb_arg(ctx.aabb), ptr(dsegs[0]), *g.args(), n, ptr(dtable), stream()),
                   "hashgrid_bw_params_tiles")

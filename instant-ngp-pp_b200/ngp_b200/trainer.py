@@ -38,18 +38,48 @@ class Trainer:
         self.step = 0
         self.last_samples = None
         self._loss_host = self._loss_event = None
+        self._works, self._sinks = [], []
+        if world_size > 1 and on_gpu:
+            self._install_grad_sinks()
+
+    def _install_grad_sinks(self):
+        """Overlapped gradient exchange for the hash table of the fused density path (> 99 % of the gradient bytes): the
+        table gradient is scattered level range by level range into a persistent buffer that IS table.grad, and every
+        finished range's all-reduce is issued at once on the process group's stream, under the next range's scatter
+        (tcnn.GradSink).  What stays exposed is the last, smallest range (the dense coarse levels) and the MLP weights."""
+        from . import tcnn
+        enc, net = getattr(self.model, "xyz_encoder", None), getattr(self.model, "sigma_net", None)
+        if enc is None or net is None or not getattr(self.model, "fused_density", False) or enc.params.dtype != torch.float32:
+            return
+        buf = torch.zeros_like(enc.params)
+        sink = tcnn.GradSink(buf, enc.grid, lambda a, b: self._works.append(dist.all_reduce(buf[a:b], op=dist.ReduceOp.SUM, async_op=True)))
+        tcnn.GRAD_SINKS[enc.params.data_ptr()] = sink
+        self._sinks.append((enc.params, sink))
 
     def allreduce_grads(self):
         if self.world_size <= 1:
             return
         # largest tensors first: the hash tables are > 99 % of the bytes
-        ps = sorted((p for p in list(self.model.parameters()) + self.extra_params if p.grad is not None), key=lambda p: -p.numel())
-        works = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
+        sunk = {id(p) for p, _ in self._sinks}           # already in flight, slice by slice, since the backward pass
+        ps = sorted((p for p in list(self.model.parameters()) + self.extra_params if p.grad is not None and id(p) not in sunk),
+                    key=lambda p: -p.numel())
+        works = self._works + [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
+        self._works = []
         for w in works:
             w.wait()
         if not self.fused:                     # the fused optimiser folds 1/world_size into its gradient scale
             for p in ps:
                 p.grad.div_(self.world_size)
+
+    def backward_and_exchange(self, loss):
+        """loss.backward() + the data-parallel gradient sum; afterwards every p.grad holds the SUM over ranks (the optimiser
+        folds in 1/world_size)."""
+        self.opt.zero_grad(set_to_none=True)
+        for p, sink in self._sinks:            # the scatter accumulates in place into table.grad (tcnn.GradSink)
+            sink.buf.zero_()
+            p.grad = sink.buf
+        loss.backward()
+        self.allreduce_grads()
 
     def train_step(self, rays_o, rays_d, rgb_gt, update_grid=True, target=None, host_loss=False, **step_kwargs):
         """-> (loss 0-dim tensor, results dict).  No host sync besides the marcher's sample count.
@@ -71,9 +101,7 @@ class Trainer:
                 self._loss_event = torch.cuda.Event()
             self._loss_host.copy_(loss.detach(), non_blocking=True)
             self._loss_event.record()
-        self.opt.zero_grad(set_to_none=True)
-        loss.backward()
-        self.allreduce_grads()
+        self.backward_and_exchange(loss)
         self.opt.step()
         self.step += 1
         self.last_samples = results["total_samples"]

@@ -320,3 +320,40 @@ def test_hashgrid_block_order_does_not_change_results(F, monkeypatch):
         k0p = 32
         v = lambda t: t.view(-1, k0p // 8, 128 * 16 + 64)[:, :, :128 * 16]
         assert torch.equal(v(out["0"][2]), v(out["1"][2]))
+
+
+@pytest.mark.parametrize("n", [129, 40001])
+def test_grad_sink_level_ranges_equal_full_scatter(n):
+    """tcnn.GradSink (data-parallel gradient exchange): the table gradient scattered level range by level range, finest
+    first, straight into table.grad must equal the one-launch scatter (the ranges partition the levels; within a level
+    the same reductions are issued), and every range must be announced exactly once with its flat slice."""
+    from ngp_b200 import tcnn
+    enc, _ = _grid(16, 2, 15, 16, 0.5)
+    net = tcnn.Network(32, 16, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                                "n_neurons": 64, "n_hidden_layers": 1}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = (torch.rand(n, 3, device="cuda", generator=g) - 0.5)
+    aabb = (-0.5, -0.5, -0.5, 1.0, 1.0, 1.0)
+    gh = torch.randn(n, 16, device="cuda", generator=g); gs = torch.randn(n, device="cuda", generator=g)
+
+    def run():
+        enc.params.grad = None; net.params.grad = None
+        h, sig = net.forward_density_field(x, enc, aabb)
+        return h, sig
+    h, sig = run()
+    ((h * gh).sum() + (sig * gs).sum()).backward()
+    full = enc.params.grad.clone()
+    buf = torch.zeros_like(enc.params)
+    seen = []
+    sink = tcnn.GradSink(buf, enc.grid, lambda a, b: seen.append((a, b)))
+    assert sink.ranges[0][1] == 16 and sink.ranges[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(sink.ranges, sink.ranges[1:]))
+    tcnn.GRAD_SINKS[enc.params.data_ptr()] = sink
+    try:
+        h, sig = run()
+        enc.params.grad = buf
+        ((h * gh).sum() + (sig * gs).sum()).backward()
+    finally:
+        tcnn.GRAD_SINKS.clear()
+    assert enc.params.grad is buf and seen == sink.flat
+    assert sorted(seen)[0][0] == 0 and sorted(seen)[-1][1] == buf.numel()
+    assert rel(buf, full) < 1e-5
