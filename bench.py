@@ -445,6 +445,13 @@ def gpu_arm(args):
         rend = render_bench(model, scene, poses, rank=rank, world=world, esf=wl["esf"])
         if args.render_4k:
             rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world, esf=wl["esf"])
+    dp_exchange = None
+    if world > 1:     # what the gradient exchange costs: the same step with the exchange switched off (replicas diverge: timing only, last thing done)
+        tr._exchange = "none"
+        t_none, _, _ = timed(step_resident, min(args.steps, 20))
+        per, per_none = t_res / args.steps * 1e3, t_none / min(args.steps, 20) * 1e3
+        dp_exchange = {"ms_per_step_with_exchange": per, "ms_per_step_without_exchange": per_none, "exposed_ms": per - per_none,
+                       "frac_of_step": (per - per_none) / per, "mode": "per-tensor NCCL all-reduce after backward (see profiles/r02b_dp_exchange_probe.txt)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -548,14 +555,13 @@ def gpu_arm(args):
         "vs_baseline": None, "dtype": "fp32 (bf16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": wl["name"], "rays_per_gpu": R, "global_batch_rays": world * R, "samples_per_ray": spr, "samples_per_ray_timed_steps": {"min": min(spr_timed), "max": max(spr_timed), "mean": sum(spr_timed) / len(spr_timed)},
                    "pretrain_steps": args.pretrain, "psnr_after_pretrain": q, "l2": "inputs_exceed_l2 (>250 MB of samples per step)",
-                   "parallelism": (f"ray-sharded dp{world} ({args.scaling} scaling), NCCL all-reduce of table+MLP gradients; table slices all-reduced "
-                                   "under the remaining scatter launches (tcnn.GradSink)") if world > 1 else "single GPU",
+                   "parallelism": f"ray-sharded dp{world} ({args.scaling} scaling), NCCL all-reduce of table+MLP gradients after backward" if world > 1 else "single GPU",
                    "occupancy": "analytic voxelisation at step 0, then update_density_grid every 16 steps (inside the timed region)"},
         "e2e": {"value": world * R * args.steps / t_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": t_e2e / args.steps * 1e3,
                 "path": "pinned host (img_idxs i64, pix_idxs i64, rgb f32[, label]) -> H2D on a copy stream one step ahead -> ngp_get_rays -> "
                         "Trainer.train_step(host_loss=True): loss -> pinned host right after the forward pass, waited for after the step is enqueued; every step"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "render": rend, "configs": others,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "render": rend, "configs": others, "dp_exchange": dp_exchange,
     }
     print(json.dumps(line))
     if world > 1:

@@ -20,7 +20,7 @@ from .rendering import render
 class Trainer:
     def __init__(self, model, lr=1e-2, eps=1e-15, update_interval=16, warmup_steps=256, density_threshold=0.01 * 1024 / 3 ** 0.5,
                  lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1, max_grad_norm=None,
-                 extra_params=()):
+                 extra_params=(), exchange="after"):
         self.model = model
         self.loss_fn = NeRFLoss(lambda_opa=lambda_opa, lambda_distortion=lambda_distortion)
         # extra_params: parameters outside the field that the step also trains (the appearance embedding, train.py:117-119)
@@ -39,7 +39,14 @@ class Trainer:
         self.last_samples = None
         self._loss_host = self._loss_event = None
         self._works, self._sinks = [], []
-        if world_size > 1 and on_gpu:
+        # Gradient exchange mode.  "after" (default): per-tensor async all-reduce issued after backward(), waited for before Adam.
+        # "overlap": table slices all-reduced under the remaining scatter launches (tcnn.GradSink) — measured SLOWER on B200 +
+        # NVSwitch for the 44 MB table (profiles/r02b_dp_exchange_probe.txt: 7.22 vs 7.09 ms/step at N=2; the all-reduce is only
+        # 0.04 ms exposed and competes with the L2-bound scatter when overlapped), kept for tables where the exchange is long.
+        # "none": timing probe only.  NGP_DP_EXCHANGE overrides.
+        import os
+        self._exchange = os.environ.get("NGP_DP_EXCHANGE", exchange)
+        if world_size > 1 and on_gpu and self._exchange == "overlap":
             self._install_grad_sinks()
 
     def _install_grad_sinks(self):

@@ -42,14 +42,14 @@ def _worker(rank, world, port, out):
         return orig_rand_like(t, *a, **k)
     torch.rand_like = fake_rand_like
 
-    def make(ws):
+    def make(ws, exchange="after"):
         torch.manual_seed(0)
         m = NGPCompact(scale=0.5, log2_T=17).to(dev)
         with torch.no_grad():
             m.xyz_encoder.params.mul_(3000.0)
         m.density_grid.copy_(scene_density_grid(scene))
         vren.packbits(m.density_grid, 0.5, m.density_bitfield)
-        return m, Trainer(m, world_size=ws, render_kwargs=dict(exp_step_factor=0.0, num_classes=0))
+        return m, Trainer(m, world_size=ws, render_kwargs=dict(exp_step_factor=0.0, num_classes=0), exchange=exchange)
 
     def grads(tr, m, o, d, c):
         res = render(m, o, d, **tr.render_kwargs)
@@ -57,24 +57,28 @@ def _worker(rank, world, port, out):
         tr.backward_and_exchange(sum(v.mean() for v in losses.values()))
         return {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}, int(res["total_samples"])
 
-    m, tr = make(world)
-    assert len(tr._sinks) == 1 and len(tr._sinks[0][1].ranges) >= 3          # the overlapped exchange is really in use
+    from ngp_b200 import tcnn
     h = R // world
-    state["off"] = rank * h
-    g_dp, n_dp = grads(tr, m, ro[rank * h:(rank + 1) * h].contiguous(), rd[rank * h:(rank + 1) * h].contiguous(), rgb[rank * h:(rank + 1) * h].contiguous())
-    g_dp = {k: v / world for k, v in g_dp.items()}          # the fused optimiser's 1/world_size
-    tot = torch.tensor([n_dp], device=dev); dist.all_reduce(tot)
-    # replicas hold bit-identical summed gradients
-    for k, v in g_dp.items():
-        other = v.clone(); dist.broadcast(other, 0)
-        assert torch.equal(other, v), k
+    result = {}
+    for exchange in ("after", "overlap"):      # both exchange modes of the trainer
+        tcnn.GRAD_SINKS.clear()
+        m, tr = make(world, exchange)
+        if exchange == "overlap":
+            assert len(tr._sinks) == 1 and len(tr._sinks[0][1].ranges) >= 3          # the sliced exchange is really in use
+        state["off"] = rank * h
+        g_dp, n_dp = grads(tr, m, ro[rank * h:(rank + 1) * h].contiguous(), rd[rank * h:(rank + 1) * h].contiguous(), rgb[rank * h:(rank + 1) * h].contiguous())
+        g_dp = {k: v / world for k, v in g_dp.items()}          # the fused optimiser's 1/world_size
+        tot = torch.tensor([n_dp], device=dev); dist.all_reduce(tot)
+        for k, v in g_dp.items():                               # replicas hold bit-identical summed gradients
+            other = v.clone(); dist.broadcast(other, 0)
+            assert torch.equal(other, v), k
+        result[exchange] = ({k: v.cpu() for k, v in g_dp.items()}, int(tot))
     if rank == 0:
-        from ngp_b200 import tcnn
         tcnn.GRAD_SINKS.clear()
         m1, tr1 = make(1)
         state["off"] = 0
         g_un, n_un = grads(tr1, m1, ro, rd, rgb)
-        torch.save({"dp": {k: v.cpu() for k, v in g_dp.items()}, "un": {k: v.cpu() for k, v in g_un.items()}, "n": (int(tot), n_un)}, out)
+        torch.save({"dp": result, "un": {k: v.cpu() for k, v in g_un.items()}, "n_un": n_un}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,9 +89,10 @@ def test_two_rank_nccl_gradients_equal_union_batch(tmp_path):
     out = str(tmp_path / "g.pt")
     mp.spawn(_worker, args=(2, 29600 + os.getpid() % 2000, out), nprocs=2, join=True)
     r = torch.load(out)
-    assert r["n"][0] == r["n"][1] > 0                                      # same samples in total: the marcher is per ray
-    assert set(r["dp"]) == set(r["un"])
-    for k in r["un"]:
-        a, b = r["dp"][k], r["un"][k]
-        rel = float((a - b).norm() / b.norm().clamp(min=1e-30))
-        assert rel < (1e-4 if "encoder" in k else 1e-3), (k, rel)
+    for mode, (g_dp, n_dp) in r["dp"].items():
+        assert n_dp == r["n_un"] > 0                                       # same samples in total: the marcher is per ray
+        assert set(g_dp) == set(r["un"])
+        for k in r["un"]:
+            a, b = g_dp[k], r["un"][k]
+            rel = float((a - b).norm() / b.norm().clamp(min=1e-30))
+            assert rel < (1e-4 if "encoder" in k else 1e-3), (mode, k, rel)
