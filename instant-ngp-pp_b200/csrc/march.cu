@@ -142,6 +142,25 @@ __global__ void __launch_bounds__(256) coarse_occupancy_kernel(const uint8_t* __
   if ((i & 31u) == 0) coarse[i >> 5] = w;
 }
 
+// true when the segment [t, t2] of a ray provably stays clear of every occupied cell (coarse lattice above): the stepping
+// loop would then find no sample whatever its roundings.  false = "cannot tell, march it" (also for degenerate directions).
+__device__ __forceinline__ bool segment_is_clear(float ox, float oy, float oz, float dx, float dy, float dz, float t, float t2,
+                                                 const MarchParams& p) {
+  const float step = p.cull_span / fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));   // 4 cells along the fastest axis
+  if (!(step > 0.f) || !(step < 1e30f)) return false;                                // degenerate direction: just march it
+  int guard = 0;
+  for (float tc = t;; tc += step) {
+    if (++guard > 1024) return false;                                                // step below the resolution of t: just march it
+    const float tt = fminf(tc, t2);
+    const float cx = __fmaf_rn(tt, dx, ox), cy = __fmaf_rn(tt, dy, oy), cz = __fmaf_rn(tt, dz, oz);
+    const int bx = (int)fmaxf(0.0f, fminf(16.0f * (cx * p.mb0_inv + 1.0f), 31.0f));
+    const int by = (int)fmaxf(0.0f, fminf(16.0f * (cy * p.mb0_inv + 1.0f), 31.0f));
+    const int bz = (int)fmaxf(0.0f, fminf(16.0f * (cz * p.mb0_inv + 1.0f), 31.0f));
+    if ((__ldg(p.coarse + by + 32 * bz) >> bx) & 1u) return false;                   // near something occupied
+    if (tc >= t2) return true;                                                       // clear all the way
+  }
+}
+
 // Pass 0 (single cascade with a coarse lattice): thread per ray, ~30 short trips.  Rays that cannot produce a sample get
 // n_samples = 0 here; the others are appended to `live`, the queue the persistent pass 1 draws from (the order of the
 // queue is arbitrary, every output is indexed by the ray).  Doing the check inside pass 1 instead made its warps run
@@ -159,19 +178,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_cull_kernel(
     if (t >= 0) t = __fmaf_rn(p.dt0, __ldg(noise + r), t);            // the march's own start (raymarching.cu:195-198)
     if (0 <= t && t < t2) {
       const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
-      const float step = p.cull_span / fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));   // 4 cells along the fastest axis
-      if (!(step > 0.f) || !(step < 1e30f)) keep = true;                                 // degenerate direction: just march it
-      int guard = 0;
-      for (float tc = t; !keep; tc += step) {
-        if (++guard > 1024) { keep = true; break; }                     // step below the resolution of t: just march it
-        const float tt = fminf(tc, t2);
-        const float cx = __fmaf_rn(tt, dx, ox), cy = __fmaf_rn(tt, dy, oy), cz = __fmaf_rn(tt, dz, oz);
-        const int bx = (int)fmaxf(0.0f, fminf(16.0f * (cx * p.mb0_inv + 1.0f), 31.0f));
-        const int by = (int)fmaxf(0.0f, fminf(16.0f * (cy * p.mb0_inv + 1.0f), 31.0f));
-        const int bz = (int)fmaxf(0.0f, fminf(16.0f * (cz * p.mb0_inv + 1.0f), 31.0f));
-        if ((__ldg(p.coarse + by + 32 * bz) >> bx) & 1u) keep = true;   // near something occupied
-        else if (tc >= t2) break;                                        // clear all the way
-      }
+      keep = !segment_is_clear(ox, oy, oz, dx, dy, dz, t, t2, p);
     }
     if (!keep) n_samples[r] = 0;
   }
@@ -383,6 +390,9 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
   float x, y, z, dt, t_mark = t;
   int s = 0;
   const int64_t base = n * n_samples_max;
+  // single-cascade culling (march_cull_kernel's test): a ray whose remaining segment is provably empty returns N_eff = 0 and
+  // an untouched hits_t without the ~200 trips of the stepping loop — the same outputs the loop would produce
+  if (p.coarse && t < t2 && segment_is_clear(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, t, t2, p)) t = t2;
   while (t < t2 && s < n_samples_max) {
     if (march_step(q, p, t, x, y, z, dt)) {
       const int64_t o = base + s;
@@ -463,6 +473,7 @@ __global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
   const float t2 = hits_t[2 * r + 1];
   float2* row = scratch + j * kScratch;
   int s = 0;
+  if (p.coarse && t < t2 && segment_is_clear(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, t, t2, p)) t = t2;   // provably empty: N = 0
   while (t < t2 && s < n_next) {
     if (march_step(q, p, t, x, y, z, dt)) {
       row[s] = make_float2(t, dt);
@@ -491,6 +502,11 @@ static MarchParams make_params(const uint8_t* bitfield, int cascades, float scal
   p.coarse = nullptr;
   p.cull_span = 8.0f * p.mb0 / (float)grid_size;      // 4 cells of 2*mip_bound/G
   return p;
+}
+
+static bool cull_enabled() {
+  static const bool on = !(getenv("NGP_MARCH_CULL") && atoi(getenv("NGP_MARCH_CULL")) == 0);
+  return on;
 }
 
 }  // namespace ngp
@@ -548,7 +564,7 @@ NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d
   const int64_t gmax = (int64_t)kSMs * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
   const int G = (int)(ceil_div(n_rays, kMarchBlock) < gmax ? ceil_div(n_rays, kMarchBlock) : gmax);
   const int row_len = max_samples < kTrainRow ? (max_samples < 1 ? 1 : max_samples) : kTrainRow;
-  static const bool cull_on = !(getenv("NGP_MARCH_CULL") && atoi(getenv("NGP_MARCH_CULL")) == 0);
+  const bool cull_on = cull_enabled();
   if (simple && cull_on && grid_size == 128 && n_rays >= 2048 && ((uintptr_t)density_bitfield & 7u) == 0) {
     MarchParams pc = p;
     uint32_t* coarse = coarse_of(w, n_rays, kTrainRow);
@@ -595,11 +611,22 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
                                  int grid_size, int max_samples, int n_samples, int64_t n_alive, float* xyzs,
                                  float* dirs, float* deltas, float* ts, int32_t* n_eff_samples, void* stream) {
   if (n_alive <= 0) return 0;
-  const MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
   const int B = (int)ceil_div(n_alive, kMarchBlock);
-  march_test_kernel<<<B, kMarchBlock, 0, (cudaStream_t)stream>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples,
-                                                                 n_alive, xyzs, dirs, deltas, ts, n_eff_samples);
+  cudaStream_t s = (cudaStream_t)stream;
+  // empty-ray culling (single cascade, no exponential stepping: the synthetic-scene case, where most rays of a frame miss the
+  // object): the 4 KB coarse lattice lives in a stream-ordered allocation, released right after the launch
+  uint32_t* coarse = nullptr;
+  if (cull_enabled() && cascades == 1 && exp_step_factor == 0.0f && grid_size == 128 && n_alive >= 2048 && ((uintptr_t)density_bitfield & 7u) == 0 &&
+      cudaMallocAsync((void**)&coarse, 4096, s) == cudaSuccess) {
+    coarse_occupancy_kernel<<<128, 256, 0, s>>>(density_bitfield, coarse);
+    NGP_LAUNCH_CHECK("ngp_raymarching_test/coarse");
+    p.coarse = coarse;
+  } else { cudaGetLastError(); coarse = nullptr; }
+  march_test_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples,
+                                             n_alive, xyzs, dirs, deltas, ts, n_eff_samples);
   NGP_LAUNCH_CHECK("ngp_raymarching_test");
+  if (coarse) cudaFreeAsync(coarse, s);
   return 0;
 }
 
@@ -619,7 +646,14 @@ NGP_API int ngp_render_advance(const float* rays_o, const float* rays_d, float* 
   if (n_next > kScratch) return set_error_msg("ngp_render_advance: n_next must be <= 256");
   cudaStream_t s = (cudaStream_t)stream;
   const MarchWs w = carve(workspace, n_alive_in);
-  const MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  if (prev_rays_a == nullptr && n_next > 0 && cull_enabled() && cascades == 1 && exp_step_factor == 0.0f && grid_size == 128 && n_alive_in >= 2048 &&
+      ((uintptr_t)density_bitfield & 7u) == 0) {       // round 0 sees every ray of the frame: drop the provably empty ones without marching them
+    uint32_t* coarse = coarse_of(w, n_alive_in, kScratch);
+    coarse_occupancy_kernel<<<128, 256, 0, s>>>(density_bitfield, coarse);
+    NGP_LAUNCH_CHECK("ngp_render_advance/coarse");
+    p.coarse = coarse;
+  }
   cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), s);
   if (n_next > 0) cudaMemsetAsync(w.n_samples, 0, n_alive_in * sizeof(int32_t), s);
   const int B = (int)ceil_div(n_alive_in, kMarchBlock);

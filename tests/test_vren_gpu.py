@@ -312,6 +312,16 @@ def test_composite_test_fw(vren, vref, classes):
     assert same.mean() > 0.995
     for k in st:
         close(N(ours[k])[same], orc[k][same])
+    if vref is not None:            # the reference's own kernel on the same tensors (volumerendering.cu:314-423)
+        live = {k: T(v) for k, v in st.items()}
+        alive_v = torch.arange(n, device="cuda")
+        vref.composite_test_fw(sh(ft["sigmas"]), sh(ft["rgbs"], 3), sh(ft["normals_pred"], 3), sh(ft["normals_raw"], 3),
+                               sh(ft["sems"], classes), T(dl), T(ts), T(ht), alive_v, 1e-2, classes, T(neff), live["opacity"],
+                               live["depth"], live["rgb"], live["normal"], live["normal_raw"], live["sem"])
+        same_v = N(alive) == N(alive_v)
+        assert same_v.mean() > 0.995
+        for k in st:
+            close(N(ours[k])[same_v], N(live[k])[same_v])
 
 
 # ------------------------------------------------------------------------------------ goldens (reference CUDA outputs)
@@ -406,7 +416,7 @@ def test_expand_per_ray_matches_repeat_interleave(W):
 
 
 @pytest.mark.parametrize("kind", ["boxes", "shell", "sparse", "empty", "one_cell", "lego"])
-def test_raymarching_train_culling_keeps_counts_bit_exact(vren, kind):
+def test_raymarching_train_culling_keeps_counts_bit_exact(vren, vref, kind):
     """Empty-ray culling of the single-cascade training march (march.cu coarse_occupancy_kernel: rays whose segment stays
     4 cells clear of every occupied cell skip the stepping loop) only engages from 2048 rays on — more than the golden
     cases carry — so: 20 000 rays (incl. axis-parallel / grazing / inside / missing ones) against the C oracle, bit for
@@ -442,3 +452,49 @@ def test_raymarching_train_culling_keeps_counts_bit_exact(vren, kind):
         assert int(rcnt[0]) == 0
     else:
         assert int(rcnt[0]) > 0 and (ra[:, 2] == 0).any() and (ra[:, 2] > 0).any()        # both kinds of rays present
+    if vref is not None:            # ... and against the reference's own kernel, live
+        va, vx, vd, vdl, vts, vc = vref.raymarching_train(T(o), T(d), T(h), T(bf), 1, scale, 0.0, T(noise), 128, 1024)
+        tot = int(N(vc)[0])
+        ca, cx, cts = cases.canonical_order(N(va), N(vx[:tot]), N(vts[:tot]))
+        assert tot == int(rcnt[0]) and (ca == N(rays_a)).all()
+        assert (bits(cts) == bits(N(ts))).all() and (bits(cx) == bits(N(xyzs))).all()
+
+
+@pytest.mark.parametrize("kind", ["boxes", "sparse", "empty", "one_cell", "lego"])
+def test_raymarching_test_culling_is_bit_exact(vren, vref, kind):
+    """The test-time marcher (and round 0 of the wavefront renderer) drops provably empty rays of a single-cascade scene
+    without running the stepping loop (march.cu segment_is_clear; engages from 2048 alive rays).  20 000 rays, two rounds,
+    against the C oracle and the reference's own kernel: N_eff, samples and the in-place hits_t must not change by a bit."""
+    n, scale = 20000, 0.5
+    if kind == "empty":
+        bf = np.zeros(128 ** 3 // 8, np.uint8)
+    elif kind == "one_cell":
+        bf = np.zeros(128 ** 3 // 8, np.uint8)
+        for (x, y, z) in ((127, 127, 127), (0, 64, 3), (60, 61, 67)):
+            code = int(cases.morton_enc(np.array([x]), np.array([y]), np.array([z]))[0])
+            bf[code >> 3] |= np.uint8(1 << (code & 7))
+    elif kind == "lego":
+        from synth_scenes import BoxScene, scene_density_grid, pack_bitfield_torch
+        bf = pack_bitfield_torch(scene_density_grid(BoxScene("lego")), 0.5).numpy()
+    else:
+        bf = cases.bitfield(kind, 1, seed=4)
+    o, d = cases.rays(n, scale, seed=23)
+    if kind == "one_cell":
+        tg = (np.array([[127, 127, 127], [0, 64, 3], [60, 61, 67]], np.float32) + 0.5) / 128 - 0.5
+        k = n // 3
+        d[:k] = (tg[np.arange(k) % 3] + np.random.RandomState(5).normal(size=(k, 3)).astype(np.float32) * 0.004 - o[:k])
+    cnt, ht0, _ = oracle.ray_aabb_intersect(o, d, np.zeros((1, 3), np.float32), np.full((1, 3), scale, np.float32), 1)
+    h = cases.near_clamp(ht0)
+    ht, ht_o, ht_v = T(h.copy()), h.copy(), T(h.copy())
+    alive = torch.arange(n, device="cuda")
+    total = 0
+    for ns in (4, 16):
+        x, dd, dl, ts, neff = vren.raymarching_test(T(o), T(d), ht, alive, T(bf), 1, scale, 0.0, 128, 1024, ns)
+        ox, od, odl, ots, oneff = oracle.raymarching_test(o, d, ht_o, np.arange(n), bf, 1, scale, 0.0, 128, 1024, ns)
+        assert (N(neff) == oneff).all() and (bits(N(ts)) == bits(ots)).all() and (bits(N(dl)) == bits(odl)).all()
+        assert (bits(N(x)) == bits(ox)).all() and (bits(N(dd)) == bits(od)).all() and (bits(N(ht)) == bits(ht_o)).all()
+        if vref is not None:
+            vx, vd, vdl, vts, vneff = vref.raymarching_test(T(o), T(d), ht_v, alive, T(bf), 1, scale, 0.0, 128, 1024, ns)
+            assert (N(vneff) == N(neff)).all() and (bits(N(vts)) == bits(N(ts))).all() and (bits(N(ht_v)) == bits(N(ht))).all()
+        total += int(oneff.sum())
+    assert (total == 0) == (kind == "empty")

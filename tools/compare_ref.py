@@ -32,11 +32,24 @@ def timeit(fn, iters=10):
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
 
+def device_ms(fn, iters=10):
+    """GPU time per call from CUPTI kernel records (torch.profiler): every kernel / memset the call launches, without the
+    host-side launch overhead that dominates the event timing of the 10-microsecond ops."""
+    from torch.profiler import profile, ProfilerActivity
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters): fn()
+        torch.cuda.synchronize()
+    return sum(e.self_device_time_total for e in prof.key_averages()) / iters / 1e3
+
+
 rows = []
 def cmp(name, f_ours, f_ref, iters=10):
     a, b = timeit(f_ours, iters), timeit(f_ref, iters)
-    rows.append({"op": name, "ours_ms": a, "reference_ms": b, "speedup": b / a})
-    print(f"{name:34s} ours {a:9.3f} ms   reference {b:9.3f} ms   x{b / a:6.1f}", flush=True)
+    da, db = device_ms(f_ours, iters), device_ms(f_ref, iters)
+    rows.append({"op": name, "ours_ms": a, "reference_ms": b, "speedup": b / a, "ours_device_ms": da, "reference_device_ms": db, "device_speedup": db / da})
+    print(f"{name:36s} call: ours {a:8.3f} ms  reference {b:8.3f} ms  x{b / a:5.1f}   |   GPU time: ours {da:8.4f} ms  reference {db:8.4f} ms  x{db / da:5.1f}", flush=True)
 
 coords = torch.randint(0, 128, (128 ** 3, 3), dtype=torch.int32, device=dev)
 cmp("morton3D (128^3)", lambda: vren.morton3D(coords), lambda: ref.morton3D(coords))
