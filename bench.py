@@ -218,9 +218,9 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
     import torch.distributed as dist
     from ngp_b200.rendering import render
     out = {}
-    full = getattr(model, "has_normals", True)        # fields with normal / semantic heads render through the reference-style loop
+    full = getattr(model, "has_normals", True)        # fields with normal / semantic heads: ngp_render_advance_full composites those streams too
     extra = extra or {}
-    scheds = (("geometric", "reference") if full else ("wavefront", "geometric", "reference")) if world == 1 else (("geometric",) if full else ("wavefront",))
+    scheds = (("wavefront", "reference") if full else ("wavefront", "geometric", "reference")) if world == 1 else ("wavefront",)
     with torch.no_grad():
         for sched in scheds:
             def frame(i):

@@ -91,6 +91,16 @@ int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, 
                        int cascades, float scale, float exp_step_factor, int grid_size, int max_samples, int n_next,
                        float* opacity, float* depth, float* rgb, int64_t* alive_out, int32_t* counters, void* workspace,
                        void* stream);
+/* the same round with the normal / semantic streams of the reference's test-time compositor (volumerendering.cu:335-373):
+ * normals_pred, normals_raw (S,3) and sems (S,classes) of the previous round's samples are composited into normal, normal_raw
+ * (R,3) and sem (R,classes) next to rgb / depth / opacity.  Pass NULL / 0 for all seven to get ngp_render_advance. */
+int ngp_render_advance_full(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in, int64_t n_alive_in,
+                            const int64_t* prev_rays_a, const float* sigmas, const float* rgbs, const float* deltas,
+                            const float* ts, float T_threshold, const uint8_t* density_bitfield, int cascades, float scale,
+                            float exp_step_factor, int grid_size, int max_samples, int n_next, float* opacity, float* depth,
+                            float* rgb, int64_t* alive_out, int32_t* counters, void* workspace, const float* normals_pred,
+                            const float* normals_raw, const float* sems, int classes, float* normal, float* normal_raw,
+                            float* sem, void* stream);
 int ngp_render_emit(const float* rays_o, const float* rays_d, const float* hits_t, const int64_t* alive_out,
                     int64_t n_slots, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
                     int grid_size, int max_samples, const void* workspace, int64_t capacity, int64_t* rays_a,

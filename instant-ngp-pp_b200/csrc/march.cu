@@ -380,9 +380,12 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t,
     const int64_t* __restrict__ alive, MarchParams p, int n_samples_max, int64_t n_alive,
     float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts,
-    int32_t* __restrict__ n_eff) {
-  const int64_t n = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
-  if (n >= n_alive) return;
+    int32_t* __restrict__ n_eff, const int32_t* __restrict__ live = nullptr, const int* __restrict__ n_live = nullptr) {
+  int64_t n = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  if (live) {                                   // slots that survived march_test_cull_kernel, compacted: full warps of real work
+    if (n >= (int64_t)__ldg(n_live)) return;
+    n = __ldg(live + n);
+  } else if (n >= n_alive) return;
   const int64_t r = alive[n];
   const Ray q = load_ray(rays_o, rays_d, r);
   float t = hits_t[2 * r];
@@ -390,9 +393,6 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
   float x, y, z, dt, t_mark = t;
   int s = 0;
   const int64_t base = n * n_samples_max;
-  // single-cascade culling (march_cull_kernel's test): a ray whose remaining segment is provably empty returns N_eff = 0 and
-  // an untouched hits_t without the ~200 trips of the stepping loop — the same outputs the loop would produce
-  if (p.coarse && t < t2 && segment_is_clear(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, t, t2, p)) t = t2;
   while (t < t2 && s < n_samples_max) {
     if (march_step(q, p, t, x, y, z, dt)) {
       const int64_t o = base + s;
@@ -414,6 +414,69 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
   }
 }
 
+// Pass 0 of the test-time march for single-cascade scenes (most rays of a frame miss the object): a slot whose remaining
+// segment [t, t2] is provably empty (segment_is_clear) gets exactly what the stepping loop would give it — N_eff = 0, a zero
+// row, an untouched hits_t — without the ~200 loop trips; the others are appended to `live`, which the march kernel then
+// walks with full warps (doing the test inside the march kernel leaves the warps as divergent as before: measured, no gain).
+__global__ void __launch_bounds__(kMarchBlock) march_test_cull_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+    const int64_t* __restrict__ alive, MarchParams p, int n_samples_max, int64_t n_alive,
+    float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts,
+    int32_t* __restrict__ n_eff, int32_t* __restrict__ live, int* __restrict__ n_live) {
+  const int64_t n = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  bool keep = false;
+  if (n < n_alive) {
+    const int64_t r = alive[n];
+    const float t = __ldg(hits_t + 2 * r), t2 = __ldg(hits_t + 2 * r + 1);
+    if (t < t2)
+      keep = !segment_is_clear(__ldg(rays_o + 3 * r), __ldg(rays_o + 3 * r + 1), __ldg(rays_o + 3 * r + 2), __ldg(rays_d + 3 * r),
+                               __ldg(rays_d + 3 * r + 1), __ldg(rays_d + 3 * r + 2), t, t2, p);
+    if (!keep) {
+      n_eff[n] = 0;
+      for (int k = 0; k < n_samples_max; k++) {
+        const int64_t o = n * n_samples_max + k;
+        xyzs[3 * o] = 0.f; xyzs[3 * o + 1] = 0.f; xyzs[3 * o + 2] = 0.f;
+        dirs[3 * o] = 0.f; dirs[3 * o + 1] = 0.f; dirs[3 * o + 2] = 0.f;
+        ts[o] = 0.f; deltas[o] = 0.f;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m) {
+    const unsigned lane = threadIdx.x & 31u;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(n_live, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) live[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)n;
+  }
+}
+
+// Round-0 culling of the wavefront renderer: the frame's rays whose whole segment is provably empty never enter the alive list.
+__global__ void __launch_bounds__(kMarchBlock) render_cull_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+    const int64_t* __restrict__ alive_in, int64_t n_alive_in, MarchParams p, int32_t* __restrict__ live, int* __restrict__ n_live) {
+  const int64_t i = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
+  bool keep = false;
+  int64_t r = 0;
+  if (i < n_alive_in) {
+    r = alive_in ? alive_in[i] : i;
+    const float t = __ldg(hits_t + 2 * r), t2 = __ldg(hits_t + 2 * r + 1);
+    if (t < t2)
+      keep = !segment_is_clear(__ldg(rays_o + 3 * r), __ldg(rays_o + 3 * r + 1), __ldg(rays_o + 3 * r + 2), __ldg(rays_d + 3 * r),
+                               __ldg(rays_d + 3 * r + 1), __ldg(rays_d + 3 * r + 2), t, t2, p);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (m) {
+    const unsigned lane = threadIdx.x & 31u;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(n_live, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) live[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Test-time wavefront renderer (replaces the Python loop of models/rendering.py:46-133 + the per-round
 // raymarching_test / composite_test_fw pair).  One launch per round, one thread per currently alive ray:
@@ -424,18 +487,28 @@ __global__ void __launch_bounds__(kMarchBlock) march_test_kernel(
 //      recording (t, dt) in the slot's scratch row; march_emit then packs them.
 // Rays never wait for each other across rounds, the host reads back two counters per round, and the
 // field is only evaluated on samples that exist.
+// the normal / semantic streams of the reference's test-time compositor (volumerendering.cu:335-373): per-sample inputs of the
+// previous round and the per-ray accumulators they are composited into; all NULL / 0 for fields without those heads
+struct RenderAux {
+  const float* normals_pred; const float* normals_raw; const float* sems;      // (S,3), (S,3), (S,C)
+  float* normal; float* normal_raw; float* sem;                                // (R,3), (R,3), (R,C)
+  int classes;
+};
+constexpr int kMaxClasses = 32;
+
 __global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t,
     const int64_t* __restrict__ alive_in, int64_t n_alive_in, const int64_t* __restrict__ prev_rays_a,
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
     const float* __restrict__ ts, float T_thr, MarchParams p, int n_next, float* __restrict__ opacity,
     float* __restrict__ depth, float* __restrict__ rgb, int64_t* __restrict__ alive_out, int32_t* __restrict__ counters,
-    int32_t* __restrict__ n_samples, float2* __restrict__ scratch) {
+    int32_t* __restrict__ n_samples, float2* __restrict__ scratch, const int32_t* __restrict__ live = nullptr,
+    const int* __restrict__ n_live = nullptr, RenderAux aux = RenderAux{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   const int64_t i = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
-  bool alive = i < n_alive_in;
+  bool alive = i < (live ? (int64_t)__ldg(n_live) : n_alive_in);     // live: round 0 after render_cull_kernel (ray ids, compacted)
   int64_t r = 0;
   if (alive) {
-    r = alive_in ? alive_in[i] : i;
+    r = live ? (int64_t)__ldg(live + i) : (alive_in ? alive_in[i] : i);
     if (prev_rays_a) {
       const int64_t start = prev_rays_a[3 * i + 1];
       const int N = (int)prev_rays_a[3 * i + 2];
@@ -443,15 +516,40 @@ __global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
       else {
         float T = 1.0f - opacity[r];
         float aO = 0.f, aD = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
-        for (int s = 0; s < N; s++) {
-          const int64_t o = start + s;
-          const float a = 1.0f - __expf(-__ldg(sigmas + o) * __ldg(deltas + o));
-          const float w = a * T;
-          aR = fmaf(w, __ldg(rgbs + 3 * o), aR); aG = fmaf(w, __ldg(rgbs + 3 * o + 1), aG); aB = fmaf(w, __ldg(rgbs + 3 * o + 2), aB);
-          aD = fmaf(w, __ldg(ts + o), aD);
-          aO += w;
-          T *= 1.0f - a;
-          if (T <= T_thr) { alive = false; break; }
+        if (aux.normal == nullptr) {
+          for (int s = 0; s < N; s++) {
+            const int64_t o = start + s;
+            const float a = 1.0f - __expf(-__ldg(sigmas + o) * __ldg(deltas + o));
+            const float w = a * T;
+            aR = fmaf(w, __ldg(rgbs + 3 * o), aR); aG = fmaf(w, __ldg(rgbs + 3 * o + 1), aG); aB = fmaf(w, __ldg(rgbs + 3 * o + 2), aB);
+            aD = fmaf(w, __ldg(ts + o), aD);
+            aO += w;
+            T *= 1.0f - a;
+            if (T <= T_thr) { alive = false; break; }
+          }
+        } else {                        // + normal_pred, normal_raw and the C semantic channels (volumerendering.cu:352-366)
+          float nP[3] = {0.f, 0.f, 0.f}, nR[3] = {0.f, 0.f, 0.f}, aS[kMaxClasses];
+          const int C = aux.classes;
+          for (int c = 0; c < C; c++) aS[c] = 0.f;
+          for (int s = 0; s < N; s++) {
+            const int64_t o = start + s;
+            const float a = 1.0f - __expf(-__ldg(sigmas + o) * __ldg(deltas + o));
+            const float w = a * T;
+            aR = fmaf(w, __ldg(rgbs + 3 * o), aR); aG = fmaf(w, __ldg(rgbs + 3 * o + 1), aG); aB = fmaf(w, __ldg(rgbs + 3 * o + 2), aB);
+            aD = fmaf(w, __ldg(ts + o), aD);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              nP[k] = fmaf(w, __ldg(aux.normals_pred + 3 * o + k), nP[k]);
+              nR[k] = fmaf(w, __ldg(aux.normals_raw + 3 * o + k), nR[k]);
+            }
+            for (int c = 0; c < C; c++) aS[c] = fmaf(w, __ldg(aux.sems + o * C + c), aS[c]);
+            aO += w;
+            T *= 1.0f - a;
+            if (T <= T_thr) { alive = false; break; }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; k++) { aux.normal[3 * r + k] += nP[k]; aux.normal_raw[3 * r + k] += nR[k]; }
+          for (int c = 0; c < C; c++) aux.sem[r * C + c] += aS[c];
         }
         opacity[r] += aO; depth[r] += aD;
         rgb[3 * r] += aR; rgb[3 * r + 1] += aG; rgb[3 * r + 2] += aB;
@@ -473,7 +571,6 @@ __global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
   const float t2 = hits_t[2 * r + 1];
   float2* row = scratch + j * kScratch;
   int s = 0;
-  if (p.coarse && t < t2 && segment_is_clear(q.ox, q.oy, q.oz, q.dx, q.dy, q.dz, t, t2, p)) t = t2;   // provably empty: N = 0
   while (t < t2 && s < n_next) {
     if (march_step(q, p, t, x, y, z, dt)) {
       row[s] = make_float2(t, dt);
@@ -616,17 +713,28 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
   cudaStream_t s = (cudaStream_t)stream;
   // empty-ray culling (single cascade, no exponential stepping: the synthetic-scene case, where most rays of a frame miss the
   // object): the 4 KB coarse lattice lives in a stream-ordered allocation, released right after the launch
-  uint32_t* coarse = nullptr;
+  char* tmp = nullptr;             // [4 KB coarse lattice | 16 B counter | n_alive x int32 live list], stream-ordered, released after the launches
   if (cull_enabled() && cascades == 1 && exp_step_factor == 0.0f && grid_size == 128 && n_alive >= 2048 && ((uintptr_t)density_bitfield & 7u) == 0 &&
-      cudaMallocAsync((void**)&coarse, 4096, s) == cudaSuccess) {
+      cudaMallocAsync((void**)&tmp, 4096 + 16 + (size_t)n_alive * 4, s) == cudaSuccess) {
+    uint32_t* coarse = reinterpret_cast<uint32_t*>(tmp);
+    int* n_live = reinterpret_cast<int*>(tmp + 4096);
+    int32_t* live = reinterpret_cast<int32_t*>(tmp + 4096 + 16);
     coarse_occupancy_kernel<<<128, 256, 0, s>>>(density_bitfield, coarse);
-    NGP_LAUNCH_CHECK("ngp_raymarching_test/coarse");
+    cudaMemsetAsync(n_live, 0, sizeof(int), s);
     p.coarse = coarse;
-  } else { cudaGetLastError(); coarse = nullptr; }
+    march_test_cull_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts,
+                                                    n_eff_samples, live, n_live);
+    NGP_LAUNCH_CHECK("ngp_raymarching_test/cull");
+    march_test_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts,
+                                               n_eff_samples, live, n_live);
+    NGP_LAUNCH_CHECK("ngp_raymarching_test");
+    cudaFreeAsync(tmp, s);
+    return 0;
+  }
+  cudaGetLastError();
   march_test_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_indices, p, n_samples,
                                              n_alive, xyzs, dirs, deltas, ts, n_eff_samples);
   NGP_LAUNCH_CHECK("ngp_raymarching_test");
-  if (coarse) cudaFreeAsync(coarse, s);
   return 0;
 }
 
@@ -636,32 +744,55 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
 // round 0), appends survivors to alive_out (counters[0] = their number) and marches their next <= n_next
 // samples into the workspace; ngp_render_emit then packs them.  n_next = 0 -> composite only (last round).
 // n_next must be <= 256.  workspace: ngp_render_workspace_bytes(n_alive_in).
-NGP_API int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+NGP_API int ngp_render_advance_full(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
                                int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
                                const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
                                int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
                                int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
-                               int32_t* counters, void* workspace, void* stream) {
+                               int32_t* counters, void* workspace, const float* normals_pred, const float* normals_raw,
+                               const float* sems, int classes, float* normal, float* normal_raw, float* sem, void* stream) {
   if (n_alive_in <= 0) return 0;
+  if (classes < 0 || classes > kMaxClasses) return set_error_msg("ngp_render_advance_full: classes must be in [0, 32]");
+  if ((normal == nullptr) != (normal_raw == nullptr) || (classes > 0 && normal != nullptr && sem == nullptr))
+    return set_error_msg("ngp_render_advance_full: pass normal, normal_raw (and sem when classes > 0) together or not at all");
+  RenderAux aux{normals_pred, normals_raw, sems, normal, normal_raw, sem, normal ? classes : 0};
+  if (prev_rays_a == nullptr || normals_pred == nullptr) aux.normal = nullptr;      // round 0: nothing to composite
   if (n_next > kScratch) return set_error_msg("ngp_render_advance: n_next must be <= 256");
   cudaStream_t s = (cudaStream_t)stream;
   const MarchWs w = carve(workspace, n_alive_in);
   MarchParams p = make_params(density_bitfield, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  const int32_t* live = nullptr;
+  const int* n_live = nullptr;
   if (prev_rays_a == nullptr && n_next > 0 && cull_enabled() && cascades == 1 && exp_step_factor == 0.0f && grid_size == 128 && n_alive_in >= 2048 &&
-      ((uintptr_t)density_bitfield & 7u) == 0) {       // round 0 sees every ray of the frame: drop the provably empty ones without marching them
+      ((uintptr_t)density_bitfield & 7u) == 0) {       // round 0 sees every ray of the frame: the provably empty ones never enter the alive list
     uint32_t* coarse = coarse_of(w, n_alive_in, kScratch);
+    int32_t* lv = reinterpret_cast<int32_t*>(w.t_start);
+    int* nl = reinterpret_cast<int*>(w.total) + 5;
     coarse_occupancy_kernel<<<128, 256, 0, s>>>(density_bitfield, coarse);
-    NGP_LAUNCH_CHECK("ngp_render_advance/coarse");
+    cudaMemsetAsync(nl, 0, sizeof(int), s);
     p.coarse = coarse;
+    render_cull_kernel<<<(int)ceil_div(n_alive_in, kMarchBlock), kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_in, n_alive_in, p, lv, nl);
+    NGP_LAUNCH_CHECK("ngp_render_advance/cull");
+    live = lv; n_live = nl;
   }
   cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), s);
   if (n_next > 0) cudaMemsetAsync(w.n_samples, 0, n_alive_in * sizeof(int32_t), s);
   const int B = (int)ceil_div(n_alive_in, kMarchBlock);
   render_advance_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_in, n_alive_in, prev_rays_a, sigmas, rgbs,
                                                  deltas, ts, T_threshold, p, n_next, opacity, depth, rgb, alive_out, counters,
-                                                 w.n_samples, w.scratch);
+                                                 w.n_samples, w.scratch, live, n_live, aux);
   NGP_LAUNCH_CHECK("ngp_render_advance");
   return 0;
+}
+NGP_API int ngp_render_advance(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                               int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
+                               const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
+                               int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
+                               int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
+                               int32_t* counters, void* workspace, void* stream) {
+  return ngp_render_advance_full(rays_o, rays_d, hits_t, alive_in, n_alive_in, prev_rays_a, sigmas, rgbs, deltas, ts, T_threshold,
+                                 density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples, n_next, opacity, depth, rgb,
+                                 alive_out, counters, workspace, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, stream);
 }
 
 // Packs the samples recorded by ngp_render_advance: rays_a (n_slots,3) = [ray, start, N] per slot of alive_out,

@@ -105,12 +105,13 @@ def volume_render(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pre
 
 
 @torch.no_grad()
-def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs):
-    """Test-time renderer for fields without normal / semantic heads: the reference's march -> evaluate ->
-    composite -> compact loop (rendering.py:46-133) as ONE fused advance kernel per round (composite the
-    previous round, compact the survivors, march the next round), a packing pass, and the field evaluation on
-    exactly the samples that exist.  Rounds take 4, 8, 16, ... samples; the host reads two counters per round.
-    Same samples and the same per-ray compositing recurrence as the reference loop."""
+def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pred=None, normal_raw=None, sem=None, **kwargs):
+    """Test-time renderer: the reference's march -> evaluate -> composite -> compact loop (rendering.py:46-133) as ONE fused
+    advance kernel per round (composite the previous round incl. the normal / semantic streams, compact the survivors, march
+    the next round), a packing pass, and the field evaluation on exactly the samples that exist.  Rounds take 4, 8, 16, ...
+    samples; round 0 drops the frame's provably empty rays before marching (single-cascade scenes); the host reads two
+    counters per round.  Same samples and the same per-ray compositing recurrence as the reference loop.
+    normal_pred / normal_raw (R,3) and sem (R,C): accumulators of fields with normal / semantic heads (all three or none)."""
     from . import _lib
     from ._lib import lib, ptr, check, stream
     _lib.require_device()
@@ -118,21 +119,28 @@ def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwarg
     esf = float(kwargs.get("exp_step_factor", 0.))
     T_thr = float(kwargs.get("T_threshold", 1e-4))
     max_samples = int(kwargs.get("max_samples", MAX_SAMPLES))
+    full = normal_pred is not None
+    classes = int(sem.shape[1]) if (full and sem is not None) else 0
     geo = (model.cascades, float(model.scale), esf, model.grid_size, MAX_SAMPLES)
+    bitfield = ptr(model.density_bitfield)
     alive_in, n_alive = None, N_rays
-    prev = None                        # (rays_a, sigmas, rgbs, deltas, ts) of the previous round
+    prev = None                        # (rays_a, sigmas, rgbs, deltas, ts, normals_pred, normals_raw, sems) of the previous round
     counters = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib.ngp_render_workspace_bytes(N_rays)), dtype=torch.uint8, device=dev)     # sized for round 0, reused
+    alive_bufs = [torch.empty(N_rays, dtype=torch.int64, device=dev) for _ in range(2)]
+    per_ray_emb = isinstance(kwargs.get("embedding_a", None), torch.Tensor) and kwargs["embedding_a"].shape[0] == N_rays
     total = 0
     samples, rnd = 0, 0
+    st = stream()
     while n_alive > 0:
         n_next = min(4 << rnd, 128, max_samples - samples) if samples < max_samples else 0
+        alive_out = alive_bufs[rnd & 1]
         rnd += 1; samples += n_next
-        ws = torch.empty(int(lib.ngp_render_workspace_bytes(n_alive)), dtype=torch.uint8, device=dev)
-        alive_out = torch.empty(n_alive, dtype=torch.int64, device=dev)
-        pr = prev if prev is not None else (None,) * 5
-        check(lib.ngp_render_advance(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(pr[0]), ptr(pr[1]),
-                                     ptr(pr[2]), ptr(pr[3]), ptr(pr[4]), T_thr, ptr(model.density_bitfield), *geo, n_next,
-                                     ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_out), ptr(counters), ptr(ws), stream()),
+        pr = prev if prev is not None else (None,) * 8
+        check(lib.ngp_render_advance_full(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(pr[0]), ptr(pr[1]),
+                                          ptr(pr[2]), ptr(pr[3]), ptr(pr[4]), T_thr, bitfield, *geo, n_next,
+                                          ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_out), ptr(counters), ptr(ws),
+                                          ptr(pr[5]), ptr(pr[6]), ptr(pr[7]), classes, ptr(normal_pred), ptr(normal_raw), ptr(sem), st),
               "render_advance")
         if n_next == 0:
             break
@@ -140,15 +148,22 @@ def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwarg
         rays_a = torch.empty(n_alive, 3, dtype=torch.int64, device=dev)
         xyzs = torch.empty(cap, 3, device=dev); dirs = torch.empty(cap, 3, device=dev)
         deltas = torch.empty(cap, device=dev); ts = torch.empty(cap, device=dev)
-        check(lib.ngp_render_emit(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_out), n_alive, ptr(model.density_bitfield),
+        check(lib.ngp_render_emit(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_out), n_alive, bitfield,
                                   *geo, ptr(ws), cap, ptr(rays_a), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), ptr(counters),
-                                  stream()), "render_emit")
+                                  st), "render_emit")
         n_alive_out, n_pts = (int(v) for v in counters.tolist())          # the round's one host read-back
         total += n_pts
         if n_alive_out == 0 or n_pts == 0:
             break
-        sig, col, _, _, _ = model.forward_test(xyzs[:n_pts], dirs[:n_pts], **kwargs)
-        prev = (rays_a[:n_alive_out].contiguous(), sig.contiguous(), col.contiguous(), deltas, ts)
+        kw = kwargs
+        if per_ray_emb:                 # per-ray tensors follow their rays' samples (rendering.py:217-219 at test time)
+            kw = dict(kwargs)
+            ra = rays_a[:n_alive_out]
+            kw["embedding_a"] = torch.repeat_interleave(kwargs["embedding_a"][ra[:, 0]], ra[:, 2], 0, output_size=n_pts)
+        out = model.forward_test(xyzs[:n_pts], dirs[:n_pts], **kw)
+        sig, col = out[0].contiguous(), out[1].contiguous()
+        extra = (out[2].float().contiguous(), out[3].float().contiguous(), out[4].float().contiguous()) if full else (None, None, None)
+        prev = (rays_a, sig, col, deltas, ts) + extra
         alive_in, n_alive = alive_out, n_alive_out
     return total
 
@@ -159,16 +174,24 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     hits_t = hits_t[:, 0, :].contiguous()
     classes = kwargs.get("num_classes", 7)
     N_rays, device = len(rays_o), rays_o.device
-    if not getattr(model, "has_normals", True) and kwargs.get("renderer", "wavefront") == "wavefront" \
-            and not kwargs.get("use_skybox", False):
+    if kwargs.get("renderer", "wavefront") == "wavefront" and classes <= 32:
         opacity = torch.zeros(N_rays, device=device); depth = torch.zeros(N_rays, device=device)
         rgb = torch.zeros(N_rays, 3, device=device)
-        total = render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
-        z3 = torch.zeros(N_rays, 3, device=device)
-        return {"opacity": opacity, "depth": depth, "rgb": rgb, "normal_pred": z3, "normal_raw": z3,
-                "semantic": torch.zeros(N_rays, 1, dtype=torch.long, device=device),
-                "total_samples": torch.tensor(total, device=device), "points": rays_o + rays_d * depth.unsqueeze(-1),
-                "mask": torch.zeros(N_rays, device=device)}
+        if getattr(model, "has_normals", True):          # fields with normal / semantic heads: all six accumulators
+            normal_pred = torch.zeros(N_rays, 3, device=device); normal_raw = torch.zeros(N_rays, 3, device=device)
+            sem = torch.zeros(N_rays, classes, device=device)
+            total = render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_pred, normal_raw, sem, **kwargs)
+            semantic = torch.argmax(sem, dim=-1, keepdim=True) if classes > 0 else torch.zeros(N_rays, 1, dtype=torch.long, device=device)
+            normal_pred, normal_raw = F.normalize(normal_pred, dim=-1), F.normalize(normal_raw, dim=-1)
+        else:
+            total = render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
+            normal_pred = normal_raw = torch.zeros(N_rays, 3, device=device)
+            semantic = torch.zeros(N_rays, 1, dtype=torch.long, device=device)
+        if kwargs.get("use_skybox", False):              # rendering.py:126-131
+            rgb += model.forward_skybox(rays_d) * (1 - opacity)[:, None]
+        return {"opacity": opacity, "depth": depth, "rgb": rgb, "normal_pred": normal_pred, "normal_raw": normal_raw,
+                "semantic": semantic, "total_samples": torch.tensor(total, device=device),
+                "points": rays_o + rays_d * depth.unsqueeze(-1), "mask": torch.zeros(N_rays, device=device)}
     opacity = torch.zeros(N_rays, device=device)
     depth = torch.zeros(N_rays, device=device)
     rgb = torch.zeros(N_rays, 3, device=device)

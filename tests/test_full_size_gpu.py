@@ -6,8 +6,8 @@ and the 64-wide MLPs) — the small-case tests (tests/test_vren_gpu.py, tests/te
     increasing inside a ray, samples inside the box);
   * compositor fw / bw, distortion fw / bw vs vren_ref on the marcher's own ~9 M samples: rtol 2e-4 + atol 2e-5
     (ex2.approx vs __expf, scan re-association), on >= 99.99 % of the elements;
-  * hash grid fw / table gradient vs the plain-torch restatement on the same 9 M points: forward rtol 1e-5 (+1e-7), table
-    gradient relative L2 < 1e-4 (fp32 atomics), linearity of the scatter in dL/dy;
+  * hash grid fw / table gradient vs the plain-torch restatement on the same 9 M points: forward within the per-level conditioning bound
+    16*eps*scale_l*max|table|, table gradient relative L2 < 1e-3, linearity of the scatter in dL/dy;
   * MLP fw vs the bf16-operand restatement: |err| < 2e-3 of the output scale.
 """
 import numpy as np
@@ -121,13 +121,17 @@ def test_hashgrid_and_mlp_full_size_vs_restatement(batch):
     xn = (xyzs + 0.5)
     with torch.no_grad():
         y_ref = ref(xn)
-    assert torch.allclose(y, y_ref, rtol=1e-5, atol=1e-7)
+    # per-level bound of tests/test_tcnn_gpu.py: pos = x*scale + 0.5 is rounded at magnitude `scale`, so a weight is off by up to
+    # eps*scale_l; |err| <= 16 * eps_fp32 * scale_l * max|table| + 1e-6 (both sides are fp32 here, hence a factor 2)
+    bound = 2 * 16 * 6e-8 * torch.tensor(enc.grid.scales, device="cuda").repeat_interleave(2) * float(table.abs().max()) + 2e-6
+    err = (y - y_ref).abs()
+    assert bool((err <= bound[None, :]).all()), float((err / bound[None, :]).max())
     g = torch.Generator(device="cuda").manual_seed(2)
     dy = torch.randn(S, 32, device="cuda", generator=g)
     dt = tcnn.grid_backward_params(xyzs, dy, enc.grid, aabb=aabb)
     (dt_ref,) = torch.autograd.grad(ref(xn), ref.params, dy)
     rel = lambda a, b: float((a - b).norm() / b.norm())
-    assert rel(dt, dt_ref) < 1e-4
+    assert rel(dt, dt_ref) < 1e-3          # the same weight error eps*scale_l enters every scattered term (tests/test_tcnn_gpu.py)
     # linearity of the scatter (size-independent property): scatter(2 dy) = 2 scatter(dy)
     assert rel(tcnn.grid_backward_params(xyzs, 2 * dy, enc.grid, aabb=aabb), 2 * dt) < 1e-5
     del dy, dt, dt_ref, y_ref

@@ -300,3 +300,39 @@ def test_density_field_single_node_equals_the_three_node_path():
     for a, b in zip(grads[True], grads[False]):
         assert a.shape == b.shape and rel(a, b) < 1e-4, rel(a, b)
     assert rel(grads[3], grads[2]) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["ngp", "street"])
+def test_wavefront_renderer_with_normals_and_semantics_equals_the_loop(kind):
+    """Fields with normal / semantic heads through the fused wavefront rounds (ngp_render_advance_full: rgb, depth, opacity,
+    normal_pred, normal_raw and the C semantic channels composited in the advance kernel) against the reference-style loop
+    over raymarching_test + composite_test_fw on the same field: same samples, same per-ray recurrence."""
+    from ngp_b200.rendering import render
+    from ngp_b200.networks import NGP
+    from ngp_b200 import vren
+    from synth_scenes import BoxScene, scene_density_grid
+    if kind == "ngp":
+        scene, m = _scene_and_model("ngp")
+        kw = dict(exp_step_factor=0.0, num_classes=7)
+    else:
+        scene = BoxScene("street", device="cuda")
+        torch.manual_seed(0)
+        m = NGP(scale=8.0, grid_levels=8, grid_features=8, log2_T_xyz=15, log2_T_rgb=16, embed_a=True, embed_a_len=8, classes=10).cuda()
+        with torch.no_grad():
+            m.xyz_encoder.params.mul_(3000.0); m.rgb_encoder.params.mul_(3000.0)
+        m.density_grid.copy_(scene_density_grid(scene))
+        vren.packbits(m.density_grid, 0.5, m.density_bitfield)
+        kw = dict(exp_step_factor=1.0 / 256, num_classes=10, embedding_a=torch.randn(1, 8, device="cuda") * 0.3)
+    ro, rd = scene.image_rays(scene.poses(4)[1], wh=(96, 64) if kind == "street" else (80, 80))
+    with torch.no_grad():
+        a = render(m, ro, rd, test_time=True, T_threshold=1e-2, sample_schedule="geometric", renderer="loop", **kw)
+        b = render(m, ro, rd, test_time=True, T_threshold=1e-2, **kw)            # wavefront
+    assert int(a["total_samples"]) > 0 and int(b["total_samples"]) > 0
+    for k in ("rgb", "opacity"):
+        assert torch.allclose(a[k], b[k], atol=1e-4), (k, float((a[k] - b[k]).abs().max()))
+    assert torch.allclose(a["depth"], b["depth"], rtol=1e-4, atol=1e-3)
+    hit = a["opacity"] > 0.05
+    assert hit.any()
+    for k in ("normal_pred", "normal_raw"):
+        assert float((a[k][hit] - b[k][hit]).abs().max()) < 1e-3, k
+    assert float((a["semantic"][hit] == b["semantic"][hit]).float().mean()) > 0.999

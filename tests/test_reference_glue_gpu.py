@@ -171,3 +171,42 @@ def test_reference_step_with_appearance_embedding_on_b200_kernels(glue):
     assert torch.allclose(a["opacity"], b["opacity"], rtol=2e-2, atol=2e-3)
     # the embedding reaches rgb_net: its gradient w.r.t. the expanded rows exists on both sides and agrees
     assert _relerr(b_g["rgb_net.params"], a_g["rgb_net.params"]) < 1e-1
+
+
+def test_test_time_render_matches_reference_volume_render(glue):
+    """a14, test-time half: OUR renderer (ngp_b200.rendering.render(test_time=True): wavefront rounds, our field, our kernels)
+    against the reference's own `render(test_time=True)` -> `__render_rays_test` -> `volume_render` loop (models/rendering.py:
+    46-190) over the reference's kernels (vren_ref) and the torch stand-in, same weights (the state dicts are interchangeable),
+    same rays.  The round schedules differ (reference: max(min(N_rays//N_alive, 64), min_samples) per round; ours 4, 8, 16, ...),
+    the composited result must not.  Tolerance: bf16 tensor-core heads against fp32 — rgb |err| < 2e-2, opacity / depth within 2 %."""
+    from baseline import ref_train
+    from ngp_b200.networks import NGP
+    from ngp_b200.rendering import render as our_render
+    from ngp_b200 import vren as our_vren
+    scene, ro, rd, rgb, lab, emb, grid = _inputs("street", 4096)
+    glue.use(vren="ref", tcnn="standin")
+    torch.manual_seed(0)
+    ref_model = ref_train.make_model(glue, "ngp", scale=scene.scale, device="cuda", embed_a=False, classes=7)
+    with torch.no_grad():
+        for n, p in ref_model.named_parameters():
+            if n.endswith("encoder.params"):
+                p.mul_(3000.0)
+    ref_model.density_grid.copy_(grid)
+    glue.vren.packbits(ref_model.density_grid, 0.5, ref_model.density_bitfield)
+    kw = dict(exp_step_factor=scene.exp_step_factor, num_classes=7, test_time=True, T_threshold=1e-2)
+    ref = glue.rendering.render(ref_model, ro, rd, **kw)
+    ours_model = NGP(scale=scene.scale, embed_a=False, classes=7).cuda()
+    sd = {k: v for k, v in ref_model.state_dict().items() if k in ours_model.state_dict()}
+    ours_model.load_state_dict(sd, strict=False)
+    ours_model.density_grid.copy_(grid)
+    our_vren.packbits(ours_model.density_grid, 0.5, ours_model.density_bitfield)
+    assert torch.equal(ours_model.density_bitfield, ref_model.density_bitfield)
+    ours = our_render(ours_model, ro, rd, **kw)
+    assert int(ref["total_samples"]) > 0 and int(ours["total_samples"]) > 0
+    assert float((ours["rgb"] - ref["rgb"]).abs().max()) < 2e-2
+    assert torch.allclose(ours["opacity"], ref["opacity"], rtol=2e-2, atol=2e-3)
+    assert torch.allclose(ours["depth"], ref["depth"], rtol=2e-2, atol=2e-2)
+    hit = ref["opacity"] > 0.2
+    cos = (ours["normal_raw"][hit] * ref["normal_raw"][hit]).sum(-1)
+    assert float(cos.median()) > 0.999
+    assert float((ours["semantic"][hit] == ref["semantic"][hit]).float().mean()) > 0.98
