@@ -101,6 +101,23 @@ int ngp_render_advance_full(const float* rays_o, const float* rays_d, float* hit
                             float* rgb, int64_t* alive_out, int32_t* counters, void* workspace, const float* normals_pred,
                             const float* normals_raw, const float* sems, int classes, float* normal, float* normal_raw,
                             float* sem, void* stream);
+/* One whole round for the ngp_pl-shaped field (density MLP L*F -> width -> 16 with sigma = exp(h0); colour MLP [SH4(d) | h] ->
+ * width (x rgb_hidden) -> 3 sigmoid): advance + emit + hash grid -> bf16 tiles -> both MLPs, every launch reading its live
+ * element count from device memory (n_alive_dev = the previous round's counters, NULL in round 0; counters[1] of this round),
+ * so the host enqueues round after round from BOUNDS (n_alive_bound slots, buffers of n_alive_bound * n_next samples) and
+ * reads the counters back late.  One trip of the loop of models/rendering.py:75-124 without a host round trip.
+ * counters: 2 x int32 of THIS round = [alive slots after it, samples marched in it].  feat_tiles: workspace of
+ * ceil(cap/128) * ngp_feature_tile_bytes bytes; h (cap,16), sigmas (cap), rgbs (cap,3). */
+int ngp_render_round_compact(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                             int64_t n_alive_bound, const int32_t* n_alive_dev, const int64_t* prev_rays_a,
+                             const float* prev_sigmas, const float* prev_rgbs, const float* prev_deltas, const float* prev_ts,
+                             float T_threshold, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                             int grid_size, int max_samples, int n_next, float* opacity, float* depth, float* rgb,
+                             int64_t* alive_out, int32_t* counters, void* workspace, int64_t* rays_a, float* xyzs, float* dirs,
+                             float* deltas, float* ts, const float* aabb, const void* table, int table_dtype, int n_levels,
+                             int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                             const float* sigma_params, const float* rgb_params, int width, int rgb_hidden, void* feat_tiles,
+                             float* h, float* sigmas, float* rgbs, void* stream);
 int ngp_render_emit(const float* rays_o, const float* rays_d, const float* hits_t, const int64_t* alive_out,
                     int64_t n_slots, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
                     int grid_size, int max_samples, const void* workspace, int64_t capacity, int64_t* rays_a,

@@ -24,6 +24,15 @@ constexpr int kSMs = 148;                  // B200
 int set_error(cudaError_t e, const char* where);   // api.cu
 int set_error_msg(const char* msg);
 
+// internal launchers shared between translation units (not exported): the `_dn` forms take the element count from device
+// memory (n is then the bound the launch is sized for) — used by the test-time wavefront round, ngp_render_round_compact
+int mlp_fw_launch(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind, const int64_t* seg_stride,
+                  const float* params, int width, int n_hidden, int n_out, int act_hidden, int act_out, int64_t n,
+                  const int32_t* n_dev, float* out, int64_t out_stride, float* aux_exp_out, void* stream);
+int hashgrid_fw_tiles_launch(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels, int n_features,
+                             int log2_hashmap_size, int base_resolution, float per_level_scale, int64_t n, const int32_t* n_dev,
+                             void* y_tiles, void* stream);
+
 #define NGP_LAUNCH_CHECK(where)                                   \
   do {                                                            \
     cudaError_t _e = cudaGetLastError();                          \

@@ -50,6 +50,7 @@ struct GridMeta {
   // and L2 at 46 % — the misses that matter are the reductions' own sector fetches, L2 hit rate 54 %).
   int chunk_major;
   uint32_t n_sblocks;      // sample blocks of this launch (chunk_major only)
+  const int32_t* n_dev;    // gather only, optional: the sample count lives in device memory (n = min(n, *n_dev)); blocks past it exit
   int chunk0, level_end;   // scatter over a level RANGE [chunk0 * LC, level_end) (ngp_hashgrid_bw_params_tiles_range); default 0, n_levels
 };
 __device__ __forceinline__ void block_coords(const GridMeta& m, int n_chunks, uint32_t& sblock, int& chunk) {
@@ -173,6 +174,11 @@ __global__ void __launch_bounds__(256) hashgrid_fw_kernel(const float* __restric
   const int n_chunks = TILES ? m.k0p / 8 : (m.n_levels + LC - 1) / LC;
   uint32_t sblock; int chunk;
   block_coords(m, n_chunks, sblock, chunk);                                                        // GridMeta::chunk_major
+  if (m.n_dev) {                                    // launch sized for a bound: whole blocks past the live count leave at once
+    const int64_t nd = (int64_t)__ldg(m.n_dev);
+    if (nd < n) n = nd;
+    if ((int64_t)sblock * 128 >= ((n + 127) >> 7 << 7)) return;
+  }
   const int64_t i = (int64_t)sblock * (blockDim.x >> 1) + (threadIdx.x >> 1);                      // 128 samples per CTA
   const uint32_t xh = threadIdx.x & 1u;                                                            // which x-neighbour
   const int l0 = chunk * LC;
@@ -554,7 +560,7 @@ static int fill_meta(GridMeta& m, int n_levels, int F, int log2_T, int base_res,
     off += (uint32_t)sz;
   }
   m.offset[n_levels] = off;
-  m.chunk_major = 0; m.n_sblocks = 1; m.chunk0 = 0; m.level_end = n_levels;
+  m.chunk_major = 0; m.n_sblocks = 1; m.chunk0 = 0; m.level_end = n_levels; m.n_dev = nullptr;
   return 0;
 }
 
@@ -733,13 +739,14 @@ NGP_API int64_t ngp_feature_tile_bytes(int n_levels, int n_features) {
   return (int64_t)feat_tile_bytes((n_levels * n_features + 15) / 16 * 16);
 }
 // y_tiles (ceil(N/128) * ngp_feature_tile_bytes) = bf16(encode(x)) in the MLP's operand-tile layout (see the kernel).
-NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels,
+int ngp::hashgrid_fw_tiles_launch(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels,
                                   int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
-                                  int64_t n, void* y_tiles, void* stream) {
+                                  int64_t n, const int32_t* n_dev, void* y_tiles, void* stream) {
   if (n <= 0) return 0;
   GridMeta m;
   if (fill_meta(m, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, aabb))
     return set_error_msg("ngp_hashgrid_fw_tiles: bad grid config");
+  m.n_dev = n_dev;
   cudaStream_t st = (cudaStream_t)stream;
   NGP_F_DISPATCH(n_features, {
     const unsigned grid = (unsigned)(ceil_div(n, 128) * (m.k0p / 8));      // one lane pair per (sample, 16-byte chunk), padded width
@@ -749,6 +756,12 @@ NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void*
   });
   NGP_LAUNCH_CHECK("ngp_hashgrid_fw_tiles");
   return 0;
+}
+NGP_API int ngp_hashgrid_fw_tiles(const float* x, const float* aabb, const void* table, int table_dtype, int n_levels,
+                                  int n_features, int log2_hashmap_size, int base_resolution, float per_level_scale,
+                                  int64_t n, void* y_tiles, void* stream) {
+  return ngp::hashgrid_fw_tiles_launch(x, aabb, table, table_dtype, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale,
+                                       n, nullptr, y_tiles, stream);
 }
 // dtable += scatter(dL/dy) with dL/dy in gradient tiles (ceil(N/128) * 128 * k0p floats, see the kernel), levels
 // [level_begin, level_end) only.  Launching the scatter as a few level ranges lets the caller hand each finished slice of the

@@ -505,7 +505,9 @@ __global__ void __launch_bounds__(kMarchBlock) render_advance_kernel(
     int32_t* __restrict__ n_samples, float2* __restrict__ scratch, const int32_t* __restrict__ live = nullptr,
     const int* __restrict__ n_live = nullptr, RenderAux aux = RenderAux{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0}) {
   const int64_t i = (int64_t)blockIdx.x * kMarchBlock + threadIdx.x;
-  bool alive = i < (live ? (int64_t)__ldg(n_live) : n_alive_in);     // live: round 0 after render_cull_kernel (ray ids, compacted)
+  // n_live: the live slot count in device memory (n_alive_in is then only the bound the launch is sized for); live: round 0
+  // after render_cull_kernel (ray ids, compacted)
+  bool alive = i < (n_live ? min((int64_t)__ldg(n_live), n_alive_in) : n_alive_in);
   int64_t r = 0;
   if (alive) {
     r = live ? (int64_t)__ldg(live + i) : (alive_in ? alive_in[i] : i);
@@ -744,8 +746,26 @@ NGP_API int ngp_raymarching_test(const float* rays_o, const float* rays_d, float
 // round 0), appends survivors to alive_out (counters[0] = their number) and marches their next <= n_next
 // samples into the workspace; ngp_render_emit then packs them.  n_next = 0 -> composite only (last round).
 // n_next must be <= 256.  workspace: ngp_render_workspace_bytes(n_alive_in).
+static int render_advance_launch(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                               int64_t n_alive_in, const int32_t* n_alive_dev, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
+                               const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
+                               int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
+                               int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
+                               int32_t* counters, void* workspace, const float* normals_pred, const float* normals_raw,
+                               const float* sems, int classes, float* normal, float* normal_raw, float* sem, void* stream);
 NGP_API int ngp_render_advance_full(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
                                int64_t n_alive_in, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
+                               const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
+                               int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
+                               int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
+                               int32_t* counters, void* workspace, const float* normals_pred, const float* normals_raw,
+                               const float* sems, int classes, float* normal, float* normal_raw, float* sem, void* stream) {
+  return render_advance_launch(rays_o, rays_d, hits_t, alive_in, n_alive_in, nullptr, prev_rays_a, sigmas, rgbs, deltas, ts, T_threshold,
+                               density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples, n_next, opacity, depth, rgb,
+                               alive_out, counters, workspace, normals_pred, normals_raw, sems, classes, normal, normal_raw, sem, stream);
+}
+static int render_advance_launch(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                               int64_t n_alive_in, const int32_t* n_alive_dev, const int64_t* prev_rays_a, const float* sigmas, const float* rgbs,
                                const float* deltas, const float* ts, float T_threshold, const uint8_t* density_bitfield,
                                int cascades, float scale, float exp_step_factor, int grid_size, int max_samples,
                                int n_next, float* opacity, float* depth, float* rgb, int64_t* alive_out,
@@ -774,7 +794,7 @@ NGP_API int ngp_render_advance_full(const float* rays_o, const float* rays_d, fl
     render_cull_kernel<<<(int)ceil_div(n_alive_in, kMarchBlock), kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, alive_in, n_alive_in, p, lv, nl);
     NGP_LAUNCH_CHECK("ngp_render_advance/cull");
     live = lv; n_live = nl;
-  }
+  } else if (n_alive_dev) n_live = reinterpret_cast<const int*>(n_alive_dev);
   cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), s);
   if (n_next > 0) cudaMemsetAsync(w.n_samples, 0, n_alive_in * sizeof(int32_t), s);
   const int B = (int)ceil_div(n_alive_in, kMarchBlock);
@@ -817,4 +837,55 @@ NGP_API int ngp_render_emit(const float* rays_o, const float* rays_d, const floa
   NGP_LAUNCH_CHECK("ngp_render_emit/emit");
   cudaMemcpyAsync(counters + 1, w.total, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);   // low word of the int64 total
   return 0;
+}
+
+// ---- one whole round of the test-time renderer for the ngp_pl-shaped field, sized by BOUNDS --------------------------
+// advance (composite the previous round, compact, march) -> emit (pack) -> field (hash grid -> bf16 tiles -> density net ->
+// colour net) in one call, every launch taking its live element count from DEVICE memory: the alive count of the
+// previous round (n_alive_dev, NULL in round 0) and this round's own counters.  The host therefore never has to wait for
+// a count before it can enqueue the next round: it passes an upper bound of the alive slots (n_alive_bound, e.g. the
+// count read back one round late) and buffers sized for n_alive_bound * n_next samples.  counters (2 x int32, one pair
+// per round so that late read-backs stay valid) = [alive slots after this round, samples marched in this round].
+// Replaces one trip of the loop of models/rendering.py:75-124 (raymarching_test, forward_test, composite_test_fw and the
+// alive-index compaction) for fields of the NGPCompact shape (networks.py): density MLP 32 -> width -> 16 with
+// sigma = exp(h0), colour MLP [SH4(d) | h] -> width -> width -> 3, sigmoid.
+NGP_API int ngp_render_round_compact(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
+                                     int64_t n_alive_bound, const int32_t* n_alive_dev, const int64_t* prev_rays_a,
+                                     const float* prev_sigmas, const float* prev_rgbs, const float* prev_deltas, const float* prev_ts,
+                                     float T_threshold, const uint8_t* density_bitfield, int cascades, float scale,
+                                     float exp_step_factor, int grid_size, int max_samples, int n_next, float* opacity,
+                                     float* depth, float* rgb, int64_t* alive_out, int32_t* counters, void* workspace,
+                                     int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts, const float* aabb,
+                                     const void* table, int table_dtype, int n_levels, int n_features, int log2_hashmap_size,
+                                     int base_resolution, float per_level_scale, const float* sigma_params, const float* rgb_params,
+                                     int width, int rgb_hidden, void* feat_tiles, float* h, float* sigmas, float* rgbs, void* stream) {
+  if (n_alive_bound <= 0) return 0;
+  int rc = render_advance_launch(rays_o, rays_d, hits_t, alive_in, n_alive_bound, n_alive_dev, prev_rays_a, prev_sigmas, prev_rgbs,
+                                 prev_deltas, prev_ts, T_threshold, density_bitfield, cascades, scale, exp_step_factor, grid_size,
+                                 max_samples, n_next, opacity, depth, rgb, alive_out, counters, workspace, nullptr, nullptr, nullptr, 0,
+                                 nullptr, nullptr, nullptr, stream);
+  if (rc || n_next <= 0) return rc;
+  const int64_t cap = n_alive_bound * n_next;
+  rc = ngp_render_emit(rays_o, rays_d, hits_t, alive_out, n_alive_bound, density_bitfield, cascades, scale, exp_step_factor, grid_size,
+                       max_samples, workspace, cap, rays_a, xyzs, dirs, deltas, ts, counters, stream);
+  if (rc) return rc;
+  const int32_t* n_pts = counters + 1;
+  const int LF = n_levels * n_features;
+  rc = hashgrid_fw_tiles_launch(xyzs, aabb, table, table_dtype, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale,
+                                cap, n_pts, feat_tiles, stream);
+  if (rc) return rc;
+  {   // density net on the feature tiles; sigma = exp(h0) from the same epilogue
+    const float* sp[1] = {reinterpret_cast<const float*>(feat_tiles)};
+    const int sw[1] = {LF}, sk[1] = {2};
+    const int64_t ss[1] = {0};
+    rc = mlp_fw_launch(1, sp, sw, sk, ss, sigma_params, width, 1, 16, /*ReLU*/ 1, /*None*/ 0, cap, n_pts, h, 16, sigmas, stream);
+    if (rc) return rc;
+  }
+  {   // colour net on [SH4(normalised d) | h]
+    const float* sp[2] = {dirs, h};
+    const int sw[2] = {16, 16}, sk[2] = {1, 0};
+    const int64_t ss[2] = {3, 16};
+    rc = mlp_fw_launch(2, sp, sw, sk, ss, rgb_params, width, rgb_hidden, 3, /*ReLU*/ 1, /*Sigmoid*/ 2, cap, n_pts, rgbs, 3, nullptr, stream);
+  }
+  return rc;
 }

@@ -54,6 +54,7 @@ struct MlpCfg {
   int no, nop;                   // output width / padded to 16
   int act_h, act_o;
   int slots;                     // tiles in flight per CTA
+  const int32_t* n_dev;          // forward only, optional: the row count lives in device memory (n = min(n, *n_dev)) — test-time wavefront rounds
   // shared memory: [0,64) MMA mbarriers, [64,128) landing-zone mbarriers, [128,132) TMEM base, weights (shared by all slots), then one region per slot
   uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]   (absolute)
   uint32_t slot_base, slot_bytes;
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
                                                                       float* __restrict__ out, int64_t out_stride,
                                                                       float* __restrict__ aux_exp) {
   extern __shared__ __align__(128) uint8_t smem[];
+  if (c.n_dev) { const int64_t nd = (int64_t)__ldg(c.n_dev); if (nd < n) n = nd; }
   const Dims d = make_dims<SH>(c);
   const uint32_t tmem = cta_setup(c, d, params, smem);
   Slot S = make_slot(c, d, smem, tmem);
@@ -1078,15 +1080,17 @@ static int match_shape(const MlpCfg& c) {
 // tiles written by ngp_hashgrid_fw_tiles (must be the only segment; its input gradient comes back as gradient tiles).
 // Activations: 0 none, 1 ReLU, 2 sigmoid, 3 exp.  aux_exp_out (optional, N floats) = exp(out[:,0]) taken
 // before the output activation (the ngp_pl density head).
-NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+// n_dev (optional, device): the live row count, n then being an upper bound the launch is sized for (ngp_render_round_compact)
+int ngp::mlp_fw_launch(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
                        const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
-                       int act_hidden, int act_out, int64_t n, float* out, int64_t out_stride, float* aux_exp_out,
+                       int act_hidden, int act_out, int64_t n, const int32_t* n_dev, float* out, int64_t out_stride, float* aux_exp_out,
                        void* stream) {
   if (n <= 0) return 0;
   MlpCfg c;
   const int rc = build_cfg(c, n_seg, seg_ptr, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, false);
   if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_fw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
   pick_slots(c, false, kFwSlots, (int)(sizeof(kFwSlots) / sizeof(int)));
+  c.n_dev = n_dev;
   SegPtrs in; for (int s = 0; s < kMaxSeg; s++) in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
   bool launched = false;
   const int shape = match_shape(c);
@@ -1110,6 +1114,13 @@ NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   }
   NGP_LAUNCH_CHECK("ngp_mlp_fw");
   return 0;
+}
+NGP_API int ngp_mlp_fw(int n_seg, const float* const* seg_ptr, const int* seg_width, const int* seg_kind,
+                       const int64_t* seg_stride, const float* params, int width, int n_hidden, int n_out,
+                       int act_hidden, int act_out, int64_t n, float* out, int64_t out_stride, float* aux_exp_out,
+                       void* stream) {
+  return ngp::mlp_fw_launch(n_seg, seg_ptr, seg_width, seg_kind, seg_stride, params, width, n_hidden, n_out, act_hidden, act_out, n, nullptr,
+                            out, out_stride, aux_exp_out, stream);
 }
 
 // dparams (+=, fp32 atomics; caller zeroes) and optional per-segment input gradients

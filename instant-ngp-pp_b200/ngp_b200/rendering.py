@@ -168,6 +168,83 @@ def render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, normal_
     return total
 
 
+def _round_schedule(max_samples):
+    """samples per round: 4, 8, 16, 32, 64, then 128 until max_samples is reached"""
+    out, tot, k = [], 0, 0
+    while tot < max_samples:
+        n = min(4 << k, 128, max_samples - tot)
+        out.append(n); tot += n; k += 1
+    return out
+
+
+@torch.no_grad()
+def render_wavefront_compact(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs):
+    """render_wavefront for the ngp_pl-shaped field (networks.NGPCompact) with the round loop resident on the device: every
+    round is ONE C-ABI call (ngp_render_round_compact: advance + pack + hash grid + both MLPs) whose launches read their live
+    counts from device memory, so rounds are enqueued back to back from BOUNDS of the alive count and the host never waits
+    for the round it has just enqueued: it blocks once after round 0 (where the frame's empty rays leave: the bound drops 4-5x)
+    and from then on reads each round's counters one round late, while the next round is already running.
+    The reference's loop (models/rendering.py:75-124) synchronises three times per round."""
+    from . import _lib, tcnn
+    from ._lib import lib, ptr, check, stream
+    _lib.require_device()
+    N_rays, dev = len(rays_o), rays_o.device
+    esf = float(kwargs.get("exp_step_factor", 0.))
+    T_thr = float(kwargs.get("T_threshold", 1e-4))
+    sched = _round_schedule(int(kwargs.get("max_samples", MAX_SAMPLES)))
+    geo = (model.cascades, float(model.scale), esf, model.grid_size, MAX_SAMPLES)
+    enc, snet, cnet = model.xyz_encoder, model.sigma_net, model.rgb_net
+    g = enc.grid
+    LF = g.n_levels * g.n_features
+    tile_bytes = int(lib.ngp_feature_tile_bytes(g.n_levels, g.n_features))
+    aabb = tcnn._aabb_arg(model.aabb())
+    table, sp, cp = enc.params.detach(), snet.params.detach(), cnet.params.detach()
+    field = (aabb, ptr(table), 0, *g.args(), ptr(sp), ptr(cp), snet.mlp.width, cnet.mlp.n_hidden)
+    bitfield = ptr(model.density_bitfield)
+    R = len(sched)
+    counters = torch.zeros(R + 1, 2, dtype=torch.int32, device=dev)                 # one pair per round: late read-backs stay valid
+    host = torch.zeros(R + 1, 2, dtype=torch.int32).pin_memory()
+    events = [None] * (R + 1)
+    ws = torch.empty(int(lib.ngp_render_workspace_bytes(N_rays)), dtype=torch.uint8, device=dev)
+    alive_bufs = [torch.empty(N_rays, dtype=torch.int64, device=dev) for _ in range(2)]
+    st = stream()
+    cbase = counters.data_ptr()
+    alive_in, bound, prev = None, N_rays, (None,) * 5
+    known = -1                                   # last round whose counters have reached the host
+    last = -1
+    for k, n_next in enumerate(sched):
+        if bound == 0:
+            break
+        cap = bound * n_next
+        alive_out = alive_bufs[k & 1]
+        rays_a = torch.empty(bound, 3, dtype=torch.int64, device=dev)
+        xyzs = torch.empty(cap, 3, device=dev); dirs = torch.empty(cap, 3, device=dev)
+        deltas = torch.empty(cap, device=dev); ts = torch.empty(cap, device=dev)
+        tiles = torch.empty((cap + 127) // 128 * tile_bytes, dtype=torch.uint8, device=dev)
+        h = torch.empty(cap, 16, device=dev); sig = torch.empty(cap, device=dev); col = torch.empty(cap, 3, device=dev)
+        check(lib.ngp_render_round_compact(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), bound, (cbase + 8 * (k - 1)) if k else None,
+                                           ptr(prev[0]), ptr(prev[1]), ptr(prev[2]), ptr(prev[3]), ptr(prev[4]), T_thr, bitfield, *geo, n_next,
+                                           ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_out), cbase + 8 * k, ptr(ws),
+                                           ptr(rays_a), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), *field, ptr(tiles), ptr(h), ptr(sig), ptr(col), st),
+              "render_round_compact")
+        host[k].copy_(counters[k], non_blocking=True)
+        events[k] = torch.cuda.Event(); events[k].record()
+        prev, alive_in, last = (rays_a, sig, col, deltas, ts), alive_out, k
+        # the bound of the NEXT round: the newest alive count the host may know without stalling the device — round k itself
+        # after round 0 (one blocking wait, the frame's empty rays have just left), round k - 1 afterwards
+        want = k if k == 0 else k - 1
+        if want > known:
+            events[want].synchronize(); known = want
+        bound = min(bound, int(host[known, 0]))
+    # composite the last marched round (n_next = 0: no march, no field)
+    if last >= 0 and bound > 0:
+        check(lib.ngp_render_round_compact(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), bound, cbase + 8 * last,
+                                           ptr(prev[0]), ptr(prev[1]), ptr(prev[2]), ptr(prev[3]), ptr(prev[4]), T_thr, bitfield, *geo, 0,
+                                           ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_bufs[(last + 1) & 1]), cbase + 8 * R, ptr(ws),
+                                           None, None, None, None, None, *field, None, None, None, None, st), "render_round_compact")
+    return int(counters[:R, 1].sum())
+
+
 @torch.no_grad()
 def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     """rendering.py:135-190."""
@@ -184,7 +261,11 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
             semantic = torch.argmax(sem, dim=-1, keepdim=True) if classes > 0 else torch.zeros(N_rays, 1, dtype=torch.long, device=device)
             normal_pred, normal_raw = F.normalize(normal_pred, dim=-1), F.normalize(normal_raw, dim=-1)
         else:
-            total = render_wavefront(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
+            compact = (kwargs.get("device_loop", True) and getattr(model, "fused_density", False) and hasattr(model, "sigma_net")
+                       and model.xyz_encoder.params.dtype == torch.float32 and model.sigma_net.mlp.n_hidden == 1 and model.sigma_net.mlp.n_out == 16
+                       and model.rgb_net.mlp.n_out == 3 and model.rgb_net.mlp.width == model.sigma_net.mlp.width)
+            fn = render_wavefront_compact if compact else render_wavefront
+            total = fn(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
             normal_pred = normal_raw = torch.zeros(N_rays, 3, device=device)
             semantic = torch.zeros(N_rays, 1, dtype=torch.long, device=device)
         if kwargs.get("use_skybox", False):              # rendering.py:126-131
