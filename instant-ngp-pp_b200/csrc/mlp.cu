@@ -199,6 +199,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // ---- slot geometry ---------------------------------------------------------------------------------
 struct Slot {
   uint32_t id, t;           // slot index in the CTA; thread index in the slot (= tile row)
+  bool lead;                // this warp is the slot's first warp: one elected lane of it issues the slot's MMAs / bulk copies
   uint32_t tacc;            // TMEM address of the slot's accumulator (lane 0)
   uint32_t trow;            // same columns, this warp's lane quadrant
   uint32_t twg;             // TMEM address (lane 0) of the CTA-wide wgrad accumulators
@@ -288,9 +289,16 @@ __device__ __forceinline__ uint32_t cta_setup(const MlpCfg& c, const Dims& d, co
 }
 __device__ __forceinline__ Slot make_slot(const MlpCfg& c, const Dims& d, uint8_t* smem, uint32_t tmem) {
   Slot S;
-  S.id = threadIdx.x >> 7; S.t = threadIdx.x & 127u;
+  // Everything but S.t is the same for the 32 lanes of a warp.  Routing the warp index (and the TMEM base read from
+  // shared memory) through a lane-0 shuffle tells the compiler so: slot addresses, TMEM addresses and with them the
+  // MMA descriptors then live in UNIFORM registers, and the single-thread issue blocks lose the per-MMA
+  // R2UR.BROADCAST / ELECT waterfall they had when these were per-lane values (18 -> 4 instructions per UTCHMMA,
+  // profiles/sass/mlp_*: the issue block is serial time of the slot's tile chain).
+  const uint32_t warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  tmem = __shfl_sync(0xffffffffu, tmem, 0);
+  S.id = warp_u >> 2; S.t = threadIdx.x & 127u; S.lead = (warp_u & 3u) == 0u;
   S.tacc = tmem + S.id * c.acc_cols;
-  S.trow = S.tacc + ((((threadIdx.x >> 5) & 3u) * 32u) << 16);
+  S.trow = S.tacc + (((warp_u & 3u) * 32u) << 16);
   S.twg = tmem + c.wg_base;
   S.bar = reinterpret_cast<uint64_t*>(smem) + S.id; S.phase = 0;
   S.full = reinterpret_cast<uint64_t*>(smem) + 8 + S.id; S.fphase = 0;
@@ -416,33 +424,37 @@ __device__ __forceinline__ void zero_pad_cols(const MlpCfg& c, const Dims& d, ui
 }
 
 // ---- MMA issue helpers (single thread) ------------------------------------------------------------
+// Descriptors are built ONCE per operand and stepped along K by adding to the 14-bit start-address field: shared
+// memory ends below 2^18 bytes, so (address >> 4) never carries out of the field and the step is one 32-bit add.
+__device__ __forceinline__ uint64_t desc_step(uint64_t d, uint32_t bytes) {
+  const uint32_t lo = (uint32_t)d + (bytes >> 4);
+  return (d & 0xFFFFFFFF00000000ull) | lo;
+}
 // D[128 x N] = A[128 x K] (K-major tile, 128 rows) * B[N x K]^T (K-major tile with b_rows rows)
 __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t b_rows, int N, int K) {
   const uint32_t id = idesc_bf16(kTile, N, 0, 0);
-  for (int k = 0; k < K; k += 16) {
-    const uint64_t da = smem_desc(a_addr + (k >> 3) * chunk_stride(kTile), chunk_stride(kTile), 128);
-    const uint64_t db = smem_desc(b_addr + (k >> 3) * chunk_stride(b_rows), chunk_stride(b_rows), 128);
-    mma_bf16(tmem_d, da, db, id, k > 0);
-  }
+  const uint64_t da = smem_desc(a_addr, chunk_stride(kTile), 128);
+  const uint64_t db = smem_desc(b_addr, chunk_stride(b_rows), 128);
+  for (int k = 0; k < K; k += 16)
+    mma_bf16(tmem_d, desc_step(da, (k >> 3) * chunk_stride(kTile)), desc_step(db, (k >> 3) * chunk_stride(b_rows)), id, k > 0);
 }
 // D[128 x N] = dZ[128 x K] (K-major) * W[K x N] where W's tile is [w_rows(K) x N cols]: MN-major B.
 __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t w_rows, int N, int K) {
   const uint32_t id = idesc_bf16(kTile, N, 0, 1);
-  for (int k = 0; k < K; k += 16) {
-    const uint64_t da = smem_desc(a_addr + (k >> 3) * chunk_stride(kTile), chunk_stride(kTile), 128);
-    const uint64_t db = smem_desc(w_addr + k * 16, 128, chunk_stride(w_rows));   // LBO = next 8 rows(k), SBO = next 8 cols(n)
-    mma_bf16(tmem_d, da, db, id, k > 0);
-  }
+  const uint64_t da = smem_desc(a_addr, chunk_stride(kTile), 128);
+  const uint64_t db = smem_desc(w_addr, 128, chunk_stride(w_rows));   // LBO = next 8 rows(k), SBO = next 8 cols(n)
+  for (int k = 0; k < K; k += 16)
+    mma_bf16(tmem_d, desc_step(da, (k >> 3) * chunk_stride(kTile)), desc_step(db, k * 16), id, k > 0);
 }
 // D[M x N] += P[128 x M]^T * Q[128 x N]   (both 128-row sample tiles read MN-major, K = samples); the
 // accumulator is zero-initialised once per CTA, every slot accumulates into it.
 __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t p_addr, uint32_t q_addr, int M, int N) {
   const uint32_t id = idesc_bf16(M, N, 1, 1);
-  for (int k = 0; k < kTile; k += 16) {
-    const uint64_t da = smem_desc(p_addr + k * 16, 128, chunk_stride(kTile));
-    const uint64_t db = smem_desc(q_addr + k * 16, 128, chunk_stride(kTile));
-    mma_bf16(tmem_d, da, db, id, true);
-  }
+  const uint64_t da = smem_desc(p_addr, 128, chunk_stride(kTile));
+  const uint64_t db = smem_desc(q_addr, 128, chunk_stride(kTile));
+#pragma unroll
+  for (int k = 0; k < kTile; k += 16)
+    mma_bf16(tmem_d, desc_step(da, k * 16), desc_step(db, k * 16), id, true);
 }
 
 // hidden-layer epilogue: the thread's row of the wp accumulator columns -> act -> bf16 tile row, CH columns
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
   if (!xt) zero_pad_cols(c, d, t, Xs);
   {
     const int64_t first = (int64_t)blockIdx.x * SLOTS + S.id;
-    if (t == 0 && first < n_tiles) {
+    if (S.lead && first < n_tiles && elect_one()) {
       if (xt) issue_tile_prefetch(c, in, first, 0, S);
       else if (tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
     }
@@ -543,8 +555,8 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
     {   // the landing zone is free again: fetch the slot's next tile while this one is computed
       const int64_t nxt = tile + tstride;
       if (nxt < n_tiles) {
-        if (xt) { if (t == 0) issue_tile_prefetch(c, in, nxt, buf ^ 1, S); }
-        else if (tile_is_bulk(c, d, nxt, n)) { if (t == 0) issue_prefetch(c, d, in, nxt, S); }
+        if (xt) { if (S.lead && elect_one()) issue_tile_prefetch(c, in, nxt, buf ^ 1, S); }
+        else if (tile_is_bulk(c, d, nxt, n)) { if (S.lead && elect_one()) issue_prefetch(c, d, in, nxt, S); }
         else if (row + tstride * kTile < n) prefetch_row(c, d, in, row + tstride * kTile);
       }
       __syncwarp();
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
       const bool last = l == d.nh;
       const int N = last ? d.nop : d.wp;
       const int K = l == 0 ? d.k0p : d.wp;
-      if (t == 0) {
+      if (S.lead && elect_one()) {
         fence_after_sync();
         issue_fwd(S.tacc, S.sbase + (l == 0 ? xoff : c.off_h[0]), smem_u32(smem) + c.off_w[l], (uint32_t)N, N, K);
         mma_commit(S.bar);
@@ -639,7 +651,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
   const bool xt = d.seg_kind[0] == kSegTiles;
   {
     const int64_t first = (int64_t)blockIdx.x * SLOTS + S.id;
-    if (t == 0 && first < n_tiles) {
+    if (S.lead && first < n_tiles && elect_one()) {
       if (xt) issue_tile_prefetch(c, in, first, 0, S);
       else if (tile_is_bulk(c, d, first, n)) issue_prefetch(c, d, in, first, S);
     }
@@ -656,7 +668,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     publish(S);
     {
       const int64_t nxt = tile + tstride;
-      if (t == 0 && nxt < n_tiles) {
+      if (S.lead && nxt < n_tiles && elect_one()) {
         if (xt) issue_tile_prefetch(c, in, nxt, buf ^ 1, S);
         else if (tile_is_bulk(c, d, nxt, n)) issue_prefetch(c, d, in, nxt, S);
       }
@@ -700,7 +712,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     }
     // ---- recompute the forward chain; H_{l+1} kept in smem (post-activation, bf16)
     for (int l = 0; l < d.nh; l++) {
-      if (t == 0) {
+      if (S.lead && elect_one()) {
         fence_after_sync();
         issue_fwd(S.tacc, S.sbase + (l == 0 ? xoff : c.off_h[l - 1]), wbase + c.off_w[l], (uint32_t)d.wp, d.wp, l == 0 ? d.k0p : d.wp);
         mma_commit(S.bar);
@@ -743,7 +755,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     }
     // ---- output layer pre-activation -> dZ_out = dL/dy * act_o'(z)
     if (!skip_out) {
-    if (t == 0) {
+    if (S.lead && elect_one()) {
       fence_after_sync();
       issue_fwd(S.tacc, S.sbase + c.off_h[d.nh - 1], wbase + c.off_w[d.nh], (uint32_t)d.nop, d.nop, d.wp);
       mma_commit(S.bar);
@@ -800,7 +812,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
       const uint32_t ain = S.sbase + (l == 0 ? xoff : c.off_h[l - 1]);
       const uint32_t dza = S.sbase + (is_out ? c.off_dz : c.off_h[l]);
       const bool need_dgrad = l > 0 || want_dx;
-      if (t == 0) {
+      if (S.lead && elect_one()) {
         fence_after_sync();
         if (is_out) issue_wgrad(S.twg + c.tm_wg[l], ain, dza, d.wp, d.nop);   // D^T[in x out]
         else issue_wgrad(S.twg + c.tm_wg[l], dza, ain, d.wp, Kin);            // D[out x in]
