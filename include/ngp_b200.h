@@ -56,6 +56,23 @@ int ngp_packbits(const void* density_grid, int dtype, int64_t n_bytes, float den
 int ngp_packbits_dthr(const float* density_grid, int64_t n_bytes, const float* density_threshold_dev,
                       uint8_t* density_bitfield, void* stream);
 
+/* ------------------------------------------------------------------ f2: occupancy update as one kernel chain
+ * NGP.sample_uniform_and_occupied_cells + NGP.update_density_grid   models/networks.py:294-333,379-408
+ * (per cascade: randint, morton3D, nonzero, randint, fancy index, morton3D_invert, cat, rand_like, index_put, then
+ * where / maximum over the grid, a masked mean with .item(), packbits).  Split at the one step that belongs to the
+ * model — density(xyzs):
+ *   sample : mask(grid > thr) -> popcount scan -> one thread per draw: M uniform cells + M occupied cells per cascade
+ *            (warmup: every cell), jittered world positions          -> indices (Cc*n) i32 (-1 = void), xyzs (Cc*n,3)
+ *   update : decay -> atomicMax scatter of the densities -> mean of the positive cells -> thr = min(mean, threshold)
+ *            -> packbits, all on the stream; grid and bitfield are updated in place.
+ * workspace: ngp_occupancy_workspace_bytes(cascades) bytes, 16-byte aligned, zero-filled once by the caller. */
+int64_t ngp_occupancy_workspace_bytes(int cascades);
+int ngp_occupancy_sample(const float* density_grid, int cascades, float scale, float density_threshold, int64_t M, int warmup,
+                         uint64_t seed, void* workspace, int32_t* indices, float* xyzs, void* stream);
+int ngp_occupancy_update(float* density_grid, int cascades, const int32_t* indices, const float* density, int64_t n_per_cascade,
+                         float decay, const float* count_grid, float density_threshold, void* workspace,
+                         uint8_t* density_bitfield, void* stream);
+
 /* ------------------------------------------------------------------ a2: training ray marcher
  * vren.raymarching_train  binding.cpp:60-81 -> raymarching.cu:283-332, split so the caller can
  * size the outputs exactly (or not sync at all):
@@ -241,6 +258,10 @@ int ngp_grad_sumsq(const float* g, int64_t n, float* accum, void* stream);
 int ngp_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream);
 int ngp_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream);
+/* lazy variant: entries with an exactly-zero gradient keep p / exp_avg / exp_avg_sq (tiny-cuda-nn's rule for encoding
+ * parameters; 4 B instead of 28 B for every hash-table entry the batch did not touch).  Opt-in: not torch.optim.Adam's rule. */
+int ngp_adam_step_lazy(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream);
 
 /* ------------------------------------------------------------------ a14: per-ray tensors repeated per sample
  * torch.repeat_interleave(v[rays_a[:, 0]], rays_a[:, 2], 0)  models/rendering.py:217-219 (appearance embeddings) and its

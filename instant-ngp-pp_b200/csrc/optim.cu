@@ -41,6 +41,10 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
   p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);     // torch.optim.Adam: denom = sqrt(v)/sqrt(bc2) + eps
 }
 
+// LAZY: entries whose gradient is exactly zero are left alone (p, m, v untouched) — tiny-cuda-nn's Adam for encoding
+// parameters (hash-table entries no sample of the batch touched keep their moments instead of coasting on them).  The
+// skipped entries cost 4 B (the gradient read) instead of 28 B.  Not torch.optim.Adam's rule, hence opt-in.
+template <bool LAZY>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float b1, float b2, float eps,
                                                    float step_size, float inv_sqrt_bc2, const float* __restrict__ gscale) {
@@ -49,16 +53,19 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
   const int64_t n4 = aligned ? (n >> 2) : 0;                             // parameter views at odd offsets take the scalar loop
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
     const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
-    adam1(P.x, G.x * gs, M.x, V.x, b1, b2, eps, step_size, inv_sqrt_bc2);
-    adam1(P.y, G.y * gs, M.y, V.y, b1, b2, eps, step_size, inv_sqrt_bc2);
-    adam1(P.z, G.z * gs, M.z, V.z, b1, b2, eps, step_size, inv_sqrt_bc2);
-    adam1(P.w, G.w * gs, M.w, V.w, b1, b2, eps, step_size, inv_sqrt_bc2);
+    if (LAZY && G.x == 0.f && G.y == 0.f && G.z == 0.f && G.w == 0.f) continue;
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    if (!LAZY || G.x != 0.f) adam1(P.x, G.x * gs, M.x, V.x, b1, b2, eps, step_size, inv_sqrt_bc2);
+    if (!LAZY || G.y != 0.f) adam1(P.y, G.y * gs, M.y, V.y, b1, b2, eps, step_size, inv_sqrt_bc2);
+    if (!LAZY || G.z != 0.f) adam1(P.z, G.z * gs, M.z, V.z, b1, b2, eps, step_size, inv_sqrt_bc2);
+    if (!LAZY || G.w != 0.f) adam1(P.w, G.w * gs, M.w, V.w, b1, b2, eps, step_size, inv_sqrt_bc2);
     reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
   }
-  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (LAZY && g[i] == 0.f) continue;
     adam1(p[i], g[i] * gs, m[i], v[i], b1, b2, eps, step_size, inv_sqrt_bc2);
+  }
 }
 
 static inline int flat_grid(int64_t n) {
@@ -92,8 +99,20 @@ NGP_API int ngp_adam_step(float* params, const float* grads, float* exp_avg, flo
                           float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream) {
   if (n <= 0) return 0;
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
-  adam_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
-                                                             (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
+  adam_kernel<false><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                                    (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
   NGP_LAUNCH_CHECK("ngp_adam_step");
+  return 0;
+}
+
+// Same update restricted to the entries with a non-zero gradient (tiny-cuda-nn's rule for encoding parameters): the others keep
+// p, exp_avg and exp_avg_sq.  `step` is the tensor-wide step count (bias correction is not tracked per entry, as in tcnn).
+NGP_API int ngp_adam_step_lazy(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, int step, const float* grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  adam_kernel<true><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                                   (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
+  NGP_LAUNCH_CHECK("ngp_adam_step_lazy");
   return 0;
 }

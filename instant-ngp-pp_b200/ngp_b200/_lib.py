@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_ROOT, "libngp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_ROOT), "include", "ngp_b200.h")
 
 _CT = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
-       "uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32}
+       "uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "uint64_t": ctypes.c_uint64}
 
 
 def parse_header(path=HEADER_PATH):
@@ -64,7 +64,8 @@ def last_error() -> str:
 
 # count + block sums + block scan (+ coarse lattice + cull pre-pass when the single-cascade culling applies, march.cu);
 # every other entry point = 1 launch
-_KERNELS_PER_CALL = {"raymarching_train/count": 3, "raymarching_train/count+cull": 5}
+_KERNELS_PER_CALL = {"raymarching_train/count": 3, "raymarching_train/count+cull": 5,
+                     "occupancy_sample": 3, "occupancy_sample/warmup": 1, "occupancy_update": 4}
 _launches = 0
 
 

@@ -118,9 +118,47 @@ class _OccupancyMixin:
                 valid = (count > 0) & (~too_near)
                 self.density_grid[c, indices[i:i + chunk]] = torch.where(valid, 0., -1.)
 
+    fused_update = True       # occupancy update as one kernel chain (csrc/occupancy.cu: ngp_occupancy_sample / _update)
+
+    def _occ_workspace(self):
+        from ._lib import lib
+        ws = getattr(self, "_occ_ws", None)
+        if ws is None or ws.device != self.density_grid.device:
+            ws = self._occ_ws = torch.zeros(int(lib.ngp_occupancy_workspace_bytes(self.cascades)), dtype=torch.uint8,
+                                            device=self.density_grid.device)
+        return ws
+
     @torch.no_grad()
-    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+    def sample_cells_fused(self, density_threshold, warmup=False, seed=None):
+        """-> (indices (Cc*n) i32 with -1 = void draw, xyzs (Cc*n, 3), n): the cells of sample_uniform_and_occupied_cells /
+        get_all_cells for ALL cascades with their jittered positions, from one 3-kernel chain (no nonzero, no host sync).
+        The random stream is counter based: `seed` (default: one draw from torch's CPU generator, so torch.manual_seed
+        fixes it) and the draw's index determine every sample."""
+        from ._lib import lib, ptr, check, stream
+        G, Cc, dev = self.grid_size, self.cascades, self.density_grid.device
+        M = G ** 3 // 4
+        n = G ** 3 if warmup else 2 * M
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        indices = torch.empty(Cc * n, dtype=torch.int32, device=dev)
+        xyzs = torch.empty(Cc * n, 3, device=dev)
+        check(lib.ngp_occupancy_sample(ptr(self.density_grid), Cc, float(self.scale), float(density_threshold), M, int(bool(warmup)),
+                                       seed & 0xFFFFFFFFFFFFFFFF, ptr(self._occ_workspace()), ptr(indices), ptr(xyzs), stream()),
+              "occupancy_sample/warmup" if warmup else "occupancy_sample")
+        return indices, xyzs, n
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False, seed=None):
         """EMA-max update of the occupancy grid + repack of the bitfield (networks.py:379-408)."""
+        if self.fused_update and self.density_grid.is_cuda and self.density_grid.dtype == torch.float32:
+            from ._lib import lib, ptr, check, stream
+            indices, xyzs, n = self.sample_cells_fused(density_threshold, warmup, seed)
+            sig = self.density(xyzs).float().contiguous()
+            cg = self.count_grid.contiguous() if erode else None
+            check(lib.ngp_occupancy_update(ptr(self.density_grid), self.cascades, ptr(indices), ptr(sig), n, float(decay), ptr(cg),
+                                           float(density_threshold), ptr(self._occ_workspace()), ptr(self.density_bitfield), stream()),
+                  "occupancy_update")
+            return
         G = self.grid_size
         tmp = torch.zeros_like(self.density_grid)
         cells = self.get_all_cells() if warmup else self.sample_uniform_and_occupied_cells(G ** 3 // 4, density_threshold)

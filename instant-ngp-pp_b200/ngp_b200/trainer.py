@@ -20,7 +20,7 @@ from .rendering import render
 class Trainer:
     def __init__(self, model, lr=1e-2, eps=1e-15, update_interval=16, warmup_steps=256, density_threshold=0.01 * 1024 / 3 ** 0.5,
                  lambda_distortion=3e-4, lambda_opa=2e-4, render_kwargs=None, world_size=1, max_grad_norm=None,
-                 extra_params=(), exchange="after"):
+                 extra_params=(), exchange="after", lazy_adam=False):
         self.model = model
         self.loss_fn = NeRFLoss(lambda_opa=lambda_opa, lambda_distortion=lambda_distortion)
         # extra_params: parameters outside the field that the step also trains (the appearance embedding, train.py:117-119)
@@ -28,7 +28,14 @@ class Trainer:
         params = [p for p in model.parameters() if p.numel() > 0] + self.extra_params
         on_gpu = len(params) > 0 and params[0].is_cuda
         # train.py:244-251,435: Adam + global-norm clip, fused (device-resident clip coefficient, 1/world averaging)
-        self.opt = (FusedAdam(params, lr=lr, eps=eps, max_grad_norm=max_grad_norm, grad_scale=1.0 / world_size) if on_gpu
+        # Gradient exchange mode, see below ("sharded" lives in the optimiser: reduce-scatter -> Adam on 1/world -> all-gather)
+        import os
+        self._exchange = os.environ.get("NGP_DP_EXCHANGE", exchange)
+        shard = None
+        if world_size > 1 and on_gpu and self._exchange == "sharded":
+            shard = (dist.get_rank(), world_size)
+        self.opt = (FusedAdam(params, lr=lr, eps=eps, max_grad_norm=max_grad_norm, grad_scale=1.0 / world_size, shard=shard,
+                              lazy=lazy_adam) if on_gpu
                     else torch.optim.Adam(params, lr=lr, eps=eps))
         self.fused = on_gpu
         self.update_interval, self.warmup_steps = update_interval, warmup_steps
@@ -43,9 +50,10 @@ class Trainer:
         # "overlap": table slices all-reduced under the remaining scatter launches (tcnn.GradSink) — measured SLOWER on B200 +
         # NVSwitch for the 44 MB table (profiles/r02b_dp_exchange_probe.txt: 7.22 vs 7.09 ms/step at N=2; the all-reduce is only
         # 0.04 ms exposed and competes with the L2-bound scatter when overlapped), kept for tables where the exchange is long.
+        # "sharded": the tensors FusedAdam.is_sharded names (the hash tables) are not all-reduced at all — the optimiser
+        # reduce-scatters their gradients, updates its 1/world slice (optimiser state and traffic / world) and all-gathers the
+        # parameters in place; everything else goes through the all-reduce below.
         # "none": timing probe only.  NGP_DP_EXCHANGE overrides.
-        import os
-        self._exchange = os.environ.get("NGP_DP_EXCHANGE", exchange)
         if world_size > 1 and on_gpu and self._exchange == "overlap":
             self._install_grad_sinks()
 
@@ -68,8 +76,9 @@ class Trainer:
             return
         # largest tensors first: the hash tables are > 99 % of the bytes
         sunk = {id(p) for p, _ in self._sinks}           # already in flight, slice by slice, since the backward pass
-        ps = sorted((p for p in list(self.model.parameters()) + self.extra_params if p.grad is not None and id(p) not in sunk),
-                    key=lambda p: -p.numel())
+        in_opt = getattr(self.opt, "is_sharded", lambda p: False)      # exchanged by the sharded optimiser itself
+        ps = sorted((p for p in list(self.model.parameters()) + self.extra_params
+                     if p.grad is not None and id(p) not in sunk and not in_opt(p)), key=lambda p: -p.numel())
         works = self._works + [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in ps]
         self._works = []
         for w in works:
