@@ -252,6 +252,20 @@ int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_width, con
                const float* saved_out /* optional: forward output, skips the output-layer recompute */,
                int64_t saved_out_stride, void* stream);
 
+/* ------------------------------------------------------------------ a12: the density net on tcgen05 (csrc/density_net.cu)
+ * xyz_net = Sequential(Linear(128,128), Softplus, Linear(128,1)) + sigma_act = Softplus   models/networks.py:54-59,172-181
+ * and the autograd normals through it (torch.autograd.grad(create_graph=True) + loss.backward())   networks.py:186-196.
+ *   fw : e (N,128) -> sigma (N), s2 (N) = sigmoid(pre-activation of sigma), g_e (N,128) | NULL = d sigma / d e
+ *   bw : upstream dsigma (N) | NULL, d_ge (N,128) | NULL (+ the forward's g_e) -> de (N,128) | NULL,
+ *        += dW1 (128,128), db1 (128), dw2 (128), db2 (1)
+ * W1 row-major (out,in) = xyz_net[0].weight, b1 = xyz_net[0].bias, w2 = xyz_net[2].weight (128), b2 = xyz_net[2].bias.
+ * bf16 tensor-core operands, fp32 accumulation.  n_in and width must be 128. */
+int ngp_density_net_fw(const float* e, const float* W1, const float* b1, const float* w2, const float* b2, int64_t n, int n_in,
+                       int width, float* sigma, float* s2, float* g_e, void* stream);
+int ngp_density_net_bw(const float* e, const float* d_ge, const float* g_e, const float* dsigma, const float* s2, const float* W1,
+                       const float* b1, const float* w2, int64_t n, int n_in, int width, float* de, float* dW1, float* db1,
+                       float* dw2, float* db2, void* stream);
+
 /* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
  * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */
 int ngp_grad_sumsq(const float* g, int64_t n, float* accum, void* stream);

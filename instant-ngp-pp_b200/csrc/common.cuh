@@ -97,6 +97,25 @@ __device__ __forceinline__ int mip_from_dt(float dt, int grid_size, int cascades
   return min(cascades - 1, max(0, frexp_exponent(__fmul_rn(dt, (float)grid_size))));
 }
 
+// ---------------------------------------------------------------- density-net activations (density_head.cu, density_net.cu)
+// softplus and sigmoid of the same z from ONE exponential: e = exp(-|z|) in (0, 1],
+//     sigmoid(z) = z >= 0 ? 1/(1+e) : e/(1+e) ;  softplus(z) = max(z, 0) + log(1 + e)
+// (no overflow for any z; above torch's linear threshold 20 the log term is < 2.1e-9 and vanishes in fp32 exactly as
+// torch's switch to the identity does).  MUFU.EX2 + MUFU.RCP + MUFU.LG2: with expf / log1pf / an IEEE division per
+// element the kernels were ALU bound at 42 % (fw) / 56 % (bw) of the HBM rate (profiles/r01e_step_profile_playground_after.txt).
+struct SpSg { float sp, sg; };
+__device__ __forceinline__ SpSg softplus_sigmoid(float z) {
+  const float e = __expf(-fabsf(z));
+  float r;                                     // 1 + e is in (1, 2]: MUFU.RCP alone (1 ulp); __frcp_rn's IEEE fix-up was 45 % of the
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));      // density-net kernels' instructions (profiles/r02d_ncu_density_net_*)
+  SpSg o;
+  o.sg = z >= 0.f ? r : e * r;
+  o.sp = fmaxf(z, 0.f) + __logf(1.f + e);
+  return o;
+}
+__device__ __forceinline__ float softplus1(float z) { return softplus_sigmoid(z).sp; }
+__device__ __forceinline__ float sigmoid1(float z) { return softplus_sigmoid(z).sg; }
+
 // ---------------------------------------------------------------- warp utilities
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

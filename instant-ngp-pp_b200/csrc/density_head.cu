@@ -21,23 +21,6 @@
 
 namespace ngp {
 
-// softplus and sigmoid of the same z from ONE exponential: e = exp(-|z|) in (0, 1],
-//     sigmoid(z) = z >= 0 ? 1/(1+e) : e/(1+e) ;  softplus(z) = max(z, 0) + log(1 + e)
-// (no overflow for any z; above torch's linear threshold 20 the log term is < 2.1e-9 and vanishes in fp32 exactly as
-// torch's switch to the identity does).  MUFU.EX2 + MUFU.RCP + MUFU.LG2: with expf / log1pf / an IEEE division per
-// element the kernels were ALU bound at 42 % (fw) / 56 % (bw) of the HBM rate (profiles/r01e_step_profile_playground_after.txt).
-struct SpSg { float sp, sg; };
-__device__ __forceinline__ SpSg softplus_sigmoid(float z) {
-  const float e = __expf(-fabsf(z));
-  const float r = __frcp_rn(1.f + e);
-  SpSg o;
-  o.sg = z >= 0.f ? r : e * r;
-  o.sp = fmaxf(z, 0.f) + __logf(1.f + e);
-  return o;
-}
-__device__ __forceinline__ float softplus1(float z) { return softplus_sigmoid(z).sp; }
-__device__ __forceinline__ float sigmoid1(float z) { return softplus_sigmoid(z).sg; }
-
 constexpr int kHeadMaxK = 4;   // W <= 512
 
 template <int K>

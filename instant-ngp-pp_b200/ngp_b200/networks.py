@@ -195,6 +195,31 @@ class _tf32_matmul:
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
+def _dn_fw(e, W1, b1, W2, b2, want_ge=True):
+    """The density net on tcgen05 (csrc/density_net.cu): e (N,128) -> sigma (N), s2 (N), g_e (N,128) | None."""
+    from ._lib import lib, ptr, check, stream
+    n = e.shape[0]
+    sigma = torch.empty(n, device=e.device); s2 = torch.empty(n, device=e.device)
+    g_e = torch.empty(n, W1.shape[1], device=e.device) if want_ge else None
+    check(lib.ngp_density_net_fw(ptr(e), ptr(W1.detach().contiguous()), ptr(b1.detach().contiguous()), ptr(W2.detach().reshape(-1).contiguous()),
+                                 ptr(b2.detach().contiguous()), n, e.shape[1], W1.shape[0], ptr(sigma), ptr(s2), ptr(g_e), stream()),
+          "density_net_fw")
+    return sigma, s2, g_e
+
+
+def _dn_bw(e, d_ge, g_e, dsigma, s2, W1, b1, W2, need_de=True):
+    """-> de (N,128) | None, dW1 (128,128), db1 (128), dW2 (1,128), db2 (1) for upstream (dsigma | None, d_ge | None)."""
+    from ._lib import lib, ptr, check, stream
+    n, W = e.shape[0], W1.shape[0]
+    de = torch.empty_like(e) if need_de else None
+    acc = torch.zeros(W * W + 2 * W + 4, device=e.device)         # one memset for all four parameter gradients
+    dW1, db1, dw2, db2 = acc[:W * W].view(W, W), acc[W * W:W * W + W], acc[W * W + W:W * W + 2 * W], acc[W * W + 2 * W:W * W + 2 * W + 1]
+    check(lib.ngp_density_net_bw(ptr(e), ptr(d_ge), ptr(g_e) if d_ge is not None else None, ptr(dsigma), ptr(s2), ptr(W1.detach().contiguous()),
+                                 ptr(b1.detach().contiguous()), ptr(W2.detach().reshape(-1).contiguous()), n, e.shape[1], W,
+                                 ptr(de), ptr(dW1), ptr(db1), ptr(dw2), ptr(db2), stream()), "density_net_bw")
+    return de, dW1, db1, dw2[None], db2
+
+
 class _DensityNormalsFn(torch.autograd.Function):
     """(sigma (N), g_e (N,D) = d sigma / d e) of the reference's torch density net
         sigma = Softplus(Linear(W,1)(Softplus(Linear(D,W)(e))))                       (networks.py:54-59,172-181)
@@ -211,6 +236,11 @@ class _DensityNormalsFn(torch.autograd.Function):
         e = e.contiguous()
         n, W = e.shape[0], W1.shape[0]
         ctx.tf32 = tf32
+        ctx.set_materialize_grads(False)
+        if tf32 == "tc05":                          # one tcgen05 kernel per direction (csrc/density_net.cu)
+            sigma, s2, g_e = _dn_fw(e, W1, b1, W2, b2)
+            ctx.save_for_backward(e, W1, b1, W2, s2, g_e)
+            return sigma, g_e
         with _tf32_matmul(tf32):
             z1 = torch.addmm(b1, e, W1.t())
         sigma = torch.empty(n, device=e.device); s2 = torch.empty(n, device=e.device)
@@ -228,6 +258,11 @@ class _DensityNormalsFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dsigma, dg):
         from ._lib import lib, ptr, check, stream
+        if ctx.tf32 == "tc05":
+            e, W1, b1, W2, s2, g_e = ctx.saved_tensors
+            de, dW1, db1, dW2, db2 = _dn_bw(e, dg.contiguous() if dg is not None else None, g_e,
+                                            dsigma.contiguous() if dsigma is not None else None, s2, W1, b1, W2, ctx.needs_input_grad[0])
+            return de, dW1, db1, dW2, db2, None
         e, W1, w2, z1, s2, t = ctx.saved_tensors
         n, W = z1.shape
         with _tf32_matmul(ctx.tf32):
@@ -261,6 +296,13 @@ class _DensityFieldNormalsFn(torch.autograd.Function):
         n, W = x.shape[0], W1.shape[0]
         tb = table.detach()
         enc = tcnn.grid_forward(x, tb, grid, aabb)
+        if tf32 == "tc05":
+            sigma, s2, g_e = _dn_fw(enc, W1, b1, W2, b2)
+            g_x = tcnn.grid_backward_input(x, g_e, tb, grid, aabb)
+            ctx.grid, ctx.aabb, ctx.tf32 = grid, aabb, tf32
+            ctx.set_materialize_grads(False)
+            ctx.save_for_backward(x, table, W1, b1, W2, enc, s2, g_e)      # 1 KB / sample (the torch-GEMM path keeps 2.5 KB)
+            return sigma, g_x
         with _tf32_matmul(tf32):
             z1 = torch.addmm(b1, enc, W1.t())
         sigma = torch.empty(n, device=x.device); s2 = torch.empty(n, device=x.device)
@@ -280,9 +322,13 @@ class _DensityFieldNormalsFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dsigma, dgx):
         from ._lib import lib, ptr, check, stream
-        x, table, W1, w2, enc, z1, s2, t, g_e = ctx.saved_tensors
+        tc = ctx.tf32 == "tc05"
+        if tc:
+            x, table, W1, b1, W2, enc, s2, g_e = ctx.saved_tensors
+        else:
+            x, table, W1, w2, enc, z1, s2, t, g_e = ctx.saved_tensors
         g, aabb = ctx.grid, ctx.aabb
-        n, W = z1.shape
+        n, W = enc.shape[0], W1.shape[0]
         tdt = 0 if table.dtype == torch.float32 else 1
         d_ge = v = None
         if dgx is not None:
@@ -290,6 +336,15 @@ class _DensityFieldNormalsFn(torch.autograd.Function):
             d_ge = torch.empty_like(enc)            # d(dgx . g_x)/d(g_e): the gather with the input-gradient coefficients
             check(lib.ngp_hashgrid_bwbw_input(ptr(x), tcnn._aabb_arg(aabb), ptr(dgx), None, ptr(table.detach()), tdt, *g.args(), n,
                                               None, ptr(d_ge), stream()), "hashgrid_bwbw_input")
+        if tc:
+            de, dW1, db1, dW2, db2 = _dn_bw(enc, d_ge, g_e, dsigma.contiguous() if dsigma is not None else None, s2, W1, b1, W2, True)
+            dtable = None
+            if ctx.needs_input_grad[1]:
+                dtable = torch.zeros(g.n_params, dtype=torch.float32, device=x.device)
+                check(lib.ngp_hashgrid_bw_params_dual(ptr(x), tcnn._aabb_arg(aabb), ptr(de), ptr(dgx), ptr(g_e) if dgx is not None else None,
+                                                      *g.args(), n, ptr(dtable), stream()), "hashgrid_bw_params_dual")
+            return None, dtable, dW1, db1, dW2, db2, None, None, None
+        if d_ge is not None:
             with _tf32_matmul(ctx.tf32):
                 v = d_ge @ W1.t()
         dz1 = torch.empty_like(z1); dz2 = torch.empty(n, device=z1.device)
@@ -360,7 +415,8 @@ class _TwoHeadsFn(torch.autograd.Function):
 
 class NGP(nn.Module, _OccupancyMixin):
     def __init__(self, scale, rgb_act="Sigmoid", use_skybox=False, embed_a=False, embed_a_len=12, classes=7,
-                 grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16, density_net_tf32=True):
+                 grid_levels=16, grid_features=8, log2_T_xyz=19, log2_T_rgb=21, base_res=16, density_net_tf32=True,
+                 density_net_tc=True):
         super().__init__()
         # The density net is the one part of the field the reference keeps in torch (nn.Linear 128 -> 128 -> 1 with
         # Softplus, double-differentiated for the normals, networks.py:54-59): its fp32 matmuls run on the SIMT pipe by
@@ -368,6 +424,11 @@ class NGP(nn.Module, _OccupancyMixin):
         # cores — the precision class SURVEY.md a12 states for this net; every other head already rounds to bf16.
         # torch's switch is process-wide, so it is flipped only around this net's own GEMMs (_tf32_matmul) and restored.
         self.density_net_tf32 = density_net_tf32
+        # density_net_tc: the whole net (both GEMM pairs, Softplus epilogues, closed-form double backward) as one tcgen05 kernel per
+        # direction (csrc/density_net.cu; bf16 operands like every other head).  Needs the reference's 128 -> 128 -> 1 shape and
+        # fp32 (TF32 off) NOT requested: density_net_tf32=False keeps meaning "exact fp32 GEMMs" for the parity tests.
+        import os
+        self.density_net_tc = density_net_tc and density_net_tf32 and os.environ.get("NGP_DENSITY_NET_TC", "1") != "0"   # env: A/B runs only
         self.rgb_act = rgb_act
         self.use_skybox = use_skybox
         self.embed_a = embed_a
@@ -408,11 +469,22 @@ class NGP(nn.Module, _OccupancyMixin):
     def _normalise(self, x):
         return (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
 
+    def _density_tc(self):
+        l0, l2 = self.xyz_net[0], self.xyz_net[2]
+        return (self.density_net_tc and l0.weight.is_cuda and l0.in_features == 128 and l0.out_features == 128 and l2.out_features == 1
+                and l0.weight.dtype == torch.float32 and self.xyz_encoder.params.dtype == torch.float32)
+
     def density(self, x, return_feat=False, grad=True, grad_feat=True):
         """sigmas (N) [, feat_rgb (N, L*F)] for x (N,3) in [-scale, scale]  (networks.py:165-184)."""
         x, ab = x.contiguous(), self.aabb()              # (x - xyz_min) / (xyz_max - xyz_min) happens inside the grid kernels
-        with torch.set_grad_enabled(grad and torch.is_grad_enabled()), _tf32_matmul(self.density_net_tf32):
-            sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(x, ab))[:, 0])
+        if self._density_tc() and not (grad and torch.is_grad_enabled()):
+            # no graph wanted (occupancy update, test-time density): encoder + ONE forward kernel, no g_e
+            with torch.no_grad():
+                l0, l2 = self.xyz_net[0], self.xyz_net[2]
+                sigmas = _dn_fw(self.xyz_encoder(x, ab), l0.weight, l0.bias, l2.weight, l2.bias, want_ge=False)[0]
+        else:
+            with torch.set_grad_enabled(grad and torch.is_grad_enabled()), _tf32_matmul(self.density_net_tf32):
+                sigmas = self.sigma_act(self.xyz_net(self.xyz_encoder(x, ab))[:, 0])
         if not return_feat:
             return sigmas
         with torch.set_grad_enabled(grad_feat and torch.is_grad_enabled()):
@@ -425,14 +497,15 @@ class NGP(nn.Module, _OccupancyMixin):
         (networks.py:186-196)."""
         x, ab = x.detach().contiguous(), self.aabb()
         l0, l2 = self.xyz_net[0], self.xyz_net[2]
+        mode = "tc05" if self._density_tc() else self.density_net_tf32
         if (self.fused_density_field and self.fused_density_head and x.is_cuda and self.xyz_encoder.params.dtype == torch.float32
                 and l0.out_features % 128 == 0 and l0.out_features <= 512):
             sigmas, g_xn = _DensityFieldNormalsFn.apply(x, self.xyz_encoder.params, l0.weight, l0.bias, l2.weight, l2.bias,
-                                                        self.xyz_encoder.grid, ab, self.density_net_tf32)
+                                                        self.xyz_encoder.grid, ab, mode)
             return sigmas, self.rgb_encoder(x, ab), g_xn / (self.xyz_max - self.xyz_min)
         enc = self.xyz_encoder(x, ab)
         if self.fused_density_head and enc.is_cuda and enc.dtype == torch.float32 and l0.out_features % 128 == 0 and l0.out_features <= 512:
-            sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias, self.density_net_tf32)
+            sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias, mode)
         else:       # any other density net: generic autograd double backward, as the reference does it
             sigmas = self.sigma_act(self.xyz_net(enc)[:, 0])
             (g_enc,) = torch.autograd.grad(sigmas, enc, torch.ones_like(sigmas), create_graph=True)
