@@ -38,10 +38,12 @@ constexpr uint32_t kDnTile = 16u * (128u * 16u + 64u);          // one 128 x 128
 constexpr uint32_t kOffB1 = 128, kOffW2 = 640, kOffScr = 1152;  // fp32 b1[128], w2[128], scratch[512]
 constexpr uint32_t kOffW1 = 3200;                               // W1 tile
 constexpr uint32_t kOffT0 = kOffW1 + kDnTile;                   // first sample tile
-constexpr uint32_t kFwSmem = kOffT0 + kDnTile;                  // 70 784 B: 3 CTAs per SM
+constexpr uint32_t kFwScratch = 8u * 32u * 36u * 4u;             // g_e transpose scratch (8 warps x 32 rows x (32+4) floats): aliases the X tile
+constexpr uint32_t kFwSmem = kOffT0 + kFwScratch;               // 73 856 B: 3 CTAs per SM
 constexpr uint32_t kOffX = kOffT0, kOffDG = kOffX + kDnTile, kOffT = kOffDG + kDnTile, kOffDZ = kOffT + kDnTile;
 constexpr uint32_t kOffOnes = kOffDZ + kDnTile;                 // 128 x 16 tile of ones
-constexpr uint32_t kBwSmem = kOffOnes + 2u * (128u * 16u + 64u);
+constexpr uint32_t kOffBwScr = kOffOnes + 2u * (128u * 16u + 64u);
+constexpr uint32_t kBwSmem = kOffBwScr + 16u * 32u * 20u * 4u;  // de transpose scratch (16 warps x 32 rows x (16+4) floats): 217 344 B
 // TMEM columns of the backward kernel
 constexpr uint32_t kColZ1 = 0, kColV = 128, kColDE = 0, kColDW1 = 256, kColDB1 = 384;
 
@@ -49,6 +51,27 @@ __device__ __forceinline__ void st_quad_bf16(uint8_t* tile, uint32_t r, uint32_t
   uint2 q;
   q.x = pack_bf16(v.x, v.y); q.y = pack_bf16(v.z, v.w);
   *reinterpret_cast<uint2*>(tile + toff(kTile, r, c)) = q;
+}
+
+// Row-major fp32 output from a thread-per-row register layout: lane r of a warp holds COLS consecutive columns of row r (what a
+// 32x32b TMEM load gives).  Stored directly, every instruction touches 32 different lines (16 B each) — the L1 serves one line
+// per clock.  Through a padded per-warp scratch (conflict-free 16-byte phases both ways) each store instruction covers
+// 32*4/COLS whole rows of COLS*4 contiguous bytes: 4 (COLS = 32) or 8 (COLS = 16) lines instead of 32.
+template <int COLS>
+__device__ __forceinline__ void store_rows_coalesced(float* scratch, const float* v, float* gbase, int64_t gstride, int rows_valid, uint32_t lane) {
+  constexpr int LD = COLS + 4, LPR = COLS / 4, RPI = 32 / LPR;
+#pragma unroll
+  for (int j = 0; j < COLS / 4; j++)
+    *reinterpret_cast<float4*>(scratch + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; it++) {
+    const int row = it * RPI + rsub;
+    const float4 x = *reinterpret_cast<const float4*>(scratch + row * LD + c4);
+    if (row < rows_valid) __stcs(reinterpret_cast<float4*>(gbase + row * gstride + c4), x);
+  }
+  __syncwarp();
 }
 
 // CTA prologue shared by both kernels: barriers, TMEM, b1 / w2 / W1 -> shared memory
@@ -76,7 +99,7 @@ __device__ __forceinline__ uint32_t dn_setup(uint8_t* smem, const float* __restr
 }
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(256) density_net_fw_kernel(const float* __restrict__ e, const float* __restrict__ W1,
+__global__ void __launch_bounds__(256, 3) density_net_fw_kernel(const float* __restrict__ e, const float* __restrict__ W1,
                                                              const float* __restrict__ b1, const float* __restrict__ w2,
                                                              const float* __restrict__ b2p, int64_t n, float* __restrict__ sigma,
                                                              float* __restrict__ s2_out, float* __restrict__ ge) {
@@ -157,17 +180,20 @@ __global__ void __launch_bounds__(256) density_net_fw_kernel(const float* __rest
     if (ge) {
       mbar_wait(bar, phase); phase ^= 1;
       fence_after_sync();
+      // G is complete, so the X / U tile is dead: it is the transpose scratch of the coalesced g_e store
+      float* scratch = reinterpret_cast<float*>(Xt) + warp * (32 * 36);
+      const int64_t wrow0 = row0 + q * 32;                       // first row of this warp's quadrant
+      const int rows_valid = (int)(n - wrow0 < 32 ? (n - wrow0 < 0 ? 0 : n - wrow0) : 32);
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         const uint32_t c0 = 64u * h + 32u * g;
         float v[32];
         tmem_ld32(trow + c0, v);
-        if (grow < n) {
-          float4* dst = reinterpret_cast<float4*>(ge + grow * kDn + c0);
 #pragma unroll
-          for (int k = 0; k < 8; k++) __stcs(dst + k, make_float4(o.sg * v[4 * k], o.sg * v[4 * k + 1], o.sg * v[4 * k + 2], o.sg * v[4 * k + 3]));
-        }
+        for (int k = 0; k < 32; k++) v[k] *= o.sg;
+        store_rows_coalesced<32>(scratch, v, ge + wrow0 * kDn + c0, kDn, rows_valid, lane);
       }
+      __syncthreads();                                           // the scratch is the next tile's X
     }
     // the next tile's first barrier orders these TMEM / scratch reads before its MMA / scratch writes
   }
@@ -312,16 +338,15 @@ __global__ void __launch_bounds__(512) density_net_bw_kernel(const float* __rest
     mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
     if (de) {
+      float* scratch = reinterpret_cast<float*>(smem + kOffBwScr) + warp * (32 * 20);
+      const int64_t wrow0 = row0 + q * 32;
+      const int rows_valid = (int)(n - wrow0 < 32 ? (n - wrow0 < 0 ? 0 : n - wrow0) : 32);
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         const uint32_t c0 = 32u * h + 16u * g;
         float v[16];
         tmem_ld16(trow + kColDE + c0, v);
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(de + grow * kDn + c0);
-#pragma unroll
-          for (int k = 0; k < 4; k++) __stcs(dst + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-        }
+        store_rows_coalesced<16>(scratch, v, de + wrow0 * kDn + c0, kDn, rows_valid, lane);
       }
     }
   }

@@ -51,3 +51,18 @@ for lo in range(0, g.n_levels, 2):
     kind = ["dense" if g.dense[l] else "hashed" for l in (lo, lo + 1)]
     print(f"levels {lo:2d}-{lo + 1:2d}: {t:7.3f} ms  res {res[lo]:5d},{res[lo + 1]:5d}  entries {g.sizes[lo]:7d},{g.sizes[lo + 1]:7d}  {kind[0]},{kind[1]}")
 print(f"sum of the pairs: {tot:.3f} ms")
+for lo in (2, 4, 6, 8):
+    print(f"levels {lo:2d}-{g.n_levels - 1:2d}: {run(lo, g.n_levels, reps):7.3f} ms  (one launch, coarse levels below {lo} left out)")
+
+
+def run_full(reps):
+    for _ in range(2):
+        check(lib.ngp_hashgrid_bw_params_tiles(ptr(xw), tcnn._aabb_arg(aabb), ptr(dy), *g.args(), S, ptr(dtab), stream()), "bw")
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        check(lib.ngp_hashgrid_bw_params_tiles(ptr(xw), tcnn._aabb_arg(aabb), ptr(dy), *g.args(), S, ptr(dtab), stream()), "bw")
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
