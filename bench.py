@@ -210,7 +210,7 @@ def kernel_breakdown(model, xyzs, dirs):
     return out
 
 
-def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1, esf=0.0, num_classes=0, extra=None):
+def render_bench(model, scene, poses, frames=9, wh=(1920, 1080), chunk=1 << 20, rank=0, world=1, esf=0.0, num_classes=0, extra=None):
     """Test-time rendering (BASELINE.json configs[4]): full frames through raymarching_test +
     composite_test_fw rounds, T_threshold 1e-2 (render.py:125); Mrays/s for both round schedules.
     With world > 1 every frame's rays are split into `world` contiguous tiles, one per rank, no collective on
@@ -238,26 +238,32 @@ def render_bench(model, scene, poses, frames=3, wh=(1920, 1080), chunk=1 << 20, 
                                renderer="wavefront" if sched == "wavefront" else "loop", **extra)
                     tot += int(r["total_samples"])
                 return tot, n
-            frame(0); torch.cuda.synchronize()
+            # warm-up: two frames for the product path (allocator pools, lazy kernel attributes), one for the comparison loops
+            for w in range(2 if sched == scheds[0] else 1):
+                frame(w); torch.cuda.synchronize()
             nf = frames if sched == scheds[0] and not full else 1
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            per_frame = []
             for i in range(nf):
-                tot, nr = frame(i + 1)
-            torch.cuda.synchronize()
-            dt = torch.tensor([(time.perf_counter() - t0) / nf], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tot, nr = frame(i + 2)
+                torch.cuda.synchronize()
+                per_frame.append(time.perf_counter() - t0)
+            per_frame.sort()
+            dt = torch.tensor([per_frame[len(per_frame) // 2]], device="cuda", dtype=torch.float64)      # median frame (wall clock: a host hiccup must not decide)
             tt = torch.tensor([float(tot)], device="cuda", dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(tt, op=dist.ReduceOp.SUM)
             dt, tot = float(dt), float(tt)
-            out[sched] = {"Mrays_per_s": nr / dt / 1e6, "ms_per_frame": dt * 1e3, "samples_per_ray": tot / nr}
+            out[sched] = {"Mrays_per_s": nr / dt / 1e6, "ms_per_frame": dt * 1e3, "samples_per_ray": tot / nr, "frames": nf,
+                          "ms_min": per_frame[0] * 1e3, "ms_max": per_frame[-1] * 1e3}
     return {"metric": "render Mrays/s", "frame": f"{wh[0]}x{wh[1]}", "value": out[scheds[0]]["Mrays_per_s"], "unit": "Mrays/s",
             "n_gpus": world, "sharding": "contiguous ray tiles per rank, no collective" if world > 1 else "single GPU",
             "legend": "wavefront = fused advance kernel per round; geometric / reference = reference-style loop over "
                       "raymarching_test + composite_test_fw with 4,8,16.. / the reference's own round sizes",
-            "timing": "wall clock incl. the per-round host read-backs, rays generated on device, max over ranks", **{k: v for k, v in out.items()}}
+            "timing": "wall clock per frame incl. the per-round host read-backs, rays generated on device; median over `frames` frames after warm-up, max over ranks", **{k: v for k, v in out.items()}}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -444,7 +450,7 @@ def gpu_arm(args):
     if not args.no_render and not full:
         rend = render_bench(model, scene, poses, rank=rank, world=world, esf=wl["esf"])
         if args.render_4k:
-            rend["4k"] = render_bench(model, scene, poses, frames=2, wh=(3840, 2160), rank=rank, world=world, esf=wl["esf"])
+            rend["4k"] = render_bench(model, scene, poses, frames=5, wh=(3840, 2160), rank=rank, world=world, esf=wl["esf"])
     dp_exchange = None
     if world > 1:     # what the gradient exchange costs: the same step with the exchange switched off (replicas diverge: timing only, last thing done)
         tr._exchange = "none"

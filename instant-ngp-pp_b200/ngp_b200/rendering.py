@@ -261,7 +261,11 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
             semantic = torch.argmax(sem, dim=-1, keepdim=True) if classes > 0 else torch.zeros(N_rays, 1, dtype=torch.long, device=device)
             normal_pred, normal_raw = F.normalize(normal_pred, dim=-1), F.normalize(normal_raw, dim=-1)
         else:
-            compact = (kwargs.get("device_loop", True) and getattr(model, "fused_density", False) and hasattr(model, "sigma_net")
+            # device_loop: rounds enqueued from bounds, counters read one round late (render_wavefront_compact).  Opt-in: measured on
+            # B200 (tools/render_probe.py, medians over 12-20 frames, profiles/r02d_render_probe.txt) the host-driven loop below is the
+            # faster one at every frame size — 1080p 11.5 vs 13.6 ms, 4K 43.0 vs 52.9 ms, a 1/8-frame tile 3.87 vs 3.99 ms: sizing
+            # every round by a bound of the alive count costs more (buffers, idle threads) than the two-counter read-back it avoids.
+            compact = (kwargs.get("device_loop", False) and getattr(model, "fused_density", False) and hasattr(model, "sigma_net")
                        and model.xyz_encoder.params.dtype == torch.float32 and model.sigma_net.mlp.n_hidden == 1 and model.sigma_net.mlp.n_out == 16
                        and model.rgb_net.mlp.n_out == 3 and model.rgb_net.mlp.width == model.sigma_net.mlp.width)
             fn = render_wavefront_compact if compact else render_wavefront
