@@ -53,27 +53,6 @@ __device__ __forceinline__ void st_quad_bf16(uint8_t* tile, uint32_t r, uint32_t
   *reinterpret_cast<uint2*>(tile + toff(kTile, r, c)) = q;
 }
 
-// Row-major fp32 output from a thread-per-row register layout: lane r of a warp holds COLS consecutive columns of row r (what a
-// 32x32b TMEM load gives).  Stored directly, every instruction touches 32 different lines (16 B each) — the L1 serves one line
-// per clock.  Through a padded per-warp scratch (conflict-free 16-byte phases both ways) each store instruction covers
-// 32*4/COLS whole rows of COLS*4 contiguous bytes: 4 (COLS = 32) or 8 (COLS = 16) lines instead of 32.
-template <int COLS>
-__device__ __forceinline__ void store_rows_coalesced(float* scratch, const float* v, float* gbase, int64_t gstride, int rows_valid, uint32_t lane) {
-  constexpr int LD = COLS + 4, LPR = COLS / 4, RPI = 32 / LPR;
-#pragma unroll
-  for (int j = 0; j < COLS / 4; j++)
-    *reinterpret_cast<float4*>(scratch + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  __syncwarp();
-  const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
-#pragma unroll
-  for (int it = 0; it < 32 / RPI; it++) {
-    const int row = it * RPI + rsub;
-    const float4 x = *reinterpret_cast<const float4*>(scratch + row * LD + c4);
-    if (row < rows_valid) __stcs(reinterpret_cast<float4*>(gbase + row * gstride + c4), x);
-  }
-  __syncwarp();
-}
-
 // CTA prologue shared by both kernels: barriers, TMEM, b1 / w2 / W1 -> shared memory
 __device__ __forceinline__ uint32_t dn_setup(uint8_t* smem, const float* __restrict__ W1, const float* __restrict__ b1,
                                              const float* __restrict__ w2, uint32_t tm_cols, uint32_t warp) {

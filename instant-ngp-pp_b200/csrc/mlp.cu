@@ -54,6 +54,7 @@ struct MlpCfg {
   int no, nop;                   // output width / padded to 16
   int act_h, act_o;
   int slots;                     // tiles in flight per CTA
+  int coop_stage;                // wide fp32 input rows staged warp-cooperatively (whole rows per load instruction)
   const int32_t* n_dev;          // forward only, optional: the row count lives in device memory (n = min(n, *n_dev)) — test-time wavefront rounds
   // shared memory: [0,64) MMA mbarriers, [64,128) landing-zone mbarriers, [128,132) TMEM base, weights (shared by all slots), then one region per slot
   uint32_t off_w[kMaxHidden + 1];  // weight tiles: layer 0..nh-1, then output layer at [nh]   (absolute)
@@ -269,7 +270,7 @@ __device__ __forceinline__ void cta_teardown(const MlpCfg& c, const Dims& d, uin
 // Thread t of a slot stages ITS row of every input segment as bf16 into the slot's X tile (16-byte row chunks:
 // a warp writes 512 contiguous bytes per store) — rows are 48..640 contiguous bytes in global memory, so every
 // sector a thread touches is fully used; SH segments are evaluated in registers (no dir_encoder pass, no cat).
-__device__ __forceinline__ void stage_row(const MlpCfg& c, const Dims& d, const SegPtrs& in, int64_t row, bool valid, uint32_t t, uint8_t* Xs) {
+__device__ __forceinline__ void stage_row(const MlpCfg& c, const Dims& d, const SegPtrs& in, int64_t row, bool valid, uint32_t t, uint8_t* Xs, int64_t n) {
   int col = 0;
   _Pragma("unroll") for (int s = 0; s < kMaxSeg; s++) { if (s >= d.n_seg) break;
     const int w = d.seg_w[s];
@@ -288,7 +289,10 @@ __device__ __forceinline__ void stage_row(const MlpCfg& c, const Dims& d, const 
       else { for (int i = 0; i < 16; i++) st_elem(Xs, kTile, t, col + i, o[i]); }
     } else {
       const bool vec = ((w & 3) == 0) && ((c.seg_stride[s] & 3) == 0) && ((((uintptr_t)in.p[s]) & 15) == 0);
-      if (vec && ((col | w) & 7) == 0) {
+      if (c.coop_stage && vec && w >= 32 && (w & (w - 1)) == 0 && (col & 3) == 0) {
+        // wide rows (the (S,128) feature matrix of the reference's heads): whole rows per load instruction, not one row per thread
+        stage_rows_coop(in.p[s], c.seg_stride[s], w, col, row - t, n, t >> 5, t & 31u, Xs);
+      } else if (vec && ((col | w) & 7) == 0) {
 #pragma unroll 4
         for (int c8 = 0; c8 < w; c8 += 8) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_fw_kernel(MlpCfg c, 
     const uint32_t xoff = c.off_x + (xt ? buf * c.x_bytes : 0u);
     if (xt) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; }
     else if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
-    else stage_row(c, d, in, row, row < n, t, Xs);
+    else stage_row(c, d, in, row, row < n, t, Xs, n);
     publish(S);
     {   // the landing zone is free again: fetch the slot's next tile while this one is computed
       const int64_t nxt = tile + tstride;
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(kSlotThreads * SLOTS) mlp_bw_kernel(MlpCfg c, 
     const uint32_t xoff = c.off_x + (xt ? buf * c.x_bytes : 0u);
     if (xt) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; }
     else if (tile_is_bulk(c, d, tile, n)) { mbar_wait(S.full, S.fphase); S.fphase ^= 1; convert_raw(c, d, S, Xs); }
-    else stage_row(c, d, in, row, valid, t, Xs);
+    else stage_row(c, d, in, row, valid, t, Xs, n);
     publish(S);
     {
       const int64_t nxt = tile + tstride;
@@ -1023,6 +1027,7 @@ int ngp::mlp_fw_launch(int n_seg, const float* const* seg_ptr, const int* seg_wi
   if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_fw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
   pick_slots(c, false, kFwSlots, (int)(sizeof(kFwSlots) / sizeof(int)));
   c.n_dev = n_dev;
+  c.coop_stage = getenv("NGP_MLP_STAGE_COOP_FW") ? env_int("NGP_MLP_STAGE_COOP_FW") : 1;
   SegPtrs in; for (int s = 0; s < kMaxSeg; s++) in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;
   bool launched = false;
   const int shape = match_shape(c);
@@ -1069,6 +1074,11 @@ NGP_API int ngp_mlp_bw(int n_seg, const float* const* seg_ptr, const int* seg_wi
   const int rc = build_cfg(c, n_seg, seg_ptr, seg_width, seg_kind, seg_stride, width, n_hidden, n_out, act_hidden, act_out, true);
   if (rc) { char b[128]; snprintf(b, sizeof b, "ngp_mlp_bw: unsupported MLP shape (code %d)", rc); return set_error_msg(b); }
   pick_slots(c, true, kBwSlots, (int)(sizeof(kBwSlots) / sizeof(int)));
+  // Wide-row staging stays per thread in the backward kernel.  Measured on the reference heads at 14 M samples (tools/step_profile_ngp.py,
+  // profiles/r02d_mlp_wide_rows.txt): cooperative staging gains 0.75 ms per forward launch, but with the backward's 2 slots of 128
+  // threads a thread's 32 independent row loads hide more latency than warp-wide batches do (+0.1 ms), and routing the input
+  // gradient through a transposed whole-row store cost +0.8 ms against the direct 64-byte runs (tried, removed).
+  c.coop_stage = getenv("NGP_MLP_STAGE_COOP_BW") ? env_int("NGP_MLP_STAGE_COOP_BW") : 0;
   SegPtrs in; SegGrads dg;
   for (int s = 0; s < kMaxSeg; s++) {
     in.p[s] = s < n_seg ? seg_ptr[s] : nullptr;

@@ -91,4 +91,65 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t p_addr, ui
 }
 
 
+// Row-major fp32 output from a thread-per-row register layout: lane r of a warp holds COLS consecutive columns of row r (what a
+// 32x32b TMEM load gives).  Stored directly, every instruction touches 32 different lines (16 B each) — the L1 serves one line
+// per clock.  Through a padded per-warp scratch (conflict-free 16-byte phases both ways) each store instruction covers
+// 32*4/COLS whole rows of COLS*4 contiguous bytes: 4 (COLS = 32) or 8 (COLS = 16) lines instead of 32.
+template <int COLS>
+__device__ __forceinline__ void store_rows_coalesced(float* scratch, const float* v, float* gbase, int64_t gstride, int rows_valid, uint32_t lane) {
+  constexpr int LD = COLS + 4, LPR = COLS / 4, RPI = 32 / LPR;
+#pragma unroll
+  for (int j = 0; j < COLS / 4; j++)
+    *reinterpret_cast<float4*>(scratch + lane * LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; it++) {
+    const int row = it * RPI + rsub;
+    const float4 x = *reinterpret_cast<const float4*>(scratch + row * LD + c4);
+    if (row < rows_valid) __stcs(reinterpret_cast<float4*>(gbase + row * gstride + c4), x);
+  }
+  __syncwarp();
+}
+
+// Wide fp32 rows -> bf16 operand tile, warp-cooperatively: consecutive lanes read consecutive float4 of a row (w/128 lines per
+// load instruction per row) instead of one row per thread (32 lines per instruction: the L1 serves one line per clock).  Warp wq of
+// the 4 warps that own a 128-row tile stages rows [32 wq, 32 wq + 32).  w: power of two >= 32 floats; col % 4 == 0; 16-byte aligned rows.
+__device__ __forceinline__ void stage_rows_coop(const float* __restrict__ seg, int64_t stride, int w, int col, int64_t row0, int64_t n,
+                                                uint32_t wq, uint32_t lane, uint8_t* Xs) {
+  const int q = w >> 2;                                           // float4 per row
+  if (q <= 32) {
+    const int sh = __ffs(q) - 1, rpi = 32 >> sh;                  // rows per instruction
+    const uint32_t rsub = lane >> sh, f4 = lane & (uint32_t)(q - 1);
+    constexpr int B = 8;                                          // rows (instructions) in flight per lane: the loads of a batch overlap
+    for (int it = 0; it < 32 / rpi; it += B) {
+      float4 v[B];
+#pragma unroll
+      for (int j = 0; j < B; j++) {
+        const uint32_t r = 32u * wq + (uint32_t)(it + j) * rpi + rsub;
+        const int64_t g = row0 + r;
+        v[j] = ((it + j) * rpi < 32 && g < n) ? __ldg(reinterpret_cast<const float4*>(seg + g * stride) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < B; j++) {
+        const uint32_t r = 32u * wq + (uint32_t)(it + j) * rpi + rsub;
+        if ((it + j) * rpi < 32) {
+          uint2 qq; qq.x = pack_bf16(v[j].x, v[j].y); qq.y = pack_bf16(v[j].z, v[j].w);
+          *reinterpret_cast<uint2*>(Xs + toff(kTile, r, col + 4 * f4)) = qq;
+        }
+      }
+    }
+  } else {
+    for (int it = 0; it < 32; it++) {
+      const uint32_t r = 32u * wq + it;
+      const int64_t g = row0 + r;
+      for (int p0 = 0; p0 < q; p0 += 32) {
+        const float4 v = g < n ? __ldg(reinterpret_cast<const float4*>(seg + g * stride) + p0 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 qq; qq.x = pack_bf16(v.x, v.y); qq.y = pack_bf16(v.z, v.w);
+        *reinterpret_cast<uint2*>(Xs + toff(kTile, r, col + 4 * (p0 + lane))) = qq;
+      }
+    }
+  }
+}
+
 }  // namespace ngp

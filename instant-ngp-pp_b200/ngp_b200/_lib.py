@@ -13,7 +13,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)                      # instant-ngp-pp_b200/
-LIB_PATH = os.path.join(_ROOT, "libngp_b200.so")
+LIB_PATH = os.environ.get("NGP_B200_LIB") or os.path.join(_ROOT, "libngp_b200.so")      # env: A/B runs of two builds only
 HEADER_PATH = os.path.join(os.path.dirname(_ROOT), "include", "ngp_b200.h")
 
 _CT = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float,

@@ -152,14 +152,16 @@ def test_geometric_schedule_renders_the_same_image_as_the_reference_schedule():
     with torch.no_grad():
         a = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="reference", renderer="loop")
         b = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric", renderer="loop")
-        c = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2)       # wavefront kernels, device-resident round loop
-        d = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, device_loop=False)   # ... host loop, exact counts
+        c = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, device_loop=True)    # wavefront kernels, device-resident round loop
+        d = render(m, ro, rd, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2)                      # ... host-driven rounds, exact counts (default)
     # the device-resident loop launches from bounds instead of exact counts: same kernels on the same samples, bit for bit
     assert torch.equal(c["rgb"], d["rgb"]) and torch.equal(c["depth"], d["depth"]) and torch.equal(c["opacity"], d["opacity"])
     assert int(c["total_samples"]) == int(d["total_samples"])
     with torch.no_grad():
         big_o, big_d = scene.image_rays(poses[1], wh=(400, 300))                                           # > 2048 rays: round-0 culling engaged
         e = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2)
+        e2 = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, device_loop=True)
+        assert torch.equal(e["rgb"], e2["rgb"]) and int(e["total_samples"]) == int(e2["total_samples"])
         f = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric", renderer="loop")
     assert torch.allclose(e["rgb"], f["rgb"], atol=2e-5) and torch.allclose(e["opacity"], f["opacity"], atol=2e-5)
     assert int(e["total_samples"]) > 0
