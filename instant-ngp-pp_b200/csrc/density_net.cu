@@ -99,17 +99,25 @@ __global__ void __launch_bounds__(256, 3) density_net_fw_kernel(const float* __r
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTile;
-    // ---- stage X: a warp reads whole 512-byte rows (4 lines per load instruction), 4 rows in flight
+    // ---- stage X: a warp reads whole 512-byte rows (4 lines per load instruction), 8 rows in flight
 #pragma unroll
-    for (int rr = 0; rr < 16; rr += 4) {
-      float4 v[4];
+    for (int rr = 0; rr < 16; rr += 8) {
+      float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < 8; j++) {
         const int64_t g = row0 + warp + 8 * (rr + j);
         v[j] = g < n ? __ldcs(reinterpret_cast<const float4*>(e + g * kDn) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) st_quad_bf16(Xt, warp + 8 * (rr + j), lane * 4, v[j]);
+      for (int j = 0; j < 8; j++) st_quad_bf16(Xt, warp + 8 * (rr + j), lane * 4, v[j]);
+    }
+    {   // this CTA's next tile -> L2 while the current one is computed
+      const int64_t nrow0 = row0 + (int64_t)gridDim.x * kTile;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; k2 += 8) {
+        const int64_t g = nrow0 + warp + 8 * (k2 + (int)(lane >> 2));
+        if (g < n) prefetch_l2(e + g * kDn + (lane & 3u) * 32);
+      }
     }
     fence_async_smem();
     fence_before_sync();
