@@ -266,6 +266,15 @@ int ngp_density_net_bw(const float* e, const float* d_ge, const float* g_e, cons
                        const float* b1, const float* w2, int64_t n, int n_in, int width, float* de, float* dW1, float* db1,
                        float* dw2, float* db2, void* stream);
 
+/* ------------------------------------------------------------------ a13: the field's two normal outputs
+ * normals_raw = -F.normalize(grads, eps=1e-6), normals_pred = -F.normalize(norm_pred_header(feat), eps=1e-6)   models/networks.py:209,222-223
+ * as one kernel per direction; scale_* = the unit-cube -> world factor of the analytic gradient (1 for none).
+ * inv (N): 1 / max(||x * scale||, eps), negated where the norm was clamped (the Jacobian there is -I/eps). */
+int ngp_neg_normalize_fw(const float* x, float scale_x, float scale_y, float scale_z, float eps, int64_t n, float* y, float* inv,
+                         void* stream);
+int ngp_neg_normalize_bw(const float* gy, const float* y, const float* inv, float scale_x, float scale_y, float scale_z, int64_t n,
+                         float* gx, void* stream);
+
 /* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
  * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */
 int ngp_grad_sumsq(const float* g, int64_t n, float* accum, void* stream);

@@ -162,6 +162,34 @@ class DistortionLoss(torch.autograd.Function):
         return vren.distortion_loss_bw(g_loss.contiguous(), ws_inc, wts_inc, ws, deltas, ts, rays_a), None, None, None
 
 
+class NegNormalize(torch.autograd.Function):
+    """-F.normalize(x * scale, p=2, dim=-1, eps) on (N,3) rows as one kernel per direction (csrc/normals.cu) — the field's
+    normals_raw / normals_pred (models/networks.py:209,222-223).  scale: None or three python floats."""
+
+    @staticmethod
+    def forward(ctx, x, scale=None, eps=1e-6):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        x = x.contiguous().float()
+        n = x.shape[0]
+        sc = tuple(float(v) for v in scale) if scale is not None else (1.0, 1.0, 1.0)
+        y = torch.empty_like(x); inv = torch.empty(n, device=x.device)
+        check(lib.ngp_neg_normalize_fw(ptr(x), *sc, float(eps), n, ptr(y), ptr(inv), stream()), "neg_normalize_fw")
+        ctx.sc = sc
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from ._lib import lib, ptr, check, stream
+        y, inv = ctx.saved_tensors
+        gx = torch.empty_like(y)
+        check(lib.ngp_neg_normalize_bw(ptr(gy.contiguous().float()), ptr(y), ptr(inv), *ctx.sc, y.shape[0], ptr(gx), stream()), "neg_normalize_bw")
+        return gx, None, None
+
+
 class TruncExp(torch.autograd.Function):
     """exp with the backward evaluated at clamp(x, -7, 7) (custom_functions.py:200-211)."""
 

@@ -19,6 +19,7 @@ argument meaning.  What changed relative to the reference's glue:
     packbits threshold is read by the kernel's caller from a 0-dim tensor only once per update.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -492,9 +493,10 @@ class NGP(nn.Module, _OccupancyMixin):
         return sigmas, feat_rgb
 
     @torch.enable_grad()
-    def grad(self, x):
+    def grad(self, x, unit=False):
         """sigmas, feat_rgb, d sigma / d x (N,3), differentiable w.r.t. the parameters
-        (networks.py:186-196)."""
+        (networks.py:186-196).  unit=True: the gradient is left in unit-cube coordinates (the caller folds 1 / (xyz_max - xyz_min)
+        into its next kernel, see _normals)."""
         x, ab = x.detach().contiguous(), self.aabb()
         l0, l2 = self.xyz_net[0], self.xyz_net[2]
         mode = "tc05" if self._density_tc() else self.density_net_tf32
@@ -502,7 +504,7 @@ class NGP(nn.Module, _OccupancyMixin):
                 and l0.out_features % 128 == 0 and l0.out_features <= 512):
             sigmas, g_xn = _DensityFieldNormalsFn.apply(x, self.xyz_encoder.params, l0.weight, l0.bias, l2.weight, l2.bias,
                                                         self.xyz_encoder.grid, ab, mode)
-            return sigmas, self.rgb_encoder(x, ab), g_xn / (self.xyz_max - self.xyz_min)
+            return sigmas, self.rgb_encoder(x, ab), (g_xn if unit else g_xn / (self.xyz_max - self.xyz_min))
         enc = self.xyz_encoder(x, ab)
         if self.fused_density_head and enc.is_cuda and enc.dtype == torch.float32 and l0.out_features % 128 == 0 and l0.out_features <= 512:
             sigmas, g_enc = _DensityNormalsFn.apply(enc, l0.weight, l0.bias, l2.weight, l2.bias, mode)
@@ -513,7 +515,7 @@ class NGP(nn.Module, _OccupancyMixin):
         # double-backward kernel
         g_xn, _ = _GridBwFn.apply(g_enc.contiguous(), x, self.xyz_encoder.params, self.xyz_encoder.grid,
                                   True, False, ab)
-        grads = g_xn / (self.xyz_max - self.xyz_min)
+        grads = g_xn if unit else g_xn / (self.xyz_max - self.xyz_min)
         feat_rgb = self.rgb_encoder(x, ab)
         return sigmas, feat_rgb, grads
 
@@ -541,16 +543,27 @@ class NGP(nn.Module, _OccupancyMixin):
             return _TwoHeadsFn.apply(feat_rgb, a.params, b.params, ma, mb)
         return a(feat_rgb), b(feat_rgb)
 
+    fused_normals = True          # -normalize(.) of both normal outputs as one kernel per direction (csrc/normals.cu)
+
+    def _normals(self, grads, n_out, fused):
+        """-> normals_raw, normals_pred (networks.py:209,222-223).  fused: `grads` is in unit-cube coordinates and the world scale
+        1 / (xyz_max - xyz_min) is applied inside the kernel."""
+        if fused:
+            from .custom_functions import NegNormalize
+            inv_range = tuple(1.0 / r for r in self.aabb()[3:])
+            return NegNormalize.apply(grads, inv_range, 1e-6), NegNormalize.apply(n_out, None, 1e-6)
+        return -F.normalize(grads, p=2, dim=-1, eps=1e-6), -F.normalize(n_out, p=2, dim=-1, eps=1e-6)
+
     def log_radiance_to_rgb(self, log_radiances, **kwargs):
         out = [getattr(self, f"tonemapper_net_{i}")(log_radiances[:, i:i + 1]) for i in range(3)]
         return torch.cat(out, 1)
 
     def forward(self, x, d, **kwargs):
         """-> sigmas (N), rgbs (N,3), normals_raw (N,3), normals_pred (N,3), semantic (N,C)  (networks.py:198-240)"""
-        sigmas, feat_rgb, grads = self.grad(x)
-        normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
+        fused = self.fused_normals and x.is_cuda and os.environ.get("NGP_FUSED_NORMALS", "1") != "0"       # env: A/B runs only
+        sigmas, feat_rgb, grads = self.grad(x, unit=fused)
         n_out, s_out = self._aux_heads(feat_rgb)
-        normals_pred = -F.normalize(n_out, p=2, dim=-1, eps=1e-6)
+        normals_raw, normals_pred = self._normals(grads, n_out, fused)
         semantic = self.semantic_act(s_out)
         rgbs = self._rgb(d, feat_rgb, kwargs)
         return sigmas, rgbs, normals_raw, normals_pred, semantic
@@ -558,13 +571,13 @@ class NGP(nn.Module, _OccupancyMixin):
     def forward_test(self, x, d, **kwargs):
         """Same quantities in the reference's test-time order: sigmas, rgbs, normals_pred,
         normals_raw, semantic (networks.py:242-282).  No graph is kept."""
+        fused = self.fused_normals and x.is_cuda
         with torch.enable_grad():
-            sigmas, feat_rgb, grads = self.grad(x)
+            sigmas, feat_rgb, grads = self.grad(x, unit=fused)
         sigmas, feat_rgb, grads = sigmas.detach(), feat_rgb.detach(), grads.detach()
         with torch.no_grad():
-            normals_raw = -F.normalize(grads, p=2, dim=-1, eps=1e-6)
             n_out, s_out = self._aux_heads(feat_rgb)
-            normals_pred = -F.normalize(n_out, p=2, dim=-1, eps=1e-6)
+            normals_raw, normals_pred = self._normals(grads, n_out, fused)
             semantic = self.semantic_act(s_out)
             rgbs = self._rgb(d, feat_rgb, kwargs)
         return sigmas, rgbs, normals_pred, normals_raw, semantic

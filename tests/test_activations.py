@@ -60,3 +60,29 @@ def test_truncexp_trunctanh_match_reference_classes_cpu():
 def test_activations_match_reference_classes_gpu():
     from baseline import ref_harness
     _check("cuda", ref_harness.load(vren="ours", tcnn="standin").custom_functions)
+
+
+@pytest.mark.gpu
+def test_neg_normalize_matches_torch_normalize_forward_and_backward():
+    """NegNormalize (csrc/normals.cu) = -F.normalize(x * scale, eps=1e-6) (models/networks.py:209,222-223), incl. rows below eps (the
+    clamp branch: Jacobian -I/eps), zero rows and the folded unit-cube -> world scale."""
+    import torch.nn.functional as F
+    from ngp_b200.custom_functions import NegNormalize
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 100003
+    x = torch.randn(n, 3, device="cuda", generator=g) * 3
+    x[:50] *= 1e-8                                  # below eps
+    x[50:60] = 0.0
+    x[60:70, 1:] = 0.0                              # axis-aligned
+    gy = torch.randn(n, 3, device="cuda", generator=g)
+    for scale in (None, (1.0 / 16, 1.0 / 16, 1.0 / 16), (0.5, 2.0, 0.125)):
+        a = x.clone().requires_grad_(True)
+        b = x.clone().requires_grad_(True)
+        ya = NegNormalize.apply(a, scale, 1e-6)
+        v = b if scale is None else b * torch.tensor(scale, device="cuda")
+        yb = -F.normalize(v, p=2, dim=-1, eps=1e-6)
+        assert torch.allclose(ya, yb, rtol=1e-6, atol=1e-7)
+        (ga,) = torch.autograd.grad(ya, a, gy)
+        (gb,) = torch.autograd.grad(yb, b, gy)
+        # torch differentiates clamp_min(norm, eps) with a zero gradient on clamped rows, i.e. d(v/eps) = I/eps there as well
+        assert torch.allclose(ga, gb, rtol=2e-5, atol=1e-6 * float(gb.abs().max())), float((ga - gb).abs().max())
