@@ -522,7 +522,7 @@ def gpu_arm(args):
                 del buf
         except Exception as ex:
             roof["traffic_note"] = "no committed ncu capture for this kernel / workload: " + repr(ex)[:120]
-    cpu = None if args.no_cpu else cpu_arm(steps=3, warmup=1)[0]
+    cpu = None if (args.no_cpu or world > 1) else cpu_arm(steps=3, warmup=1)[0]       # the CPU leg is timed at N=1 only (rank 0)
     value = world * R * args.steps / t_res
     # reference GPU path on the same box, same run: the reference's unmodified glue + its own CUDA kernels + a
     # torch-op tinycudann stand-in, same scene / batch recipe / lr / Adam eps, trained args.ref_steps steps, last 10 timed
