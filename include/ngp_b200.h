@@ -274,6 +274,12 @@ int ngp_neg_normalize_fw(const float* x, float scale_x, float scale_y, float sca
                          void* stream);
 int ngp_neg_normalize_bw(const float* gy, const float* y, const float* inv, float scale_x, float scale_y, float scale_z, int64_t n,
                          float* gx, void* stream);
+/* the per-sample inputs of RefLoss   models/rendering.py:243-246:  normals_diff = (normals_raw - normals_pred)^2,
+ * normals_ori = clamp(sum(normals_raw * normalize(dirs)), min=0)^2, one kernel per direction */
+int ngp_refloss_prep_fw(const float* normals_raw, const float* normals_pred, const float* dirs, int64_t n, float* normals_diff,
+                        float* normals_ori, void* stream);
+int ngp_refloss_prep_bw(const float* normals_raw, const float* normals_pred, const float* dirs, const float* g_diff, const float* g_ori,
+                        int64_t n, float* g_raw, float* g_pred, void* stream);
 
 /* ------------------------------------------------------------------ f1: fused dense Adam + grad-norm clip
  * torch.optim.Adam + gradient_clip_val=50   train.py:244-251, 435   */

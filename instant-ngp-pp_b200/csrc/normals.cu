@@ -38,9 +38,66 @@ __global__ void __launch_bounds__(256) neg_normalize_bw_kernel(const float* __re
   gx[3 * i] = d0 * sx; gx[3 * i + 1] = d1 * sy; gx[3 * i + 2] = d2 * sz;
 }
 
+// The per-sample inputs of the Ref-NeRF regularisers (models/rendering.py:243-246):
+//     normals_diff = (normals_raw - normals_pred)^2                                  (S,3)
+//     normals_ori  = clamp(sum(normals_raw * normalize(dirs)), min=0)^2              (S)
+// as one kernel per direction instead of sub, pow, normalize (5 ops), mul, sum, clamp, pow and their ~20 backward kernels.
+__global__ void __launch_bounds__(256) refloss_prep_fw_kernel(const float* __restrict__ nraw, const float* __restrict__ npred,
+                                                              const float* __restrict__ dirs, int64_t n, float* __restrict__ diff,
+                                                              float* __restrict__ ori) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r0 = __ldg(nraw + 3 * i), r1 = __ldg(nraw + 3 * i + 1), r2 = __ldg(nraw + 3 * i + 2);
+  const float p0 = __ldg(npred + 3 * i), p1 = __ldg(npred + 3 * i + 1), p2 = __ldg(npred + 3 * i + 2);
+  const float d0 = __ldg(dirs + 3 * i), d1 = __ldg(dirs + 3 * i + 1), d2 = __ldg(dirs + 3 * i + 2);
+  const float inv = 1.0f / fmaxf(sqrtf(d0 * d0 + d1 * d1 + d2 * d2), 1e-6f);
+  const float e0 = r0 - p0, e1 = r1 - p1, e2 = r2 - p2;
+  diff[3 * i] = e0 * e0; diff[3 * i + 1] = e1 * e1; diff[3 * i + 2] = e2 * e2;
+  const float c = fmaxf((r0 * d0 + r1 * d1 + r2 * d2) * inv, 0.f);
+  ori[i] = c * c;
+}
+__global__ void __launch_bounds__(256) refloss_prep_bw_kernel(const float* __restrict__ nraw, const float* __restrict__ npred,
+                                                              const float* __restrict__ dirs, const float* __restrict__ gdiff,
+                                                              const float* __restrict__ gori, int64_t n, float* __restrict__ graw,
+                                                              float* __restrict__ gpred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r0 = __ldg(nraw + 3 * i), r1 = __ldg(nraw + 3 * i + 1), r2 = __ldg(nraw + 3 * i + 2);
+  const float p0 = __ldg(npred + 3 * i), p1 = __ldg(npred + 3 * i + 1), p2 = __ldg(npred + 3 * i + 2);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  if (gdiff) {
+    a0 = 2.f * (r0 - p0) * __ldg(gdiff + 3 * i); a1 = 2.f * (r1 - p1) * __ldg(gdiff + 3 * i + 1); a2 = 2.f * (r2 - p2) * __ldg(gdiff + 3 * i + 2);
+  }
+  if (gpred) { gpred[3 * i] = -a0; gpred[3 * i + 1] = -a1; gpred[3 * i + 2] = -a2; }
+  if (gori) {
+    const float d0 = __ldg(dirs + 3 * i), d1 = __ldg(dirs + 3 * i + 1), d2 = __ldg(dirs + 3 * i + 2);
+    const float inv = 1.0f / fmaxf(sqrtf(d0 * d0 + d1 * d1 + d2 * d2), 1e-6f);
+    const float c = (r0 * d0 + r1 * d1 + r2 * d2) * inv;
+    if (c > 0.f) { const float k = 2.f * c * __ldg(gori + i) * inv; a0 = fmaf(k, d0, a0); a1 = fmaf(k, d1, a1); a2 = fmaf(k, d2, a2); }
+  }
+  if (graw) { graw[3 * i] = a0; graw[3 * i + 1] = a1; graw[3 * i + 2] = a2; }
+}
+
 }  // namespace ngp
 
 using namespace ngp;
+
+// normals_diff (S,3), normals_ori (S) of models/rendering.py:243-246 from normals_raw, normals_pred, dirs (all (S,3)).
+NGP_API int ngp_refloss_prep_fw(const float* normals_raw, const float* normals_pred, const float* dirs, int64_t n, float* normals_diff,
+                                float* normals_ori, void* stream) {
+  if (n <= 0) return 0;
+  refloss_prep_fw_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(normals_raw, normals_pred, dirs, n, normals_diff, normals_ori);
+  NGP_LAUNCH_CHECK("ngp_refloss_prep_fw");
+  return 0;
+}
+// upstream g_diff (S,3) | NULL, g_ori (S) | NULL -> g_raw (S,3) | NULL, g_pred (S,3) | NULL
+NGP_API int ngp_refloss_prep_bw(const float* normals_raw, const float* normals_pred, const float* dirs, const float* g_diff, const float* g_ori,
+                                int64_t n, float* g_raw, float* g_pred, void* stream) {
+  if (n <= 0) return 0;
+  refloss_prep_bw_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(normals_raw, normals_pred, dirs, g_diff, g_ori, n, g_raw, g_pred);
+  NGP_LAUNCH_CHECK("ngp_refloss_prep_bw");
+  return 0;
+}
 
 // y (N,3) = -normalize(x * scale, eps) ; inv (N): 1 / max(||x*scale||, eps), negated on clamped rows (saved for the backward).
 // scale: three HOST floats (the field's 1 / (xyz_max - xyz_min); pass 1,1,1 for none).

@@ -190,6 +190,37 @@ class NegNormalize(torch.autograd.Function):
         return gx, None, None
 
 
+class RefLossPrep(torch.autograd.Function):
+    """normals_diff = (normals_raw - normals_pred)**2 and normals_ori = clamp(sum(normals_raw * normalize(dirs)), min=0)**2
+    (models/rendering.py:243-246) as one kernel per direction (csrc/normals.cu)."""
+
+    @staticmethod
+    def forward(ctx, normals_raw, normals_pred, dirs):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        nr, npd, d = normals_raw.contiguous().float(), normals_pred.contiguous().float(), dirs.contiguous().float()
+        n = nr.shape[0]
+        diff = torch.empty_like(nr); ori = torch.empty(n, device=nr.device)
+        check(lib.ngp_refloss_prep_fw(ptr(nr), ptr(npd), ptr(d), n, ptr(diff), ptr(ori), stream()), "refloss_prep_fw")
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(nr, npd, d)
+        return diff, ori
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_diff, g_ori):
+        from ._lib import lib, ptr, check, stream
+        nr, npd, d = ctx.saved_tensors
+        need_r, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_raw = torch.empty_like(nr) if need_r else None
+        g_pred = torch.empty_like(nr) if need_p else None
+        check(lib.ngp_refloss_prep_bw(ptr(nr), ptr(npd), ptr(d), ptr(g_diff.contiguous()) if g_diff is not None else None,
+                                      ptr(g_ori.contiguous()) if g_ori is not None else None, nr.shape[0], ptr(g_raw), ptr(g_pred), stream()),
+              "refloss_prep_bw")
+        return g_raw, g_pred, None
+
+
 class TruncExp(torch.autograd.Function):
     """exp with the backward evaluated at clamp(x, -7, 7) (custom_functions.py:200-211)."""
 

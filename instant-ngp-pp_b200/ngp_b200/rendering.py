@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from . import vren
-from .custom_functions import ExpandPerRay, RayAABBIntersector, RayMarcher, RefLoss, VolumeRenderer, VolumeRendererLite
+from .custom_functions import ExpandPerRay, RayAABBIntersector, RayMarcher, RefLoss, RefLossPrep, VolumeRenderer, VolumeRendererLite
 
 MAX_SAMPLES = 1024      # models/rendering.py:9
 NEAR_DISTANCE = 0.01    # models/rendering.py:10
@@ -339,9 +339,12 @@ def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
     if lite:
         return results
     # Ref-NeRF regularisers (rendering.py:243-249)
-    normals_diff = (normals_raw - normals_pred) ** 2
-    view = F.normalize(dirs, p=2, dim=-1, eps=1e-6)
-    normals_ori = torch.clamp(torch.sum(normals_raw * view, dim=-1), min=0.) ** 2
+    if normals_raw.is_cuda and normals_raw.dtype == torch.float32 and normals_pred.dtype == torch.float32:
+        normals_diff, normals_ori = RefLossPrep.apply(normals_raw, normals_pred, dirs)
+    else:
+        normals_diff = (normals_raw - normals_pred) ** 2
+        view = F.normalize(dirs, p=2, dim=-1, eps=1e-6)
+        normals_ori = torch.clamp(torch.sum(normals_raw * view, dim=-1), min=0.) ** 2
     results["Ro"], results["Rp"] = RefLoss.apply(sigmas.detach().contiguous(), normals_diff.contiguous(),
                                                  normals_ori.contiguous(), results["deltas"], results["ts"], rays_a,
                                                  T_thr)

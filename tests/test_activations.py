@@ -86,3 +86,31 @@ def test_neg_normalize_matches_torch_normalize_forward_and_backward():
         (gb,) = torch.autograd.grad(yb, b, gy)
         # torch differentiates clamp_min(norm, eps) with a zero gradient on clamped rows, i.e. d(v/eps) = I/eps there as well
         assert torch.allclose(ga, gb, rtol=2e-5, atol=1e-6 * float(gb.abs().max())), float((ga - gb).abs().max())
+
+
+@pytest.mark.gpu
+def test_refloss_prep_matches_the_torch_ops_forward_and_backward():
+    """RefLossPrep (csrc/normals.cu) = the reference's per-sample inputs of RefLoss (models/rendering.py:243-246):
+    (normals_raw - normals_pred)**2 and clamp(sum(normals_raw * normalize(dirs)), min=0)**2, with their gradients."""
+    import torch.nn.functional as F
+    from ngp_b200.custom_functions import RefLossPrep
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 70001
+    raw = F.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1)
+    pred = F.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=-1)
+    dirs = torch.randn(n, 3, device="cuda", generator=g) * 2
+    dirs[:5] = 0.0                                                   # normalize's eps branch
+    gd, go = torch.randn(n, 3, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g)
+    a = [raw.clone().requires_grad_(True), pred.clone().requires_grad_(True)]
+    b = [raw.clone().requires_grad_(True), pred.clone().requires_grad_(True)]
+    da, oa = RefLossPrep.apply(a[0], a[1], dirs)
+    db = (b[0] - b[1]) ** 2
+    ob = torch.clamp(torch.sum(b[0] * F.normalize(dirs, p=2, dim=-1, eps=1e-6), dim=-1), min=0.) ** 2
+    assert torch.allclose(da, db, rtol=1e-6, atol=1e-7) and torch.allclose(oa, ob, rtol=1e-5, atol=1e-7)
+    ga = torch.autograd.grad((da * gd).sum() + (oa * go).sum(), a)
+    gb = torch.autograd.grad((db * gd).sum() + (ob * go).sum(), b)
+    for x, y in zip(ga, gb):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)
+    (g1,) = torch.autograd.grad((RefLossPrep.apply(a[0], a[1], dirs)[1] * go).sum(), a[0])      # one output unused
+    (g2,) = torch.autograd.grad((torch.clamp(torch.sum(b[0] * F.normalize(dirs, p=2, dim=-1, eps=1e-6), dim=-1), min=0.) ** 2 * go).sum(), b[0])
+    assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-6)
