@@ -333,8 +333,9 @@ def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
     elif esf != 0 and kwargs.get("random_bg", False):
         rgb_bg = torch.rand(3, device=rays_o.device)
     else:
-        rgb_bg = torch.zeros(3, device=rays_o.device)
-    results["rgb"] = results["rgb"] + rgb_bg * (1 - results["opacity"])[:, None]
+        rgb_bg = None                    # black background: rgb + 0 * (1 - opacity) is rgb itself (rendering.py:236-241), no kernels for it
+    if rgb_bg is not None:
+        results["rgb"] = results["rgb"] + rgb_bg * (1 - results["opacity"])[:, None]
 
     if lite:
         return results
