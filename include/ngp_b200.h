@@ -266,6 +266,12 @@ int ngp_density_net_bw(const float* e, const float* d_ge, const float* g_e, cons
                        const float* b1, const float* w2, int64_t n, int n_in, int width, float* de, float* dW1, float* db1,
                        float* dw2, float* db2, void* stream);
 
+/* ------------------------------------------------------------------ a14: photometric + opacity terms of NeRFLoss
+ * d['rgb'] = (results['rgb'] - target['rgb'])**2 ; d['opacity'] = lambda_opa * (-o * log(o)), o = opacity + 1e-10   losses.py:89-96
+ * and loss = sum(mean) of train.py:310: the scalar and both gradients from one pass (loss[0] +=, caller zeroes). */
+int ngp_basic_loss(const float* rgb, const float* target, const float* opacity, int64_t n_rays, float lambda_opa, float* loss,
+                   float* drgb, float* dopacity, void* stream);
+
 /* ------------------------------------------------------------------ a13: the field's two normal outputs
  * normals_raw = -F.normalize(grads, eps=1e-6), normals_pred = -F.normalize(norm_pred_header(feat), eps=1e-6)   models/networks.py:209,222-223
  * as one kernel per direction; scale_* = the unit-cube -> world factor of the analytic gradient (1 for none).

@@ -220,3 +220,51 @@ NGP_API int ngp_composite_refloss_bw(const float* dL_dloss_o, const float* dL_dl
   NGP_LAUNCH_CHECK("ngp_composite_refloss_bw");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ photometric + opacity terms
+// mean((rgb - target)^2) + mean(lambda_opa * -(o + 1e-10) * log(o + 1e-10))  — the two per-ray terms every configuration of NeRFLoss
+// has (losses.py:89-96) together with their gradients, in ONE pass: the reference (and round 1 here) spends ~12 elementwise /
+// reduction kernels forward and as many backward on (R,3) / (R) tensors for them.  The gradients are written by the forward pass
+// (the loss is a plain mean: d/d rgb = 2 (rgb - target) / (3R), d/d o = -lambda (log(o + eps) + 1) / R) and scaled by the upstream
+// scalar in the backward.
+namespace ngp {
+__global__ void __launch_bounds__(256) basic_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ target,
+                                                         const float* __restrict__ opacity, int64_t n, float lambda_opa,
+                                                         float* __restrict__ loss, float* __restrict__ drgb, float* __restrict__ dopacity) {
+  float acc_c = 0.f, acc_o = 0.f;
+  const float inv3n = 1.0f / (3.0f * (float)n), invn = 1.0f / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float e = __ldg(rgb + 3 * i + c) - __ldg(target + 3 * i + c);
+      acc_c = fmaf(e, e, acc_c);
+      drgb[3 * i + c] = 2.f * e * inv3n;
+    }
+    const float o = __ldg(opacity + i) + 1e-10f;
+    const float lg = logf(o);
+    acc_o -= o * lg;
+    dopacity[i] = -lambda_opa * (lg + 1.f) * invn;
+  }
+  acc_c = warp_sum(acc_c); acc_o = warp_sum(acc_o);
+  __shared__ float sc[8], so[8];
+  if ((threadIdx.x & 31) == 0) { sc[threadIdx.x >> 5] = acc_c; so[threadIdx.x >> 5] = acc_o; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; w++) { a += sc[w]; b += so[w]; }
+    atomicAdd(loss, a * inv3n + lambda_opa * b * invn);
+  }
+}
+}  // namespace ngp
+
+// loss[0] += mean((rgb - target)^2) + lambda_opa * mean(-(o + 1e-10) log(o + 1e-10))   (caller zeroes loss);
+// drgb (R,3), dopacity (R) = the gradients of that scalar.
+NGP_API int ngp_basic_loss(const float* rgb, const float* target, const float* opacity, int64_t n_rays, float lambda_opa, float* loss,
+                           float* drgb, float* dopacity, void* stream) {
+  if (n_rays <= 0) return 0;
+  const int64_t blocks = ceil_div(n_rays, 256);
+  basic_loss_kernel<<<(unsigned)(blocks < kSMs * 4 ? blocks : kSMs * 4), 256, 0, (cudaStream_t)stream>>>(rgb, target, opacity, n_rays, lambda_opa, loss,
+                                                                                                drgb, dopacity);
+  NGP_LAUNCH_CHECK("ngp_basic_loss");
+  return 0;
+}

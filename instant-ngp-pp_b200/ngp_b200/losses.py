@@ -39,6 +39,30 @@ class ExponentialAnnealingWeight:
         return max(self.min, self.max * math.exp(-Tcur * self.k))
 
 
+class _BasicLossFn(torch.autograd.Function):
+    """mean((rgb - target)**2) + mean(lambda_opa * -(o + 1e-10) * log(o + 1e-10)) as ONE kernel that also writes both gradients
+    (csrc/losses.cu ngp_basic_loss); the backward only scales them by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, rgb, target, opacity, lambda_opa):
+        from . import _lib
+        from ._lib import lib, ptr, check, stream
+        _lib.require_device()
+        rgb, target, opacity = rgb.contiguous(), target.contiguous(), opacity.contiguous()
+        n = rgb.shape[0]
+        loss = torch.zeros((), device=rgb.device)
+        drgb = torch.empty_like(rgb); dopa = torch.empty_like(opacity)
+        check(lib.ngp_basic_loss(ptr(rgb), ptr(target), ptr(opacity), n, float(lambda_opa), ptr(loss), ptr(drgb), ptr(dopa), stream()), "basic_loss")
+        ctx.save_for_backward(drgb, dopa)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        drgb, dopa = ctx.saved_tensors
+        return (drgb * g if ctx.needs_input_grad[0] else None), None, (dopa * g if ctx.needs_input_grad[2] else None), None
+
+
 class NeRFLoss(nn.Module):
     """Per-ray loss dictionary; weights as in losses.py:75-83."""
 
@@ -55,8 +79,24 @@ class NeRFLoss(nn.Module):
         self.Annealing = ExponentialAnnealingWeight(max=1, min=6e-2, k=1e-3)
         self.CrossEntropyLoss = nn.CrossEntropyLoss(ignore_index=256)
 
-    def forward(self, results, target, **kwargs):
+    def total(self, results, target, **kwargs):
+        """sum(v.mean() for v in self(results, target, **kwargs).values()) — train.py:310 — as a scalar tensor.  The photometric and
+        opacity terms, which every configuration has, come from one fused kernel with their gradients; the others from forward()."""
+        rgb, opa = results["rgb"], results["opacity"]
+        fused = (rgb.is_cuda and rgb.dtype == torch.float32 and opa.dtype == torch.float32 and not kwargs.get("embed_msk", False)
+                 and rgb.dim() == 2 and rgb.shape[1] == 3 and target["rgb"].shape == rgb.shape and target["rgb"].dtype == torch.float32)
+        if not fused:
+            return sum(v.mean() for v in self(results, target, **kwargs).values())
+        loss = _BasicLossFn.apply(rgb, target["rgb"], opa, self.lambda_opa)
+        rest = self(results, target, _skip_basic=True, **kwargs)
+        for v in rest.values():
+            loss = loss + v.mean()
+        return loss
+
+    def forward(self, results, target, _skip_basic=False, **kwargs):
         d = {}
+        if _skip_basic:
+            return self._other_terms(d, results, target, **kwargs)
         if kwargs.get("embed_msk", False):
             m = kwargs["mask"]
             d["r_ms"] = torch.mean(m ** 2) * self.Annealing.getWeight(kwargs["step"])
@@ -65,6 +105,9 @@ class NeRFLoss(nn.Module):
             d["rgb"] = (results["rgb"] - target["rgb"]) ** 2
         o = results["opacity"] + 1e-10
         d["opacity"] = self.lambda_opa * (-o * torch.log(o))
+        return self._other_terms(d, results, target, **kwargs)
+
+    def _other_terms(self, d, results, target, **kwargs):
         if self.lambda_distortion > 0:
             d["distortion"] = self.lambda_distortion * DistortionLoss.apply(
                 results["ws"], results["deltas"], results["ts"], results["rays_a"])

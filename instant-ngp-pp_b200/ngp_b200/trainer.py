@@ -109,8 +109,7 @@ class Trainer:
             m.update_density_grid(self.density_threshold, warmup=self.step < self.warmup_steps)
         kw = {**self.render_kwargs, **step_kwargs} if step_kwargs else self.render_kwargs
         results = render(m, rays_o, rays_d, **kw)
-        losses = self.loss_fn(results, {"rgb": rgb_gt, **(target or {})}, **kw)
-        loss = sum(v.mean() for v in losses.values())
+        loss = self.loss_fn.total(results, {"rgb": rgb_gt, **(target or {})}, **kw)        # train.py:310 sum(lo.mean())
         if host_loss:
             if self._loss_host is None:
                 self._loss_host = torch.empty((), dtype=torch.float32).pin_memory()

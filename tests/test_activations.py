@@ -114,3 +114,25 @@ def test_refloss_prep_matches_the_torch_ops_forward_and_backward():
     (g1,) = torch.autograd.grad((RefLossPrep.apply(a[0], a[1], dirs)[1] * go).sum(), a[0])      # one output unused
     (g2,) = torch.autograd.grad((torch.clamp(torch.sum(b[0] * F.normalize(dirs, p=2, dim=-1, eps=1e-6), dim=-1), min=0.) ** 2 * go).sum(), b[0])
     assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_basic_loss_equals_the_sum_of_means():
+    """NeRFLoss.total (ngp_basic_loss: photometric + opacity terms and their gradients in one kernel) = sum(v.mean()) over the loss
+    dictionary (losses.py:89-96, train.py:310), value and gradients, incl. opacity 0 (log(1e-10)) and 1."""
+    from ngp_b200.losses import NeRFLoss
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 262144 + 7
+    rgb = torch.rand(n, 3, device="cuda", generator=g)
+    tgt = torch.rand(n, 3, device="cuda", generator=g)
+    opa = torch.rand(n, device="cuda", generator=g)
+    opa[:100] = 0.0; opa[100:200] = 1.0
+    fn = NeRFLoss(lambda_opa=2e-4, lambda_distortion=0)
+    a = [rgb.clone().requires_grad_(True), opa.clone().requires_grad_(True)]
+    b = [rgb.clone().requires_grad_(True), opa.clone().requires_grad_(True)]
+    la = fn.total({"rgb": a[0], "opacity": a[1]}, {"rgb": tgt})
+    lb = sum(v.mean() for v in fn({"rgb": b[0], "opacity": b[1]}, {"rgb": tgt}).values())
+    assert abs(float(la) - float(lb)) < 1e-6 * abs(float(lb)) + 1e-9
+    ga = torch.autograd.grad(la * 3.0, a)
+    gb = torch.autograd.grad(lb * 3.0, b)
+    assert torch.allclose(ga[0], gb[0], rtol=1e-5, atol=1e-12) and torch.allclose(ga[1], gb[1], rtol=1e-5, atol=1e-12)
