@@ -41,6 +41,9 @@ int ngp_ray_sphere_intersect(const float* rays_o, const float* rays_d, const flo
 /* ray generation: get_rays  datasets/ray_utils.py:49-72 with the gathers of train.py:136-137 fused:
  * rays_d = poses[img_idx][:, :3] . directions[pix_idx], rays_o = poses[img_idx][:, 3].  directions (P,3), poses (V,3,4);
  * img_idx NULL = poses[0] for every ray, pix_idx NULL = directions[i]. */
+/* hits_t[(t1 >= 0) & (t1 < near), 0, 0] = near with t1 = hits_t[:, 0, 0]   models/rendering.py:29-30; in place; row_stride = floats
+ * between consecutive rays' t1 (2 * max_hits) */
+int ngp_near_clamp(float* hits_t, int64_t n_rays, int64_t row_stride, float near_distance, void* stream);
 int ngp_get_rays(const float* directions, const float* poses, const int64_t* img_idx, const int64_t* pix_idx,
                  int64_t n_rays, float* rays_o, float* rays_d, void* stream);
 

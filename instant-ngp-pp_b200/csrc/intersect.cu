@@ -169,3 +169,20 @@ NGP_API int ngp_ray_sphere_intersect(const float* rays_o, const float* rays_d, c
   NGP_LAUNCH_CHECK("ngp_ray_sphere_intersect");
   return 0;
 }
+
+// hits_t[(hits_t[:,0,0] >= 0) & (hits_t[:,0,0] < near), 0, 0] = near   (models/rendering.py:29-30: rays that start inside the box begin at
+// the near plane) — in place, one launch instead of the boolean-mask index_put (compare, compare, and, nonzero / where, copy).
+namespace ngp {
+__global__ void __launch_bounds__(256) near_clamp_kernel(float* __restrict__ hits_t, int64_t n, int64_t row_stride, float near_t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t1 = hits_t[i * row_stride];
+  if (t1 >= 0.f && t1 < near_t) hits_t[i * row_stride] = near_t;
+}
+}  // namespace ngp
+NGP_API int ngp_near_clamp(float* hits_t, int64_t n_rays, int64_t row_stride, float near_distance, void* stream) {
+  if (n_rays <= 0) return 0;
+  ngp::near_clamp_kernel<<<(unsigned)ngp::ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(hits_t, n_rays, row_stride, near_distance);
+  NGP_LAUNCH_CHECK("ngp_near_clamp");
+  return 0;
+}

@@ -17,9 +17,13 @@ NEAR_DISTANCE = 0.01    # models/rendering.py:10
 def render(model, rays_o, rays_d, **kwargs):
     rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
     _, hits_t, _ = RayAABBIntersector.apply(rays_o, rays_d, model.center, model.half_size, 1)
-    # rays that start inside the box begin at the near plane (rendering.py:30) — one fused where
-    t1 = hits_t[:, 0, 0]
-    hits_t[:, 0, 0] = torch.where((t1 >= 0) & (t1 < NEAR_DISTANCE), torch.full_like(t1, NEAR_DISTANCE), t1)
+    # rays that start inside the box begin at the near plane (rendering.py:29-30)
+    if hits_t.is_cuda and hits_t.is_contiguous() and hits_t.dtype == torch.float32:
+        from ._lib import lib, ptr, check, stream
+        check(lib.ngp_near_clamp(ptr(hits_t), hits_t.shape[0], hits_t.stride(0), NEAR_DISTANCE, stream()), "near_clamp")
+    else:
+        t1 = hits_t[:, 0, 0]
+        hits_t[:, 0, 0] = torch.where((t1 >= 0) & (t1 < NEAR_DISTANCE), torch.full_like(t1, NEAR_DISTANCE), t1)
 
     fn = _render_rays_test if kwargs.get("test_time", False) else _render_rays_train
     results = fn(model, rays_o, rays_d, hits_t, **kwargs)

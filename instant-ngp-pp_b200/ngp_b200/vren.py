@@ -194,12 +194,12 @@ def composite_train_fw(sigmas, rgbs, normals_pred, sems, deltas, ts, rays_a, T_t
     C = int(classes)
     # per-ray rows are tiny: zero them so a rays_a that does not list every ray still matches the
     # reference's torch::zeros outputs; ws is fully written by the kernel.
-    total = torch.zeros(R, dtype=_I64, device=dev)
-    opacity = torch.zeros(R, dtype=_F32, device=dev)
-    depth = torch.zeros(R, dtype=_F32, device=dev)
-    rgb = torch.zeros(R, 3, dtype=_F32, device=dev)
-    normal = torch.zeros(R, 3, dtype=_F32, device=dev)
-    sem = torch.zeros(R, C, dtype=_F32, device=dev)
+    # ... from ONE zero fill: [total i64 (R) | opacity | depth | rgb (R,3) | normal (R,3) | sem (R,C)] carved out of a flat buffer
+    flat = torch.zeros(R * (10 + C), dtype=_F32, device=dev)
+    total = flat[:2 * R].view(_I64)
+    opacity, depth = flat[2 * R:3 * R], flat[3 * R:4 * R]
+    rgb, normal = flat[4 * R:7 * R].view(R, 3), flat[7 * R:10 * R].view(R, 3)
+    sem = flat[10 * R:].view(R, C)
     ws = torch.empty(S, dtype=_F32, device=dev)
     check(lib.ngp_composite_train_fw(ptr(_f32(sigmas, "sigmas")), ptr(rgbs), ptr(normals_pred), ptr(sems), ptr(deltas),
                                      ptr(ts), ptr(rays_a), float(T_threshold), C, S, R, ptr(total), ptr(opacity),

@@ -498,3 +498,16 @@ def test_raymarching_test_culling_is_bit_exact(vren, vref, kind):
             assert (N(vneff) == N(neff)).all() and (bits(N(vts)) == bits(N(ts))).all() and (bits(N(ht_v)) == bits(N(ht))).all()
         total += int(oneff.sum())
     assert (total == 0) == (kind == "empty")
+
+
+def test_near_clamp_kernel_equals_the_reference_index_put():
+    """ngp_near_clamp (rendering.py:29-30): hits_t[(t1 >= 0) & (t1 < NEAR), 0, 0] = NEAR — incl. misses (-1), exact 0, exact NEAR and -0.0."""
+    from ngp_b200._lib import lib, ptr, check, stream
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 100003
+    ht = torch.rand(n, 1, 2, device="cuda", generator=g) * 0.03 - 0.005
+    ht[:10, 0, 0] = -1.0; ht[10:20, 0, 0] = 0.0; ht[20:30, 0, 0] = 0.01; ht[30:40, 0, 0] = -0.0
+    want = ht.clone()
+    want[(want[:, 0, 0] >= 0) & (want[:, 0, 0] < 0.01), 0, 0] = 0.01
+    check(lib.ngp_near_clamp(ptr(ht), n, ht.stride(0), 0.01, stream()), "near_clamp")
+    assert torch.equal(ht, want)
