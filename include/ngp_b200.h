@@ -128,6 +128,12 @@ int ngp_render_advance_full(const float* rays_o, const float* rays_d, float* hit
  * reads the counters back late.  One trip of the loop of models/rendering.py:75-124 without a host round trip.
  * counters: 2 x int32 of THIS round = [alive slots after it, samples marched in it].  feat_tiles: workspace of
  * ceil(cap/128) * ngp_feature_tile_bytes bytes; h (cap,16), sigmas (cap), rgbs (cap,3). */
+/* the field part of such a round alone (hash grid -> tiles -> both MLPs, live count from device memory n_dev): enqueued right behind
+ * ngp_render_emit so that the host can fetch the round's counters while it runs (rendering.render_wavefront_pipelined) */
+int ngp_field_compact_fw(const float* xyzs, const float* dirs, int64_t cap, const int32_t* n_dev, const float* aabb, const void* table,
+                         int table_dtype, int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                         float per_level_scale, const float* sigma_params, const float* rgb_params, int width, int rgb_hidden,
+                         void* feat_tiles, float* h, float* sigmas, float* rgbs, void* stream);
 int ngp_render_round_compact(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_in,
                              int64_t n_alive_bound, const int32_t* n_alive_dev, const int64_t* prev_rays_a,
                              const float* prev_sigmas, const float* prev_rgbs, const float* prev_deltas, const float* prev_ts,

@@ -889,3 +889,29 @@ NGP_API int ngp_render_round_compact(const float* rays_o, const float* rays_d, f
   }
   return rc;
 }
+
+// The field part of a round on its own: hash grid -> bf16 tiles -> density net (sigma = exp(h0)) -> colour net on the `cap` sample
+// slots of the packed buffers, every launch taking the live count from DEVICE memory (n_dev: the round's counters[1]).  Lets the
+// host enqueue the field of round k right behind its emit pass and read the round's two counters (from a side stream) WHILE the
+// field runs: the next round is then sized by exact counts and the GPU never waits for the host (rendering.render_wavefront_pipelined).
+NGP_API int ngp_field_compact_fw(const float* xyzs, const float* dirs, int64_t cap, const int32_t* n_dev, const float* aabb, const void* table,
+                                 int table_dtype, int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                                 float per_level_scale, const float* sigma_params, const float* rgb_params, int width, int rgb_hidden,
+                                 void* feat_tiles, float* h, float* sigmas, float* rgbs, void* stream) {
+  if (cap <= 0) return 0;
+  const int LF = n_levels * n_features;
+  int rc = hashgrid_fw_tiles_launch(xyzs, aabb, table, table_dtype, n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale,
+                                    cap, n_dev, feat_tiles, stream);
+  if (rc) return rc;
+  {
+    const float* sp[1] = {reinterpret_cast<const float*>(feat_tiles)};
+    const int sw[1] = {LF}, sk[1] = {2};
+    const int64_t ss[1] = {0};
+    rc = mlp_fw_launch(1, sp, sw, sk, ss, sigma_params, width, 1, 16, /*ReLU*/ 1, /*None*/ 0, cap, n_dev, h, 16, sigmas, stream);
+    if (rc) return rc;
+  }
+  const float* sp[2] = {dirs, h};
+  const int sw[2] = {16, 16}, sk[2] = {1, 0};
+  const int64_t ss[2] = {3, 16};
+  return mlp_fw_launch(2, sp, sw, sk, ss, rgb_params, width, rgb_hidden, 3, /*ReLU*/ 1, /*Sigmoid*/ 2, cap, n_dev, rgbs, 3, nullptr, stream);
+}

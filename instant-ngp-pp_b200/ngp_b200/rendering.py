@@ -249,6 +249,80 @@ def render_wavefront_compact(model, rays_o, rays_d, hits_t, opacity, depth, rgb,
     return int(counters[:R, 1].sum())
 
 
+_PIPE = {}          # per device: (copy stream, pinned counter buffer)
+
+
+@torch.no_grad()
+def render_wavefront_pipelined(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs):
+    """render_wavefront for the ngp_pl-shaped field with the host read-back taken off the critical path: a round's field evaluation
+    (ngp_field_compact_fw: hash grid + both MLPs, live sample count read from device memory) is enqueued right behind its emit pass,
+    and the round's two counters travel to the host on a side stream WHILE the field runs — so every round is still sized by EXACT
+    counts (unlike the bound-sized render_wavefront_compact) but the GPU no longer idles between emit and field while the host waits,
+    allocates and launches.  Same kernels on the same samples as render_wavefront: bit-identical images."""
+    from . import _lib, tcnn
+    from ._lib import lib, ptr, check, stream
+    _lib.require_device()
+    N_rays, dev = len(rays_o), rays_o.device
+    esf = float(kwargs.get("exp_step_factor", 0.))
+    T_thr = float(kwargs.get("T_threshold", 1e-4))
+    sched = _round_schedule(int(kwargs.get("max_samples", MAX_SAMPLES)))
+    geo = (model.cascades, float(model.scale), esf, model.grid_size, MAX_SAMPLES)
+    enc, snet, cnet = model.xyz_encoder, model.sigma_net, model.rgb_net
+    g = enc.grid
+    tile_bytes = int(lib.ngp_feature_tile_bytes(g.n_levels, g.n_features))
+    table, sp, cp = enc.params.detach(), snet.params.detach(), cnet.params.detach()
+    field = (tcnn._aabb_arg(model.aabb()), ptr(table), 0, *g.args(), ptr(sp), ptr(cp), snet.mlp.width, cnet.mlp.n_hidden)
+    bitfield = ptr(model.density_bitfield)
+    R = len(sched)
+    if dev not in _PIPE:
+        _PIPE[dev] = (torch.cuda.Stream(device=dev), torch.zeros(64, 2, dtype=torch.int32).pin_memory())
+    copy_stream, host = _PIPE[dev]
+    counters = torch.zeros(R + 1, 2, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib.ngp_render_workspace_bytes(N_rays)), dtype=torch.uint8, device=dev)
+    alive_bufs = [torch.empty(N_rays, dtype=torch.int64, device=dev) for _ in range(2)]
+    main = torch.cuda.current_stream()
+    st = stream()
+    cbase = counters.data_ptr()
+    alive_in, n_alive, prev = None, N_rays, (None,) * 5
+    total, last = 0, -1
+    none3 = (None, None, None)
+    for k, n_next in enumerate(sched):
+        cap = n_alive * n_next
+        alive_out = alive_bufs[k & 1]
+        rays_a = torch.empty(n_alive, 3, dtype=torch.int64, device=dev)
+        xyzs = torch.empty(cap, 3, device=dev); dirs = torch.empty(cap, 3, device=dev)
+        deltas = torch.empty(cap, device=dev); ts = torch.empty(cap, device=dev)
+        tiles = torch.empty((cap + 127) // 128 * tile_bytes, dtype=torch.uint8, device=dev)
+        h = torch.empty(cap, 16, device=dev); sig = torch.empty(cap, device=dev); col = torch.empty(cap, 3, device=dev)
+        check(lib.ngp_render_advance_full(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(prev[0]), ptr(prev[1]),
+                                          ptr(prev[2]), ptr(prev[3]), ptr(prev[4]), T_thr, bitfield, *geo, n_next,
+                                          ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_out), cbase + 8 * k, ptr(ws),
+                                          *none3, 0, *none3, st), "render_advance")
+        check(lib.ngp_render_emit(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_out), n_alive, bitfield, *geo, ptr(ws), cap,
+                                  ptr(rays_a), ptr(xyzs), ptr(dirs), ptr(deltas), ptr(ts), cbase + 8 * k, st), "render_emit")
+        ev = torch.cuda.Event(); ev.record(main)
+        check(lib.ngp_field_compact_fw(ptr(xyzs), ptr(dirs), cap, cbase + 8 * k + 4, *field, ptr(tiles), ptr(h), ptr(sig), ptr(col), st),
+              "field_compact_fw")
+        with torch.cuda.stream(copy_stream):               # the counters leave as soon as the emit pass is done, the field keeps the GPU busy
+            copy_stream.wait_event(ev)
+            host[k % 64].copy_(counters[k], non_blocking=True)
+            done = torch.cuda.Event(); done.record(copy_stream)
+        done.synchronize()
+        n_alive_out, n_pts = int(host[k % 64, 0]), int(host[k % 64, 1])
+        total += n_pts
+        prev, alive_in, last = (rays_a, sig, col, deltas, ts), alive_out, k
+        n_alive = n_alive_out
+        if n_alive_out == 0 or n_pts == 0:
+            break
+    if last >= 0 and n_alive > 0:        # composite the last marched round (n_next = 0: no march)
+        check(lib.ngp_render_advance_full(ptr(rays_o), ptr(rays_d), ptr(hits_t), ptr(alive_in), n_alive, ptr(prev[0]), ptr(prev[1]),
+                                          ptr(prev[2]), ptr(prev[3]), ptr(prev[4]), T_thr, bitfield, *geo, 0,
+                                          ptr(opacity), ptr(depth), ptr(rgb), ptr(alive_bufs[(last + 1) & 1]), cbase + 8 * R, ptr(ws),
+                                          *none3, 0, *none3, st), "render_advance")
+    main.wait_stream(copy_stream)
+    return total
+
+
 @torch.no_grad()
 def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     """rendering.py:135-190."""
@@ -272,7 +346,13 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
             compact = (kwargs.get("device_loop", False) and getattr(model, "fused_density", False) and hasattr(model, "sigma_net")
                        and model.xyz_encoder.params.dtype == torch.float32 and model.sigma_net.mlp.n_hidden == 1 and model.sigma_net.mlp.n_out == 16
                        and model.rgb_net.mlp.n_out == 3 and model.rgb_net.mlp.width == model.sigma_net.mlp.width)
-            fn = render_wavefront_compact if compact else render_wavefront
+            fused_field = (getattr(model, "fused_density", False) and hasattr(model, "sigma_net")
+                           and model.xyz_encoder.params.dtype == torch.float32 and model.sigma_net.mlp.n_hidden == 1 and model.sigma_net.mlp.n_out == 16
+                           and model.rgb_net.mlp.n_out == 3 and model.rgb_net.mlp.width == model.sigma_net.mlp.width)
+            # pipelined rounds pay for bound-sized field launches (grids for n_alive * n_next slots, most of them empty): measured
+            # (profiles/r02d_render_probe.txt) +8 % on a 259 k-ray tile, -5 % at 2 M rays, -30 % at 8 M rays -> small batches only
+            pipelined = fused_field and kwargs.get("pipelined", N_rays <= 600_000) and not compact
+            fn = render_wavefront_compact if compact else (render_wavefront_pipelined if pipelined else render_wavefront)
             total = fn(model, rays_o, rays_d, hits_t, opacity, depth, rgb, **kwargs)
             normal_pred = normal_raw = torch.zeros(N_rays, 3, device=device)
             semantic = torch.zeros(N_rays, 1, dtype=torch.long, device=device)

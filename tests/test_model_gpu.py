@@ -162,6 +162,10 @@ def test_geometric_schedule_renders_the_same_image_as_the_reference_schedule():
         e = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2)
         e2 = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, device_loop=True)
         assert torch.equal(e["rgb"], e2["rgb"]) and int(e["total_samples"]) == int(e2["total_samples"])
+        # default = pipelined rounds (field enqueued behind emit, counters fetched on a side stream); pipelined=False = plain host-driven rounds
+        e3 = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, pipelined=False)
+        assert torch.equal(e["rgb"], e3["rgb"]) and torch.equal(e["depth"], e3["depth"]) and torch.equal(e["opacity"], e3["opacity"])
+        assert int(e["total_samples"]) == int(e3["total_samples"])
         f = render(m, big_o, big_d, exp_step_factor=0.0, num_classes=0, test_time=True, T_threshold=1e-2, sample_schedule="geometric", renderer="loop")
     assert torch.allclose(e["rgb"], f["rgb"], atol=2e-5) and torch.allclose(e["opacity"], f["opacity"], atol=2e-5)
     assert int(e["total_samples"]) > 0

@@ -35,8 +35,9 @@ def frame_rays(i):
     return scene.rays_from_pixels(poses[i % poses.shape[0]][None], torch.zeros(n, dtype=torch.long, device=dev), u, v)
 
 
-variants = {"wavefront, device-resident rounds": dict(renderer="wavefront", device_loop=True, sample_schedule="geometric"),
-            "wavefront, host-driven rounds": dict(renderer="wavefront", device_loop=False, sample_schedule="geometric"),
+variants = {"wavefront, pipelined rounds (default)": dict(renderer="wavefront", sample_schedule="geometric"),
+            "wavefront, device-resident rounds": dict(renderer="wavefront", device_loop=True, sample_schedule="geometric"),
+            "wavefront, host-driven rounds": dict(renderer="wavefront", pipelined=False, sample_schedule="geometric"),
             "reference-style loop, reference schedule": dict(renderer="loop", sample_schedule="reference")}
 with torch.no_grad():
     for name, kw in variants.items():
