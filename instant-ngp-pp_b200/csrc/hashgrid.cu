@@ -55,7 +55,10 @@ struct GridMeta {
 };
 __device__ __forceinline__ void block_coords(const GridMeta& m, int n_chunks, uint32_t& sblock, int& chunk) {
   if (m.chunk_major) { chunk = (int)(blockIdx.x / m.n_sblocks); sblock = blockIdx.x % m.n_sblocks; }
-  else { sblock = blockIdx.x / n_chunks; chunk = (int)(blockIdx.x % n_chunks); }
+  else if ((n_chunks & (n_chunks - 1)) == 0) {                 // 16 levels in chunks of 2 / 4 / 8: shift and mask instead of the
+    const int sh = __ffs(n_chunks) - 1;                         // integer division (11 % of the gather's stall samples sat on it)
+    sblock = blockIdx.x >> sh; chunk = (int)(blockIdx.x & (uint32_t)(n_chunks - 1));
+  } else { sblock = blockIdx.x / n_chunks; chunk = (int)(blockIdx.x % n_chunks); }
 }
 __device__ __forceinline__ void to_unit(const GridMeta& m, float& x, float& y, float& z) {
   if (m.affine == 2) {            // every range is a power of two: the multiplication by 1/range is exact, same bits as the division
