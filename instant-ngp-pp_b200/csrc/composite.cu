@@ -17,46 +17,79 @@
 namespace ngp {
 
 constexpr int kCP = 16;  // semantic classes handled per pass (register accumulators)
+constexpr int kFwDepth = 4, kBwDepth = 2;   // chunks of G samples whose inputs are in flight together (forward / backward compositor)
 
 // ------------------------------------------------------------------------------------------ fw
 // do_main: also produce opacity/depth/rgb/normal_pred/ws/total_samples (first class chunk only).
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ normals,
     const float* __restrict__ sems, const float* __restrict__ deltas, const float* __restrict__ ts,
     const int64_t* __restrict__ rays_a, float T_thr, int classes, int c0, int nc, bool do_main, int64_t n_rays,
     int64_t* __restrict__ total_samples, float* __restrict__ opacity, float* __restrict__ depth,
     float* __restrict__ rgb, float* __restrict__ normal_pred, float* __restrict__ sem, float* __restrict__ ws) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+  if (G == 32 && sg.n <= 0) {          // the warp's one ray is empty (most rays of a batch are): zeros, no reductions
+    if (j == 0 && sg.ray >= 0) {
+      const int64_t r = sg.ray;
+      if (do_main) {
+        total_samples[r] = 0;
+        opacity[r] = 0.f; depth[r] = 0.f;
+        rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
+        if (normal_pred) { normal_pred[3 * r] = 0.f; normal_pred[3 * r + 1] = 0.f; normal_pred[3 * r + 2] = 0.f; }
+      }
+      for (int i = 0; i < nc; i++) sem[r * classes + c0 + i] = 0.f;
+    }
+    return;
+  }
 
   float aO = 0.f, aD = 0.f, aR = 0.f, aG = 0.f, aB = 0.f, aNx = 0.f, aNy = 0.f, aNz = 0.f;
   float aS[kCP];
 #pragma unroll
   for (int i = 0; i < kCP; i++) aS[i] = 0.f;
 
+  // kFwDepth chunks of G samples per trip: every input of the trip is requested before the first scan, so a ray of up to
+  // kFwDepth * G samples (the mean non-empty ray of a Lego-shaped batch has 127) pays ONE memory round trip, not one (or, with
+  // the weights' consumers loading where they are used, two) per chunk — the kernel is a chain of dependent round trips per ray,
+  // far from the HBM rate (tools/composite_sweep.py).  A ray that has already terminated requests nothing: its remaining samples
+  // only get ws = 0.
   TState st;
-  for (int base = 0; warp_any(base < sg.n); base += G) {
-    const bool valid = base + j < sg.n;
-    const int64_t s = sg.start + base + j;
-    float a = 0.f;
-    if (valid) a = sample_alpha(__ldg(sigmas + s), __ldg(deltas + s));
-    float Tb, Ta; bool active;
-    chunk_transmittance<G>(st, a, valid, j, base, T_thr, Tb, Ta, active);
-    const float w = active ? a * Tb : 0.f;
-    if (valid && do_main) ws[s] = w;
-    if (active) {
-      if (do_main) {
-        aO += w;
-        aD = fmaf(w, __ldg(ts + s), aD);
-        aR = fmaf(w, __ldg(rgbs + 3 * s), aR); aG = fmaf(w, __ldg(rgbs + 3 * s + 1), aG); aB = fmaf(w, __ldg(rgbs + 3 * s + 2), aB);
-        if (normals) { aNx = fmaf(w, __ldg(normals + 3 * s), aNx); aNy = fmaf(w, __ldg(normals + 3 * s + 1), aNy); aNz = fmaf(w, __ldg(normals + 3 * s + 2), aNz); }
-      }
-      const float* sp = sems + s * classes + c0;
+  for (int base = 0; warp_any(base < sg.n); base += kFwDepth * G) {
+    float a[kFwDepth], t[kFwDepth], c_r[kFwDepth], c_g[kFwDepth], c_b[kFwDepth];
 #pragma unroll
-      for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = fmaf(w, __ldg(sp + i), aS[i]);
+    for (int m = 0; m < kFwDepth; m++) {
+      const int k = base + m * G + j;
+      a[m] = 0.f; t[m] = 0.f; c_r[m] = 0.f; c_g[m] = 0.f; c_b[m] = 0.f;
+      if (k < sg.n && !st.done) {
+        const int64_t s = sg.start + k;
+        const float sig = __ldg(sigmas + s), dl = __ldg(deltas + s);
+        if (do_main) { t[m] = __ldg(ts + s); c_r[m] = __ldg(rgbs + 3 * s); c_g[m] = __ldg(rgbs + 3 * s + 1); c_b[m] = __ldg(rgbs + 3 * s + 2); }
+        a[m] = sample_alpha(sig, dl);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < kFwDepth; m++) {
+      const int cb = base + m * G;
+      if (m > 0 && !warp_any(cb < sg.n)) break;
+      const bool valid = cb + j < sg.n;
+      const int64_t s = sg.start + cb + j;
+      float n_x = 0.f, n_y = 0.f, n_z = 0.f;
+      if (normals && do_main && valid && !st.done) { n_x = __ldg(normals + 3 * s); n_y = __ldg(normals + 3 * s + 1); n_z = __ldg(normals + 3 * s + 2); }
+      float Tb, Ta; bool active;
+      chunk_transmittance<G>(st, a[m], valid, j, cb, T_thr, Tb, Ta, active);
+      const float w = active ? a[m] * Tb : 0.f;
+      if (valid && do_main) ws[s] = w;
+      if (active) {
+        if (do_main) {
+          aO += w;
+          aD = fmaf(w, t[m], aD);
+          aR = fmaf(w, c_r[m], aR); aG = fmaf(w, c_g[m], aG); aB = fmaf(w, c_b[m], aB);
+          if (normals) { aNx = fmaf(w, n_x, aNx); aNy = fmaf(w, n_y, aNy); aNz = fmaf(w, n_z, aNz); }
+        }
+        const float* sp = sems + s * classes + c0;
+#pragma unroll
+        for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = fmaf(w, __ldg(sp + i), aS[i]);
+      }
     }
   }
   if (!st.done) st.n_done = sg.n;
@@ -80,16 +113,14 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
 #pragma unroll
     for (int i = 0; i < kCP; i++) if (i < nc) sem[r * classes + c0 + i] = aS[i];
   }
+  });
 }
 
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) composite_alpha_fw_kernel(
     const float* __restrict__ sigmas, const float* __restrict__ deltas, const int64_t* __restrict__ rays_a,
     float T_thr, int64_t n_rays, float* __restrict__ alphas, float* __restrict__ ws) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
   TState st;
   for (int base = 0; warp_any(base < sg.n); base += G) {
     const bool valid = base + j < sg.n;
@@ -100,11 +131,12 @@ __global__ void __launch_bounds__(256) composite_alpha_fw_kernel(
     chunk_transmittance<G>(st, a, valid, j, base, T_thr, Tb, Ta, active);
     if (valid) { alphas[s] = active ? a : 0.f; ws[s] = active ? a * Tb : 0.f; }
   }
+  });
 }
 
 // ------------------------------------------------------------------------------------------ bw
 // volumerendering.cu:212-245.  dsigma has NO normal / semantic terms (reference behaviour).
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) composite_train_bw_kernel(
     const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_drgb,
     const float* __restrict__ dL_dnormal, const float* __restrict__ dL_dsem, const float* __restrict__ dL_dws,
@@ -113,10 +145,8 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
     const float* __restrict__ opacity, const float* __restrict__ depth, const float* __restrict__ rgb,
     float T_thr, int classes, int64_t n_rays, float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs,
     float* __restrict__ dL_dnormals, float* __restrict__ dL_dsems) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+  if (G == 32 && sg.n <= 0) return;          // nothing to write for an empty ray
   const int64_t r = sg.ray < 0 ? 0 : sg.ray;
 
   float gO = 0.f, gD = 0.f, gR = 0.f, gG = 0.f, gB = 0.f, gNx = 0.f, gNy = 0.f, gNz = 0.f;
@@ -130,51 +160,65 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
   }
   // pass A: sum over the whole segment of dL_dws*ws (volumerendering.cu:206-210, 277)
   float wsum = 0.f;
-  for (int base = 0; warp_any(base < sg.n); base += G) {
-    const int64_t s = sg.start + base + j;
-    if (dL_dws && base + j < sg.n) wsum = fmaf(__ldg(dL_dws + s), __ldg(ws_saved + s), wsum);
+  if (dL_dws) {                                   // plain strided loop (no shuffles inside): the compiler batches its loads
+#pragma unroll 4
+    for (int k = j; k < sg.n; k += G) wsum = fmaf(__ldg(dL_dws + sg.start + k), __ldg(ws_saved + sg.start + k), wsum);
   }
   wsum = group_sum<G>(wsum);
 
-  // pass B
+  // pass B (kBwDepth chunks per trip, see the forward kernel)
   TState st;
   float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f, cw = 0.f;  // running sums entering the chunk
-  for (int base = 0; warp_any(base < sg.n); base += G) {
-    const bool valid = base + j < sg.n;
-    const int64_t s = sg.start + base + j;
-    float a = 0.f, dl = 0.f, t = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, gw = 0.f, wsv = 0.f;
-    if (valid) {
-      dl = __ldg(deltas + s);
-      a = sample_alpha(__ldg(sigmas + s), dl);
-      t = __ldg(ts + s);
-      c0 = __ldg(rgbs + 3 * s); c1 = __ldg(rgbs + 3 * s + 1); c2 = __ldg(rgbs + 3 * s + 2);
-      if (dL_dws) { gw = __ldg(dL_dws + s); wsv = __ldg(ws_saved + s); }
-    }
-    float Tb, Ta; bool active;
-    chunk_transmittance<G>(st, a, valid, j, base, T_thr, Tb, Ta, active);
-    const float w = active ? a * Tb : 0.f;
-    // inclusive running sums (r,g,b,d of the reference and the scanned dL_dws*ws)
-    const float pr = cr + group_incl_sum<G>(w * c0, j);
-    const float pg = cg + group_incl_sum<G>(w * c1, j);
-    const float pb = cb + group_incl_sum<G>(w * c2, j);
-    const float pd = cd + group_incl_sum<G>(w * t, j);
-    const float pw = cw + group_incl_sum<G>(gw * wsv, j);
-    cr = group_bcast<G>(pr, G - 1); cg = group_bcast<G>(pg, G - 1); cb = group_bcast<G>(pb, G - 1);
-    cd = group_bcast<G>(pd, G - 1); cw = group_bcast<G>(pw, G - 1);
-    if (valid) {
-      float ds = 0.f;
-      if (active) {
-        ds = dl * (gR * (c0 * Ta - (R - pr)) + gG * (c1 * Ta - (Gc - pg)) + gB * (c2 * Ta - (B - pb)) +
-                   gO * (1.0f - O) + gD * (t * Ta - (D - pd)) + Ta * gw - (wsum - pw));
+  for (int base = 0; warp_any(base < sg.n); base += kBwDepth * G) {
+    float a_[kBwDepth], dl_[kBwDepth], t_[kBwDepth], c0_[kBwDepth], c1_[kBwDepth], c2_[kBwDepth], gw_[kBwDepth], wsv_[kBwDepth];
+#pragma unroll
+    for (int m = 0; m < kBwDepth; m++) {
+      const int k = base + m * G + j;
+      a_[m] = 0.f; dl_[m] = 0.f; t_[m] = 0.f; c0_[m] = 0.f; c1_[m] = 0.f; c2_[m] = 0.f; gw_[m] = 0.f; wsv_[m] = 0.f;
+      if (k < sg.n && !st.done) {                 // behind the terminating sample every gradient is 0 (w = 0, ws = 0): nothing to read
+        const int64_t s = sg.start + k;
+        dl_[m] = __ldg(deltas + s);
+        const float sig = __ldg(sigmas + s);
+        t_[m] = __ldg(ts + s);
+        c0_[m] = __ldg(rgbs + 3 * s); c1_[m] = __ldg(rgbs + 3 * s + 1); c2_[m] = __ldg(rgbs + 3 * s + 2);
+        if (dL_dws) { gw_[m] = __ldg(dL_dws + s); wsv_[m] = __ldg(ws_saved + s); }
+        a_[m] = sample_alpha(sig, dl_[m]);
       }
-      dL_dsigmas[s] = ds;
-      dL_drgbs[3 * s] = gR * w; dL_drgbs[3 * s + 1] = gG * w; dL_drgbs[3 * s + 2] = gB * w;
-      if (dL_dnormals) { dL_dnormals[3 * s] = gNx * w; dL_dnormals[3 * s + 1] = gNy * w; dL_dnormals[3 * s + 2] = gNz * w; }
-      float* dsp = dL_dsems + s * classes;
-      const float* gsp = dL_dsem + r * classes;
-      for (int i = 0; i < classes; i++) dsp[i] = __ldg(gsp + i) * w;
+    }
+#pragma unroll
+    for (int m = 0; m < kBwDepth; m++) {
+      const int cbase = base + m * G;
+      if (m > 0 && !warp_any(cbase < sg.n)) break;
+      const bool valid = cbase + j < sg.n;
+      const int64_t s = sg.start + cbase + j;
+      const float a = a_[m], dl = dl_[m], t = t_[m], c0 = c0_[m], c1 = c1_[m], c2 = c2_[m], gw = gw_[m], wsv = wsv_[m];
+      float Tb, Ta; bool active;
+      chunk_transmittance<G>(st, a, valid, j, cbase, T_thr, Tb, Ta, active);
+      const float w = active ? a * Tb : 0.f;
+      // inclusive running sums (r,g,b,d of the reference and the scanned dL_dws*ws)
+      const float pr = cr + group_incl_sum<G>(w * c0, j);
+      const float pg = cg + group_incl_sum<G>(w * c1, j);
+      const float pb = cb + group_incl_sum<G>(w * c2, j);
+      const float pd = cd + group_incl_sum<G>(w * t, j);
+      const float pw = cw + group_incl_sum<G>(gw * wsv, j);
+      cr = group_bcast<G>(pr, G - 1); cg = group_bcast<G>(pg, G - 1); cb = group_bcast<G>(pb, G - 1);
+      cd = group_bcast<G>(pd, G - 1); cw = group_bcast<G>(pw, G - 1);
+      if (valid) {
+        float ds = 0.f;
+        if (active) {
+          ds = dl * (gR * (c0 * Ta - (R - pr)) + gG * (c1 * Ta - (Gc - pg)) + gB * (c2 * Ta - (B - pb)) +
+                     gO * (1.0f - O) + gD * (t * Ta - (D - pd)) + Ta * gw - (wsum - pw));
+        }
+        dL_dsigmas[s] = ds;
+        dL_drgbs[3 * s] = gR * w; dL_drgbs[3 * s + 1] = gG * w; dL_drgbs[3 * s + 2] = gB * w;
+        if (dL_dnormals) { dL_dnormals[3 * s] = gNx * w; dL_dnormals[3 * s + 1] = gNy * w; dL_dnormals[3 * s + 2] = gNz * w; }
+        float* dsp = dL_dsems + s * classes;
+        const float* gsp = dL_dsem + r * classes;
+        for (int i = 0; i < classes; i++) dsp[i] = __ldg(gsp + i) * w;
+      }
     }
   }
+  });
 }
 
 // ------------------------------------------------------------------------------------------ test
@@ -260,6 +304,18 @@ int pick_group(int64_t n_samples, int64_t n_rays) {
   return 4;
 }
 
+// Launch shape of the group kernels (compositors, distortion / Ref-NeRF losses).  With G == 32 a warp walks kRayTile rays
+// (scan.cuh for_each_ray); NGP_COMPOSITE_TILED=0 goes back to one warp per ray, NGP_COMPOSITE_BLOCK (32..256) sets the CTA size
+// (tuning only; with one warp per ray a CTA's warp slots come free only when its longest ray is done, so small CTAs won there).
+bool group_tiled() {
+  if (const char* e = getenv("NGP_COMPOSITE_TILED")) return atoi(e) != 0;
+  return true;
+}
+int group_block() {
+  if (const char* e = getenv("NGP_COMPOSITE_BLOCK")) { const int b = atoi(e); if (b == 32 || b == 64 || b == 128 || b == 256) return b; }
+  return group_tiled() ? 128 : 64;
+}
+
 }  // namespace ngp
 
 using namespace ngp;
@@ -288,8 +344,7 @@ NGP_API int ngp_composite_train_fw(const float* sigmas, const float* rgbs, const
     const int nc = classes - c0 < kCP ? (classes - c0 < 0 ? 0 : classes - c0) : kCP;
     const bool do_main = c0 == 0;
     NGP_GROUP_DISPATCH(Gsel, {
-      const int64_t blocks = ceil_div(n_rays * G, 256);
-      composite_train_fw_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(
+      NGP_GROUP_LAUNCH(composite_train_fw_kernel, st,
           sigmas, rgbs, normals_pred, sems, deltas, ts, rays_a, T_threshold, classes, c0, nc, do_main, n_rays,
           total_samples, opacity, depth, rgb, normal_pred, sem, ws);
     });
@@ -305,9 +360,7 @@ NGP_API int ngp_composite_alpha_fw(const float* sigmas, const float* deltas, con
   if (n_rays <= 0) return 0;
   const int Gsel = pick_group(n_samples, n_rays);
   NGP_GROUP_DISPATCH(Gsel, {
-    const int64_t blocks = ceil_div(n_rays * G, 256);
-    composite_alpha_fw_kernel<G><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sigmas, deltas, rays_a, T_threshold,
-                                                                                      n_rays, alphas, ws);
+    NGP_GROUP_LAUNCH(composite_alpha_fw_kernel, (cudaStream_t)stream, sigmas, deltas, rays_a, T_threshold, n_rays, alphas, ws);
   });
   NGP_LAUNCH_CHECK("ngp_composite_alpha_fw");
   return 0;
@@ -326,8 +379,7 @@ NGP_API int ngp_composite_train_bw(const float* dL_dopacity, const float* dL_dde
   if (n_rays <= 0) return 0;
   const int Gsel = pick_group(n_samples, n_rays);
   NGP_GROUP_DISPATCH(Gsel, {
-    const int64_t blocks = ceil_div(n_rays * G, 256);
-    composite_train_bw_kernel<G><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    NGP_GROUP_LAUNCH(composite_train_bw_kernel, (cudaStream_t)stream,
         dL_dopacity, dL_ddepth, dL_drgb, dL_dnormal_pred, dL_dsem, dL_dws, sigmas, rgbs, ws, deltas, ts, rays_a,
         opacity, depth, rgb, T_threshold, classes, n_rays, dL_dsigmas, dL_drgbs, dL_dnormals_pred, dL_dsems);
   });

@@ -13,52 +13,60 @@ namespace ngp {
 
 int pick_group(int64_t n_samples, int64_t n_rays);  // composite.cu
 
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) distortion_fw_kernel(
     const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
     const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ loss, float* __restrict__ ws_incl,
     float* __restrict__ wts_incl) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
   float cw = 0.f, cwt = 0.f, acc = 0.f;
-  for (int base = 0; warp_any(base < sg.n); base += G) {
-    const bool valid = base + j < sg.n;
-    const int64_t s = sg.start + base + j;
-    float w = 0.f, t = 0.f, dl = 0.f;
-    if (valid) { w = __ldg(ws + s); t = __ldg(ts + s); dl = __ldg(deltas + s); }
-    const float wt = w * t;
-    const float iw = cw + group_incl_sum<G>(w, j);
-    const float iwt = cwt + group_incl_sum<G>(wt, j);
-    float ew = __shfl_up_sync(kFull, iw, 1, G), ewt = __shfl_up_sync(kFull, iwt, 1, G);
-    if (j == 0) { ew = cw; ewt = cwt; }
-    cw = group_bcast<G>(iw, G - 1); cwt = group_bcast<G>(iwt, G - 1);
-    if (valid) {
-      ws_incl[s] = iw; wts_incl[s] = iwt;
-      // losses.cu:92-93: 2*(wts_incl*ws_excl - ws_incl*wts_excl) + 1.0f/3*ws*ws*deltas
-      acc += 2.0f * (iwt * ew - iw * ewt) + (1.0f / 3) * w * w * dl;
+  constexpr int kDepth = 4;                       // chunks whose inputs are in flight together (see composite_train_fw_kernel)
+  for (int base = 0; warp_any(base < sg.n); base += kDepth * G) {
+    float w_[kDepth], t_[kDepth], dl_[kDepth];
+#pragma unroll
+    for (int m = 0; m < kDepth; m++) {
+      const int k = base + m * G + j;
+      w_[m] = 0.f; t_[m] = 0.f; dl_[m] = 0.f;
+      if (k < sg.n) { const int64_t s = sg.start + k; w_[m] = __ldg(ws + s); t_[m] = __ldg(ts + s); dl_[m] = __ldg(deltas + s); }
+    }
+#pragma unroll
+    for (int m = 0; m < kDepth; m++) {
+      const int cbase = base + m * G;
+      if (m > 0 && !warp_any(cbase < sg.n)) break;
+      const bool valid = cbase + j < sg.n;
+      const int64_t s = sg.start + cbase + j;
+      const float w = w_[m], t = t_[m], dl = dl_[m];
+      const float wt = w * t;
+      const float iw = cw + group_incl_sum<G>(w, j);
+      const float iwt = cwt + group_incl_sum<G>(wt, j);
+      float ew = __shfl_up_sync(kFull, iw, 1, G), ewt = __shfl_up_sync(kFull, iwt, 1, G);
+      if (j == 0) { ew = cw; ewt = cwt; }
+      cw = group_bcast<G>(iw, G - 1); cwt = group_bcast<G>(iwt, G - 1);
+      if (valid) {
+        ws_incl[s] = iw; wts_incl[s] = iwt;
+        // losses.cu:92-93: 2*(wts_incl*ws_excl - ws_incl*wts_excl) + 1.0f/3*ws*ws*deltas
+        acc += 2.0f * (iwt * ew - iw * ewt) + (1.0f / 3) * w * w * dl;
+      }
     }
   }
   acc = group_sum<G>(acc);
   if (j == 0 && sg.ray >= 0) loss[sg.ray] = acc;
+  });
 }
 
 // losses.cu:110-140
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) distortion_bw_kernel(
     const float* __restrict__ dL_dloss, const float* __restrict__ ws_incl, const float* __restrict__ wts_incl,
     const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
     const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ dL_dws) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
   if (sg.n <= 0) return;
   const int64_t end = sg.start + sg.n - 1;
   const float ws_sum = __ldg(ws_incl + end), wts_sum = __ldg(wts_incl + end);
   const float g = __ldg(dL_dloss + sg.ray);
   const float g23 = g * 2.0f / 3;  // losses.cu:138 parses as ((dL_dloss*2)/3)*ws*deltas
+#pragma unroll 4
   for (int k = j; k < sg.n; k += G) {
     const int64_t s = sg.start + k;
     const float t = __ldg(ts + s), iw = __ldg(ws_incl + s), iwt = __ldg(wts_incl + s);
@@ -67,18 +75,16 @@ __global__ void __launch_bounds__(256) distortion_bw_kernel(
     v += g23 * __ldg(ws + s) * __ldg(deltas + s);
     dL_dws[s] = v;
   }
+  });
 }
 
 // ref_loss.cu:4-38
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) refloss_fw_kernel(
     const float* __restrict__ sigmas, const float* __restrict__ ndiff, const float* __restrict__ nori,
     const float* __restrict__ deltas, const int64_t* __restrict__ rays_a, float T_thr, int64_t n_rays,
     float* __restrict__ loss_o, float* __restrict__ loss_p) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
   float ax = 0.f, ay = 0.f, az = 0.f, ao = 0.f;
   TState st;
   for (int base = 0; warp_any(base < sg.n); base += G) {
@@ -99,20 +105,18 @@ __global__ void __launch_bounds__(256) refloss_fw_kernel(
     loss_o[sg.ray] = ao;
     loss_p[3 * sg.ray] = ax; loss_p[3 * sg.ray + 1] = ay; loss_p[3 * sg.ray + 2] = az;
   }
+  });
 }
 
 // ref_loss.cu:76-130
-template <int G>
+template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) refloss_bw_kernel(
     const float* __restrict__ dL_dloss_o, const float* __restrict__ dL_dloss_p, const float* __restrict__ sigmas,
     const float* __restrict__ ndiff, const float* __restrict__ nori, const float* __restrict__ deltas,
     const int64_t* __restrict__ rays_a, const float* __restrict__ loss_o, const float* __restrict__ loss_p,
     float T_thr, int64_t n_rays, float* __restrict__ dL_dsigmas, float* __restrict__ dL_dndiff,
     float* __restrict__ dL_dnori) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = gtid / G;
-  const int j = (int)(gtid % G);
-  const Seg sg = load_seg(rays_a, row, n_rays);
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
   const int64_t r = sg.ray < 0 ? 0 : sg.ray;
   float gO = 0.f, gX = 0.f, gY = 0.f, gZ = 0.f, O = 0.f, X = 0.f, Y = 0.f, Z = 0.f;
   if (sg.n > 0) {
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(256) refloss_bw_kernel(
                              : 0.f;
     }
   }
+  });
 }
 
 }  // namespace ngp
@@ -170,7 +175,7 @@ NGP_API int ngp_distortion_loss_fw(const float* ws, const float* deltas, const f
                                    float* wts_inclusive_scan, void* stream) {
   if (n_rays <= 0) return 0;
   NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
-    distortion_fw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+    NGP_GROUP_LAUNCH(distortion_fw_kernel, (cudaStream_t)stream,
         ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan);
   });
   NGP_LAUNCH_CHECK("ngp_distortion_loss_fw");
@@ -184,7 +189,7 @@ NGP_API int ngp_distortion_loss_bw(const float* dL_dloss, const float* ws_inclus
                                    float* dL_dws, void* stream) {
   if (n_rays <= 0) return 0;
   NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
-    distortion_bw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+    NGP_GROUP_LAUNCH(distortion_bw_kernel, (cudaStream_t)stream,
         dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts, rays_a, n_rays, dL_dws);
   });
   NGP_LAUNCH_CHECK("ngp_distortion_loss_bw");
@@ -198,7 +203,7 @@ NGP_API int ngp_composite_refloss_fw(const float* sigmas, const float* normals_d
                                      int64_t n_samples, int64_t n_rays, float* loss_o, float* loss_p, void* stream) {
   if (n_rays <= 0) return 0;
   NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
-    refloss_fw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+    NGP_GROUP_LAUNCH(refloss_fw_kernel, (cudaStream_t)stream,
         sigmas, normals_diff, normals_ori, deltas, rays_a, T_threshold, n_rays, loss_o, loss_p);
   });
   NGP_LAUNCH_CHECK("ngp_composite_refloss_fw");
@@ -213,7 +218,7 @@ NGP_API int ngp_composite_refloss_bw(const float* dL_dloss_o, const float* dL_dl
                                      float* dL_dnormals_diff, float* dL_dnormals_ori, void* stream) {
   if (n_rays <= 0) return 0;
   NGP_GROUP_DISPATCH(pick_group(n_samples, n_rays), {
-    refloss_bw_kernel<G><<<(unsigned)ceil_div(n_rays * G, 256), 256, 0, (cudaStream_t)stream>>>(
+    NGP_GROUP_LAUNCH(refloss_bw_kernel, (cudaStream_t)stream,
         dL_dloss_o, dL_dloss_p, sigmas, normals_diff, normals_ori, deltas, rays_a, loss_o, loss_p, T_threshold,
         n_rays, dL_dsigmas, dL_dnormals_diff, dL_dnormals_ori);
   });

@@ -43,6 +43,9 @@ struct MarchParams {
   // the 4^3 block or its 26 neighbour blocks"; NULL = off.  cull_span = 4 cells in world units.
   const uint32_t* __restrict__ coarse;
   float cull_span;
+  // x-major copy of the (single-cascade, 128^3) bitfield: bit (z*128 + y)*128 + x of a 32-bit word array (linearize_bitfield_kernel).
+  // The same bits under a cheaper address: the Morton spread costs 24 of the ~85 instructions of a marching step.  NULL = off.
+  const uint32_t* __restrict__ linear;
 };
 
 struct Ray {
@@ -64,7 +67,7 @@ __device__ __forceinline__ Ray load_ray(const float* __restrict__ rays_o, const 
 // kSimple (cascades == 1 and exp_step_factor == 0, the synthetic-scene case): calc_dt(t) is the constant
 // fmaxf(dt_min, fminf(t*0, dt_max)) = dt_min for every finite t, both mip selectors clamp to 0, and
 // mip_bound = fminf(2^-1, scale) — the same VALUES the general path computes, hoisted out of the loop.
-template <bool kSimple = false>
+template <bool kSimple = false, bool kLinear = false>
 __device__ __forceinline__ bool march_step(const Ray& q, const MarchParams& p, float& t, float& x, float& y,
                                            float& z, float& dt) {
   x = __fmaf_rn(t, q.dx, q.ox); y = __fmaf_rn(t, q.dy, q.oy); z = __fmaf_rn(t, q.dz, q.oz);
@@ -76,8 +79,14 @@ __device__ __forceinline__ bool march_step(const Ray& q, const MarchParams& p, f
   const int nx = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(x, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
   const int ny = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(y, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
   const int nz = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(0.5f, __fmaf_rn(z, mip_bound_inv, 1.0f)), p.grid_f), p.grid_m1));
-  const uint32_t idx = (uint32_t)mip * p.grid3 + morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
-  const bool occ = __ldg(p.bitfield + (idx >> 3)) & (1u << (idx & 7u));
+  bool occ;
+  if (kLinear) {                                 // kSimple, grid 128: mip == 0
+    const uint32_t lin = ((uint32_t)nz * 128u + (uint32_t)ny) * 128u + (uint32_t)nx;
+    occ = (__ldg(p.linear + (lin >> 5)) >> (lin & 31u)) & 1u;
+  } else {
+    const uint32_t idx = (uint32_t)mip * p.grid3 + morton3D((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    occ = __ldg(p.bitfield + (idx >> 3)) & (1u << (idx & 7u));
+  }
   if (occ) return true;
   // distance to the far faces of this cell along the ray
   const float tx = __fmul_rn(__fmaf_rn(__fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), q.sx), p.grid_inv), 2.0f, -1.0f), mip_bound, -x), q.dx_inv);
@@ -193,11 +202,26 @@ __global__ void __launch_bounds__(kMarchBlock) march_cull_kernel(
   }
 }
 
+// Morton-ordered bitfield (the reference's layout, raymarching.cu:35-62) -> x-major words for the single-cascade marcher:
+// thread per 32 cells of one x-row.
+__global__ void __launch_bounds__(256) linearize_bitfield_kernel(const uint8_t* __restrict__ bitfield, uint32_t* __restrict__ linear) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // 128^3 / 32 words
+  const uint32_t x0 = (w & 3u) * 32u, y = (w >> 2) & 127u, z = w >> 9;
+  const uint32_t myz = morton3D(0u, y, z);
+  uint32_t bits = 0;
+#pragma unroll 8
+  for (uint32_t i = 0; i < 32; i++) {
+    const uint32_t idx = morton3D(x0 + i, 0u, 0u) | myz;
+    bits |= ((uint32_t)(__ldg(bitfield + (idx >> 3)) >> (idx & 7u)) & 1u) << i;
+  }
+  linear[w] = bits;
+}
+
 // Pass 1, persistent: every lane owns one ray at a time and pulls the next ray index from a global
 // counter the moment its ray is finished (warp-aggregated atomicAdd), so the 32 lanes of a warp stay busy
 // although ray lengths differ by two orders of magnitude (first ncu capture: 12 of 32 lanes active).
 // One loop trip = one marching step of every lane's current ray.
-template <bool kSimple>
+template <bool kSimple, bool kLinear = false>
 __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
     const float* __restrict__ noise, MarchParams p, int max_samples, int64_t n_rays,
@@ -235,7 +259,7 @@ __global__ void __launch_bounds__(kMarchBlock) march_count_kernel(
     if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
       if (0 <= t && t < t2 && N < max_samples) {
-        if (march_step<kSimple>(q, p, t, x, y, z, dt)) {
+        if (march_step<kSimple, kLinear>(q, p, t, x, y, z, dt)) {
           if (N < row_len) row[N] = make_float2(t, dt);
           t = __fadd_rn(t, dt); N++;
         }
@@ -599,6 +623,7 @@ static MarchParams make_params(const uint8_t* bitfield, int cascades, float scal
   p.mb0 = fminf(0.5f, scale);
   p.mb0_inv = 1.0f / p.mb0;
   p.coarse = nullptr;
+  p.linear = nullptr;
   p.cull_span = 8.0f * p.mb0 / (float)grid_size;      // 4 cells of 2*mip_bound/G
   return p;
 }
@@ -615,10 +640,11 @@ using namespace ngp;
 // Workspace layout for the training marcher (caller-provided device memory):
 //   int32 n_samples[R] | float t_start[R] | int32 block_sums[B] | int64 block_offsets[B] | int64 total |
 //   float2 scratch[R][row]      row = kTrainRow (training) / kScratch (test-time wavefront)
+constexpr int64_t kLinearBytes = 128 * 128 * 128 / 8;
 static int64_t march_ws_bytes(int64_t n_rays, int row) {
   const int64_t B = ceil_div(n_rays, kMarchBlock);
   auto al = [](int64_t x) { return (x + 255) / 256 * 256; };
-  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256 + al(n_rays * row * 8) + 4096;   // + the 32^3-bit coarse lattice
+  return al(n_rays * 4) + al(n_rays * 4) + al(B * 4) + al(B * 8) + 256 + al(n_rays * row * 8) + 4096 + kLinearBytes;   // + the 32^3-bit coarse lattice, the x-major bitfield
 }
 NGP_API int64_t ngp_raymarching_train_workspace_bytes(int64_t n_rays) { return march_ws_bytes(n_rays, kTrainRow); }
 // workspace of ngp_render_advance / ngp_render_emit for n_alive_in slots
@@ -627,6 +653,10 @@ NGP_API int64_t ngp_render_workspace_bytes(int64_t n_slots) { return march_ws_by
 struct MarchWs { int32_t* n_samples; float* t_start; int32_t* block_sums; int64_t* block_offsets; int64_t* total; float2* scratch; };
 static uint32_t* coarse_of(const MarchWs& w, int64_t n_rays, int row) {
   return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(w.scratch) + (n_rays * row * 8 + 255) / 256 * 256);
+}
+// the x-major copy of the bitfield, behind the coarse lattice
+static uint32_t* linear_of(const MarchWs& w, int64_t n_rays, int row) {
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(coarse_of(w, n_rays, row)) + 4096);
 }
 static MarchWs carve(void* ws, int64_t n_rays) {
   const int64_t B = ceil_div(n_rays, kMarchBlock);
@@ -665,15 +695,23 @@ NGP_API int ngp_raymarching_train_count(const float* rays_o, const float* rays_d
   const int row_len = max_samples < kTrainRow ? (max_samples < 1 ? 1 : max_samples) : kTrainRow;
   const bool cull_on = cull_enabled();
   if (simple && cull_on && grid_size == 128 && n_rays >= 2048 && ((uintptr_t)density_bitfield & 7u) == 0) {
-    MarchParams pc = p;
+    static const bool linear_on = !(getenv("NGP_MARCH_LINEAR") && atoi(getenv("NGP_MARCH_LINEAR")) == 0);   // 0: Morton lookups (A/B only)
+    MarchParams pc = p, pm = p;
     uint32_t* coarse = coarse_of(w, n_rays, kTrainRow);
     int32_t* live = reinterpret_cast<int32_t*>(w.t_start);      // n_rays ints: the (otherwise unused) t_start area
     coarse_occupancy_kernel<<<128, 256, 0, s>>>(density_bitfield, coarse);
     NGP_LAUNCH_CHECK("ngp_raymarching_train_count/coarse");
     pc.coarse = coarse;
+    if (linear_on) {
+      uint32_t* lin = linear_of(w, n_rays, kTrainRow);
+      linearize_bitfield_kernel<<<128 * 128 * 128 / 32 / 256, 256, 0, s>>>(density_bitfield, lin);
+      NGP_LAUNCH_CHECK("ngp_raymarching_train_count/linearize");
+      pm.linear = lin;
+    }
     march_cull_kernel<<<B, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, pc, n_rays, w.n_samples, live, n_live);
     NGP_LAUNCH_CHECK("ngp_raymarching_train_count/cull");
-    march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray, live, n_live);
+    if (linear_on) march_count_kernel<true, true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, pm, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray, live, n_live);
+    else march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, pm, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray, live, n_live);
   } else if (simple) march_count_kernel<true><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray);
   else march_count_kernel<false><<<G, kMarchBlock, 0, s>>>(rays_o, rays_d, hits_t, noise, p, max_samples, n_rays, w.n_samples, w.scratch, row_len, next_ray);
   NGP_LAUNCH_CHECK("ngp_raymarching_train_count/count");

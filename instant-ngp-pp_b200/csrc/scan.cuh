@@ -58,6 +58,49 @@ __device__ __forceinline__ Seg load_seg(const int64_t* __restrict__ rays_a, int6
   return s;
 }
 
+// Which rays a thread works on.
+//   kTiled == false: group g of the grid (G consecutive threads) owns rays_a row g — one launch slot per ray.
+//   kTiled == true (G == 32 only): a warp owns kRayTile consecutive rows.  Lanes < kRayTile fetch the rows' descriptors in one
+//   coalesced request and the warp then walks them one after the other.  Most rays of a batch are empty (Lego-shaped scene: 77 %),
+//   and a warp launched for an empty ray is pure launch overhead: with one warp per ray the kernels below were bound by the rate
+//   at which CTAs start, not by memory or issue slots (tools/composite_sweep.py, profiles/r02h_composite_sweep.txt).
+// body(sg, j) is called once per row with j = the thread's lane in the group; it must write the row's outputs also for n == 0.
+constexpr int kRayTile = 8;
+template <int G, bool kTiled, typename Body>
+__device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a, int64_t n_rays, Body body) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (G == 32 && kTiled) {
+    const int lane = (int)(threadIdx.x & 31u);
+    const int64_t row0 = (gtid >> 5) * kRayTile;
+    const Seg mine = load_seg(rays_a, lane < kRayTile ? row0 + lane : n_rays, n_rays);
+#pragma unroll 1
+    for (int k = 0; k < kRayTile; k++) {
+      Seg sg;
+      sg.ray = __shfl_sync(kFull, mine.ray, k); sg.start = __shfl_sync(kFull, mine.start, k); sg.n = __shfl_sync(kFull, mine.n, k);
+      if (sg.ray < 0) break;                       // past the last row (warp-uniform)
+      body(sg, lane);
+    }
+  } else {
+    body(load_seg(rays_a, gtid / G, n_rays), (int)(gtid % G));
+  }
+}
+// threads a launch needs for n_rays rows
+__host__ __forceinline__ int64_t group_threads(int64_t n_rays, int G, bool tiled) {
+  return (G == 32 && tiled) ? ceil_div(n_rays, kRayTile) * 32 : n_rays * G;
+}
+
+bool group_tiled();   // composite.cu
+int group_block();    // composite.cu
+// inside NGP_GROUP_DISPATCH (G is the compile-time group size): kernel<G, tiled><<<grid, block, 0, stream>>>(args)
+#define NGP_GROUP_LAUNCH(KERNEL_, STREAM_, ...)                                                            \
+  do {                                                                                                     \
+    const int bs_ = ngp::group_block();                                                                    \
+    const bool tiled_ = G == 32 && ngp::group_tiled();                                                     \
+    const unsigned blocks_ = (unsigned)ceil_div(ngp::group_threads(n_rays, G, tiled_), bs_);               \
+    if (tiled_) KERNEL_<G, (G == 32)><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__);                          \
+    else KERNEL_<G, false><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__);                                     \
+  } while (0)
+
 // Transmittance bookkeeping for one chunk of G samples of one ray.
 //   in : a (alpha of my sample, 0 for lanes past the end), valid, T_carry (T before the chunk), done
 //   out: T_before / T_after for my sample, active (sample contributes: before or AT the

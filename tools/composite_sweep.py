@@ -29,8 +29,12 @@ def tm(fn, it=10):
     return s.elapsed_time(e) / it
 from ngp_b200.custom_functions import VolumeRendererLite
 from ngp_b200.losses import DistortionLoss
-for G in (8, 16, 32):
+# second axis (round 2): threads per CTA of the group kernels (NGP_COMPOSITE_BLOCK; CTA slots come free when the longest ray is done)
+# third axis: NGP_COMPOSITE_TILED (G = 32: a warp walks 8 consecutive rays instead of one launch slot per ray)
+for G, B, T in ((16, 256, 0), (32, 256, 0), (32, 64, 0), (32, 64, 1), (32, 128, 1), (32, 256, 1)) if len(sys.argv) < 2 else ((32, 64, 0), (32, 64, 1), (32, 128, 1)):
     os.environ["NGP_COMPOSITE_G"] = str(G)
+    os.environ["NGP_COMPOSITE_BLOCK"] = str(B)
+    os.environ["NGP_COMPOSITE_TILED"] = str(T)
     s1 = sig.clone().requires_grad_(True); c1 = rgb.clone().requires_grad_(True)
     def fw():
         return VolumeRendererLite.apply(s1, c1, deltas, ts, ra, 1e-4)
@@ -40,4 +44,6 @@ for G in (8, 16, 32):
     t_bw = tm(lambda: torch.autograd.grad(loss, (s1, c1), retain_graph=True))
     ws = out[4].detach().clone().requires_grad_(True)
     t_dfw = tm(lambda: DistortionLoss.apply(ws, deltas, ts, ra))
-    print(f"G={G}: composite fw {t_fw:.3f} ms  bw (incl. autograd glue) {t_bw:.3f} ms  distortion fw {t_dfw:.3f} ms", flush=True)
+    dl = DistortionLoss.apply(ws, deltas, ts, ra).sum()
+    t_dbw = tm(lambda: torch.autograd.grad(dl, (ws,), retain_graph=True))
+    print(f"G={G} block={B} tiled={T}: composite fw {t_fw:.3f} ms  bw (incl. autograd glue) {t_bw:.3f} ms  distortion fw {t_dfw:.3f} ms  bw {t_dbw:.3f} ms", flush=True)
