@@ -28,18 +28,20 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     const int64_t* __restrict__ rays_a, float T_thr, int classes, int c0, int nc, bool do_main, int64_t n_rays,
     int64_t* __restrict__ total_samples, float* __restrict__ opacity, float* __restrict__ depth,
     float* __restrict__ rgb, float* __restrict__ normal_pred, float* __restrict__ sem, float* __restrict__ ws) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
-  if (G == 32 && sg.n <= 0) {          // the warp's one ray is empty (most rays of a batch are): zeros, no reductions
-    if (j == 0 && sg.ray >= 0) {
-      const int64_t r = sg.ray;
-      if (do_main) {
-        total_samples[r] = 0;
-        opacity[r] = 0.f; depth[r] = 0.f;
-        rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
-        if (normal_pred) { normal_pred[3 * r] = 0.f; normal_pred[3 * r + 1] = 0.f; normal_pred[3 * r + 2] = 0.f; }
-      }
-      for (int i = 0; i < nc; i++) sem[r * classes + c0 + i] = 0.f;
+  // an empty ray (most rays of a batch are): zeros, no reductions
+  auto write_empty = [&](const Seg& sg) {
+    const int64_t r = sg.ray;
+    if (do_main) {
+      total_samples[r] = 0;
+      opacity[r] = 0.f; depth[r] = 0.f;
+      rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
+      if (normal_pred) { normal_pred[3 * r] = 0.f; normal_pred[3 * r + 1] = 0.f; normal_pred[3 * r + 2] = 0.f; }
     }
+    for (int i = 0; i < nc; i++) sem[r * classes + c0 + i] = 0.f;
+  };
+  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+  if (G == 32 && sg.n <= 0) {          // one warp per ray (kTiled == false): the warp's ray is empty
+    if (j == 0 && sg.ray >= 0) write_empty(sg);
     return;
   }
 
@@ -86,9 +88,11 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
           aR = fmaf(w, c_r[m], aR); aG = fmaf(w, c_g[m], aG); aB = fmaf(w, c_b[m], aB);
           if (normals) { aNx = fmaf(w, n_x, aNx); aNy = fmaf(w, n_y, aNy); aNz = fmaf(w, n_z, aNz); }
         }
-        const float* sp = sems + s * classes + c0;
+        if (nc > 0) {
+          const float* sp = sems + s * classes + c0;
 #pragma unroll
-        for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = fmaf(w, __ldg(sp + i), aS[i]);
+          for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = fmaf(w, __ldg(sp + i), aS[i]);
+        }
       }
     }
   }
@@ -99,8 +103,10 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     aR = group_sum<G>(aR); aG = group_sum<G>(aG); aB = group_sum<G>(aB);
     aNx = group_sum<G>(aNx); aNy = group_sum<G>(aNy); aNz = group_sum<G>(aNz);
   }
+  if (nc > 0) {
 #pragma unroll
-  for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = group_sum<G>(aS[i]);
+    for (int i = 0; i < kCP; i++) if (i < nc) aS[i] = group_sum<G>(aS[i]);
+  }
 
   if (j == 0 && sg.ray >= 0) {
     const int64_t r = sg.ray;
@@ -110,10 +116,12 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
       rgb[3 * r] = aR; rgb[3 * r + 1] = aG; rgb[3 * r + 2] = aB;
       if (normal_pred) { normal_pred[3 * r] = aNx; normal_pred[3 * r + 1] = aNy; normal_pred[3 * r + 2] = aNz; }
     }
+    if (nc > 0) {
 #pragma unroll
-    for (int i = 0; i < kCP; i++) if (i < nc) sem[r * classes + c0 + i] = aS[i];
+      for (int i = 0; i < kCP; i++) if (i < nc) sem[r * classes + c0 + i] = aS[i];
+    }
   }
-  });
+  }, write_empty);
 }
 
 template <int G, bool kTiled>

@@ -5,6 +5,7 @@
 // every loop that contains them runs a warp-uniform trip count (see `warp_any`).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace ngp {
 
@@ -65,19 +66,25 @@ __device__ __forceinline__ Seg load_seg(const int64_t* __restrict__ rays_a, int6
 //   and a warp launched for an empty ray is pure launch overhead: with one warp per ray the kernels below were bound by the rate
 //   at which CTAs start, not by memory or issue slots (tools/composite_sweep.py, profiles/r02h_composite_sweep.txt).
 // body(sg, j) is called once per row with j = the thread's lane in the group; it must write the row's outputs also for n == 0.
+// empty(sg) (optional, kTiled only): called by ONE lane per empty row (n == 0) — all empty rows of the tile in one pass, side by
+// side — and body() is then not called for them; without it body() sees every row.
 constexpr int kRayTile = 8;
-template <int G, bool kTiled, typename Body>
-__device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a, int64_t n_rays, Body body) {
+struct NoEmptyHandler { __device__ __forceinline__ void operator()(const Seg&) const {} };
+template <int G, bool kTiled, typename Body, typename Empty = NoEmptyHandler>
+__device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a, int64_t n_rays, Body body, Empty empty = Empty()) {
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (G == 32 && kTiled) {
+    constexpr bool kHasEmpty = !std::is_same<Empty, NoEmptyHandler>::value;
     const int lane = (int)(threadIdx.x & 31u);
     const int64_t row0 = (gtid >> 5) * kRayTile;
     const Seg mine = load_seg(rays_a, lane < kRayTile ? row0 + lane : n_rays, n_rays);
+    if (kHasEmpty && mine.ray >= 0 && mine.n <= 0) empty(mine);
 #pragma unroll 1
     for (int k = 0; k < kRayTile; k++) {
       Seg sg;
       sg.ray = __shfl_sync(kFull, mine.ray, k); sg.start = __shfl_sync(kFull, mine.start, k); sg.n = __shfl_sync(kFull, mine.n, k);
       if (sg.ray < 0) break;                       // past the last row (warp-uniform)
+      if (kHasEmpty && sg.n <= 0) continue;
       body(sg, lane);
     }
   } else {

@@ -45,7 +45,13 @@ with torch.no_grad():
     for _ in range(2):
         tcnn.mlp_backward(segs, model.rgb_net.params.detach(), m2, drgb, [False, True], saved_out=rgb)
     sigmas = torch.rand(S, device=dev) * 20
+    z0 = torch.zeros(S, 0, device=dev)
     for _ in range(2):
-        out = vren.composite_train_fw(sigmas, rgb, rgb, torch.zeros(S, 0, device=dev), deltas, ts, ra, 1e-4, 0)
+        out = vren.composite_train_fw(sigmas, rgb, None, z0, deltas, ts, ra, 1e-4, 0)
+    tot, opacity, depth, rgb_r, _, sem_r, ws = out
+    g1 = torch.randn(R, device=dev); g3 = torch.randn(R, 3, device=dev); gws = torch.randn(S, device=dev)
+    for _ in range(2):
+        vren.composite_train_bw(g1, g1, g3, None, torch.zeros(R, 0, device=dev), gws, sigmas, rgb, None, ws, deltas, ts, ra,
+                                opacity, depth, rgb_r, None, 1e-4, 0)
 torch.cuda.synchronize()
 print("rays", R, "samples", S)
