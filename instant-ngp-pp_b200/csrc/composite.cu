@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     const float* __restrict__ sems, const float* __restrict__ deltas, const float* __restrict__ ts,
     const int64_t* __restrict__ rays_a, float T_thr, int classes, int c0, int nc, bool do_main, int64_t n_rays,
     int64_t* __restrict__ total_samples, float* __restrict__ opacity, float* __restrict__ depth,
-    float* __restrict__ rgb, float* __restrict__ normal_pred, float* __restrict__ sem, float* __restrict__ ws) {
+    float* __restrict__ rgb, float* __restrict__ normal_pred, float* __restrict__ sem, float* __restrict__ ws, int ray_tile) {
   // an empty ray (most rays of a batch are): zeros, no reductions
   auto write_empty = [&](const Seg& sg) {
     const int64_t r = sg.ray;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     }
     for (int i = 0; i < nc; i++) sem[r * classes + c0 + i] = 0.f;
   };
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   if (G == 32 && sg.n <= 0) {          // one warp per ray (kTiled == false): the warp's ray is empty
     if (j == 0 && sg.ray >= 0) write_empty(sg);
     return;
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
 template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) composite_alpha_fw_kernel(
     const float* __restrict__ sigmas, const float* __restrict__ deltas, const int64_t* __restrict__ rays_a,
-    float T_thr, int64_t n_rays, float* __restrict__ alphas, float* __restrict__ ws) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    float T_thr, int64_t n_rays, float* __restrict__ alphas, float* __restrict__ ws, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   TState st;
   for (int base = 0; warp_any(base < sg.n); base += G) {
     const bool valid = base + j < sg.n;
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
     const float* __restrict__ deltas, const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
     const float* __restrict__ opacity, const float* __restrict__ depth, const float* __restrict__ rgb,
     float T_thr, int classes, int64_t n_rays, float* __restrict__ dL_dsigmas, float* __restrict__ dL_drgbs,
-    float* __restrict__ dL_dnormals, float* __restrict__ dL_dsems) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    float* __restrict__ dL_dnormals, float* __restrict__ dL_dsems, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   if (G == 32 && sg.n <= 0) return;          // nothing to write for an empty ray
   const int64_t r = sg.ray < 0 ? 0 : sg.ray;
 
@@ -313,15 +313,20 @@ int pick_group(int64_t n_samples, int64_t n_rays) {
 }
 
 // Launch shape of the group kernels (compositors, distortion / Ref-NeRF losses).  With G == 32 a warp walks kRayTile rays
-// (scan.cuh for_each_ray); NGP_COMPOSITE_TILED=0 goes back to one warp per ray, NGP_COMPOSITE_BLOCK (32..256) sets the CTA size
+// (scan.cuh for_each_ray); NGP_COMPOSITE_TILED=0 goes back to one launch slot per ray (1..8: rays per warp), NGP_COMPOSITE_BLOCK (32..256) sets the CTA size
 // (tuning only; with one warp per ray a CTA's warp slots come free only when its longest ray is done, so small CTAs won there).
-bool group_tiled() {
-  if (const char* e = getenv("NGP_COMPOSITE_TILED")) return atoi(e) != 0;
-  return true;
+int group_tile(int64_t n_samples, int64_t n_rays) {
+  if (const char* e = getenv("NGP_COMPOSITE_TILED")) { const int t = atoi(e); return t < 0 ? 0 : (t > kRayTile ? kRayTile : t); }   // 0 = off, 1..8 = rays per warp
+  // ~256 samples per warp: 8 rays where most are empty (Lego-shaped batch: 34 per ray over all rays), one ray per warp where every
+  // ray is long (street-shaped batch: 430 per ray — walking 8 such rays one after the other left the GPU with an eighth of the
+  // warps it needs: 89 -> 142 ms per step, measured)
+  const double avg = n_rays > 0 ? (double)n_samples / (double)n_rays : 0.0;
+  const int t = avg > 0.0 ? (int)(256.0 / avg + 0.5) : kRayTile;
+  return t < 1 ? 1 : (t > kRayTile ? kRayTile : t);
 }
-int group_block() {
+int group_block(bool tiled) {
   if (const char* e = getenv("NGP_COMPOSITE_BLOCK")) { const int b = atoi(e); if (b == 32 || b == 64 || b == 128 || b == 256) return b; }
-  return group_tiled() ? 128 : 64;
+  return tiled ? 128 : 64;
 }
 
 }  // namespace ngp

@@ -17,8 +17,8 @@ template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) distortion_fw_kernel(
     const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
     const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ loss, float* __restrict__ ws_incl,
-    float* __restrict__ wts_incl) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    float* __restrict__ wts_incl, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   float cw = 0.f, cwt = 0.f, acc = 0.f;
   constexpr int kDepth = 4;                       // chunks whose inputs are in flight together (see composite_train_fw_kernel)
   for (int base = 0; warp_any(base < sg.n); base += kDepth * G) {
@@ -59,8 +59,8 @@ template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) distortion_bw_kernel(
     const float* __restrict__ dL_dloss, const float* __restrict__ ws_incl, const float* __restrict__ wts_incl,
     const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
-    const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ dL_dws) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    const int64_t* __restrict__ rays_a, int64_t n_rays, float* __restrict__ dL_dws, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   if (sg.n <= 0) return;
   const int64_t end = sg.start + sg.n - 1;
   const float ws_sum = __ldg(ws_incl + end), wts_sum = __ldg(wts_incl + end);
@@ -83,8 +83,8 @@ template <int G, bool kTiled>
 __global__ void __launch_bounds__(256) refloss_fw_kernel(
     const float* __restrict__ sigmas, const float* __restrict__ ndiff, const float* __restrict__ nori,
     const float* __restrict__ deltas, const int64_t* __restrict__ rays_a, float T_thr, int64_t n_rays,
-    float* __restrict__ loss_o, float* __restrict__ loss_p) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    float* __restrict__ loss_o, float* __restrict__ loss_p, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   float ax = 0.f, ay = 0.f, az = 0.f, ao = 0.f;
   TState st;
   for (int base = 0; warp_any(base < sg.n); base += G) {
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(256) refloss_bw_kernel(
     const float* __restrict__ ndiff, const float* __restrict__ nori, const float* __restrict__ deltas,
     const int64_t* __restrict__ rays_a, const float* __restrict__ loss_o, const float* __restrict__ loss_p,
     float T_thr, int64_t n_rays, float* __restrict__ dL_dsigmas, float* __restrict__ dL_dndiff,
-    float* __restrict__ dL_dnori) {
-  for_each_ray<G, kTiled>(rays_a, n_rays, [&](const Seg& sg, const int j) {
+    float* __restrict__ dL_dnori, int ray_tile) {
+  for_each_ray<G, kTiled>(rays_a, n_rays, ray_tile, [&](const Seg& sg, const int j) {
   const int64_t r = sg.ray < 0 ? 0 : sg.ray;
   float gO = 0.f, gX = 0.f, gY = 0.f, gZ = 0.f, O = 0.f, X = 0.f, Y = 0.f, Z = 0.f;
   if (sg.n > 0) {

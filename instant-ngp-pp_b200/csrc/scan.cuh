@@ -61,8 +61,9 @@ __device__ __forceinline__ Seg load_seg(const int64_t* __restrict__ rays_a, int6
 
 // Which rays a thread works on.
 //   kTiled == false: group g of the grid (G consecutive threads) owns rays_a row g — one launch slot per ray.
-//   kTiled == true (G == 32 only): a warp owns kRayTile consecutive rows.  Lanes < kRayTile fetch the rows' descriptors in one
-//   coalesced request and the warp then walks them one after the other.  Most rays of a batch are empty (Lego-shaped scene: 77 %),
+//   kTiled == true (G == 32 only): a warp owns `tile` (1..kRayTile, chosen by the host from the mean samples per ray so that a
+//   warp gets ~256 samples: group_tile) consecutive rows.  Lanes < tile fetch the rows' descriptors in one coalesced request and
+//   the warp then walks them one after the other.  Most rays of a batch are empty (Lego-shaped scene: 77 %),
 //   and a warp launched for an empty ray is pure launch overhead: with one warp per ray the kernels below were bound by the rate
 //   at which CTAs start, not by memory or issue slots (tools/composite_sweep.py, profiles/r02h_composite_sweep.txt).
 // body(sg, j) is called once per row with j = the thread's lane in the group; it must write the row's outputs also for n == 0.
@@ -71,16 +72,16 @@ __device__ __forceinline__ Seg load_seg(const int64_t* __restrict__ rays_a, int6
 constexpr int kRayTile = 8;
 struct NoEmptyHandler { __device__ __forceinline__ void operator()(const Seg&) const {} };
 template <int G, bool kTiled, typename Body, typename Empty = NoEmptyHandler>
-__device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a, int64_t n_rays, Body body, Empty empty = Empty()) {
+__device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a, int64_t n_rays, int tile, Body body, Empty empty = Empty()) {
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (G == 32 && kTiled) {
     constexpr bool kHasEmpty = !std::is_same<Empty, NoEmptyHandler>::value;
     const int lane = (int)(threadIdx.x & 31u);
-    const int64_t row0 = (gtid >> 5) * kRayTile;
-    const Seg mine = load_seg(rays_a, lane < kRayTile ? row0 + lane : n_rays, n_rays);
+    const int64_t row0 = (gtid >> 5) * tile;
+    const Seg mine = load_seg(rays_a, lane < tile ? row0 + lane : n_rays, n_rays);
     if (kHasEmpty && mine.ray >= 0 && mine.n <= 0) empty(mine);
 #pragma unroll 1
-    for (int k = 0; k < kRayTile; k++) {
+    for (int k = 0; k < tile; k++) {
       Seg sg;
       sg.ray = __shfl_sync(kFull, mine.ray, k); sg.start = __shfl_sync(kFull, mine.start, k); sg.n = __shfl_sync(kFull, mine.n, k);
       if (sg.ray < 0) break;                       // past the last row (warp-uniform)
@@ -92,20 +93,20 @@ __device__ __forceinline__ void for_each_ray(const int64_t* __restrict__ rays_a,
   }
 }
 // threads a launch needs for n_rays rows
-__host__ __forceinline__ int64_t group_threads(int64_t n_rays, int G, bool tiled) {
-  return (G == 32 && tiled) ? ceil_div(n_rays, kRayTile) * 32 : n_rays * G;
+__host__ __forceinline__ int64_t group_threads(int64_t n_rays, int G, int tile) {
+  return (G == 32 && tile > 0) ? ceil_div(n_rays, tile) * 32 : n_rays * G;
 }
 
-bool group_tiled();   // composite.cu
-int group_block();    // composite.cu
+int group_tile(int64_t n_samples, int64_t n_rays);   // composite.cu: rays per warp at G == 32, 0 = one launch slot per ray
+int group_block(bool tiled);    // composite.cu
 // inside NGP_GROUP_DISPATCH (G is the compile-time group size): kernel<G, tiled><<<grid, block, 0, stream>>>(args)
 #define NGP_GROUP_LAUNCH(KERNEL_, STREAM_, ...)                                                            \
   do {                                                                                                     \
-    const int bs_ = ngp::group_block();                                                                    \
-    const bool tiled_ = G == 32 && ngp::group_tiled();                                                     \
-    const unsigned blocks_ = (unsigned)ceil_div(ngp::group_threads(n_rays, G, tiled_), bs_);               \
-    if (tiled_) KERNEL_<G, (G == 32)><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__);                          \
-    else KERNEL_<G, false><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__);                                     \
+    const int tile_ = G == 32 ? ngp::group_tile(n_samples, n_rays) : 0;                                    \
+    const int bs_ = ngp::group_block(tile_ > 0);                                                           \
+    const unsigned blocks_ = (unsigned)ceil_div(ngp::group_threads(n_rays, G, tile_), bs_);                \
+    if (tile_ > 0) KERNEL_<G, (G == 32)><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__, tile_);                \
+    else KERNEL_<G, false><<<blocks_, bs_, 0, STREAM_>>>(__VA_ARGS__, 0);                                  \
   } while (0)
 
 // Transmittance bookkeeping for one chunk of G samples of one ray.
