@@ -141,21 +141,27 @@ def run_reference_gpu(scene_kind="lego", field="ngp_pl", rays=1 << 18, steps_tot
             tr.train_step(*pool[i % 8])
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(timed_last + 1)]     # per-step times: the median is reported beside the mean
         t0 = time.perf_counter()
         s.record()
         samples = 0
+        marks[0].record()
         for i in range(n_un, steps_total):
             _, res = tr.train_step(*pool[i % 8])
             samples += int(res["total_samples"])
+            marks[i - n_un + 1].record()
         e.record(); torch.cuda.synchronize()
         sec = s.elapsed_time(e) * 1e-3
         wall = time.perf_counter() - t0
+        per_step = sorted(marks[k].elapsed_time(marks[k + 1]) for k in range(timed_last))
+        median_ms = per_step[timed_last // 2] if timed_last % 2 else 0.5 * (per_step[timed_last // 2 - 1] + per_step[timed_last // 2])
         with torch.no_grad():          # held-out rays: the same set bench.py evaluates its own arm on (seed 4321)
             ro, rd = scene.sample_rays(eval_rays, poses, torch.Generator(device=dev).manual_seed(4321))
             gt, *_ = scene.shade(ro, rd)
             out = glue.rendering.render(model, ro, rd, **rkw)
             psnr = float(glue.metrics.psnr(out["rgb"], gt))
         return {"value": rays * timed_last / sec, "unit": "rays/s", "ms_per_step": sec / timed_last * 1e3, "wall_ms_per_step": wall / timed_last * 1e3,
+                "ms_per_step_median": median_ms, "ms_per_step_max": per_step[-1],
                 "rays_per_step": rays, "steps_trained": steps_total, "steps_timed": timed_last, "psnr_after_steps": psnr,
                 "samples_per_ray": samples / timed_last / rays, "field": field, "vren": vren, "tinycudann": tcnn, "tf32_mlp": bool(tf32),
                 "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,

@@ -540,7 +540,7 @@ def gpu_arm(args):
             # the same reference glue with BOTH extension imports bound to libngp_b200.so (zero-edit drop-in)
             drop = ref_train.run_reference_gpu(scene_kind="lego", field="ngp_pl", rays=R, steps_total=args.ref_steps, timed_last=10,
                                                lr=wl["lr"], eps=1e-15, views=wl["views"], log2_T=wl["log2_T"], vren="ours", tcnn="ours")
-            ref_gpu["reference_glue_on_libngp_b200"] = {k: drop[k] for k in ("value", "unit", "ms_per_step", "psnr_after_steps", "samples_per_ray")}
+            ref_gpu["reference_glue_on_libngp_b200"] = {k: drop[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_median", "ms_per_step_max", "psnr_after_steps", "samples_per_ray")}
         except Exception as ex:            # baseline/_ref or vren_ref.so not present on this box
             ref_gpu = {"unavailable": repr(ex)[:300]} if ref_gpu is None else ref_gpu
     others = None
