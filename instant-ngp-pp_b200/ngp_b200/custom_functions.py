@@ -186,7 +186,8 @@ class NegNormalize(torch.autograd.Function):
         from ._lib import lib, ptr, check, stream
         y, inv = ctx.saved_tensors
         gx = torch.empty_like(y)
-        check(lib.ngp_neg_normalize_bw(ptr(gy.contiguous().float()), ptr(y), ptr(inv), *ctx.sc, y.shape[0], ptr(gx), stream()), "neg_normalize_bw")
+        gy = gy.contiguous().float()
+        check(lib.ngp_neg_normalize_bw(ptr(gy), ptr(y), ptr(inv), *ctx.sc, y.shape[0], ptr(gx), stream()), "neg_normalize_bw")
         return gx, None, None
 
 
@@ -215,8 +216,10 @@ class RefLossPrep(torch.autograd.Function):
         need_r, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_raw = torch.empty_like(nr) if need_r else None
         g_pred = torch.empty_like(nr) if need_p else None
-        check(lib.ngp_refloss_prep_bw(ptr(nr), ptr(npd), ptr(d), ptr(g_diff.contiguous()) if g_diff is not None else None,
-                                      ptr(g_ori.contiguous()) if g_ori is not None else None, nr.shape[0], ptr(g_raw), ptr(g_pred), stream()),
+        # bound to locals: two temporary .contiguous() copies inside one call expression can end up in the same freed block
+        g_diff = g_diff.contiguous() if g_diff is not None else None
+        g_ori = g_ori.contiguous() if g_ori is not None else None
+        check(lib.ngp_refloss_prep_bw(ptr(nr), ptr(npd), ptr(d), ptr(g_diff), ptr(g_ori), nr.shape[0], ptr(g_raw), ptr(g_pred), stream()),
               "refloss_prep_bw")
         return g_raw, g_pred, None
 
